@@ -1,0 +1,211 @@
+"""ctypes binding of libcrf.so (the C ABI in include/crf.h).
+
+This is the only way the Python host code reaches the GPU.  There is no CPU fallback: if the
+shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrf.so")
+
+SCAN_NO_PRIMITIVITY = 1
+
+CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_CAPACITY = range(6)
+
+#: every symbol include/crf.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
+    "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
+    "crf_scan_stats", "crf_run_end",
+]
+
+
+class CrfError(RuntimeError):
+    """A libcrf call failed (CUDA error, out of memory, capacity)."""
+
+
+class ScanParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "min_motif_size", "max_motif_size", "min_repeats", "min_span",
+        "words_per_thread", "tile_out_cap", "walk_limit_words", "result_cap", "flags")]
+
+
+class SeqInfo(ctypes.Structure):
+    _fields_ = [("n_records", ctypes.c_uint64), ("total_bases", ctypes.c_uint64), ("layout_bases", ctypes.c_uint64),
+                ("packed_bytes", ctypes.c_uint64), ("n_exotic", ctypes.c_uint64), ("max_motif_cap", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32), ("load_ms", ctypes.c_double)]
+
+
+class ScanStats(ctypes.Structure):
+    _fields_ = [("scan_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("n_results", ctypes.c_uint64),
+                ("n_tiles", ctypes.c_uint64), ("n_spilled", ctypes.c_uint64), ("n_long", ctypes.c_uint64),
+                ("n_candidates", ctypes.c_uint64), ("word_k_pairs", ctypes.c_uint64), ("reruns", ctypes.c_uint32),
+                ("launches", ctypes.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load libcrf.so once; raise (never fall back) if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CrfError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           f"(nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, u32, u64, i = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+        P = ctypes.POINTER
+        L.crf_last_error.restype = ctypes.c_char_p
+        L.crf_last_error.argtypes = []
+        L.crf_abi_version.restype = i
+        L.crf_ctx_create.argtypes = [i, P(vp)]
+        L.crf_ctx_destroy.argtypes = [vp]
+        L.crf_ctx_set_stream.argtypes = [vp, vp]
+        L.crf_ctx_synchronize.argtypes = [vp]
+        L.crf_seq_load_ascii.argtypes = [vp, vp, vp, u32, u32, i, P(vp)]
+        L.crf_seq_destroy.argtypes = [vp]
+        L.crf_seq_info.argtypes = [vp, P(SeqInfo)]
+        L.crf_scan.argtypes = [vp, P(ScanParams), P(u64)]
+        L.crf_fetch.argtypes = [vp, vp, vp, vp, vp, u64, i]
+        L.crf_scan_stats.argtypes = [vp, P(ScanStats)]
+        L.crf_run_end.argtypes = [vp, u32, u32, u32, P(u32)]
+        for name in EXPORTS:
+            if name != "crf_last_error":
+                getattr(L, name).restype = i
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc == CRF_OK:
+        return
+    msg = lib().crf_last_error().decode("utf-8", "replace")
+    if rc == CRF_ERR_ARG:
+        raise ValueError(msg)
+    if rc == CRF_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == CRF_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise CrfError(f"libcrf error {rc}: {msg}")
+
+
+class Context:
+    """One CUDA device (crf_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        self.device = device
+        _check(lib().crf_ctx_create(device, ctypes.byref(self._h)))
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().crf_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        _check(lib().crf_ctx_synchronize(self._h))
+
+    def load(self, bases, offsets=None, max_motif_cap=50, on_device=False):
+        """bases: bytes / uint8 ndarray (host) or an int device pointer (on_device=True).
+        offsets: uint64 array of n_records+1 record boundaries (default: one record)."""
+        return Sequence(self, bases, offsets, max_motif_cap, on_device)
+
+    def close(self):
+        if self._h:
+            lib().crf_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Sequence:
+    """Records resident in HBM as packed planes (crf_seq)."""
+
+    def __init__(self, ctx, bases, offsets, max_motif_cap, on_device):
+        self.ctx = ctx
+        self._h = ctypes.c_void_p()
+        keep = None
+        if on_device:
+            ptr = int(bases)
+            if offsets is None:
+                raise ValueError("offsets are required with a device pointer")
+        else:
+            if isinstance(bases, np.ndarray):
+                if bases.dtype != np.uint8 or not bases.flags.c_contiguous:
+                    raise ValueError("bases must be a C-contiguous uint8 array")
+                keep = bases
+                ptr = bases.ctypes.data
+                nbytes = bases.size
+            else:
+                keep = bytes(bases) if not isinstance(bases, bytes) else bases
+                ptr = ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p).value or 0
+                nbytes = len(keep)
+            if offsets is None:
+                offsets = np.array([0, nbytes], dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if offsets.ndim != 1 or offsets.size < 2:
+            raise ValueError("offsets must hold n_records + 1 entries")
+        self.offsets = offsets
+        self.n_records = offsets.size - 1
+        _check(lib().crf_seq_load_ascii(ctx._h, ctypes.c_void_p(ptr), ctypes.c_void_p(offsets.ctypes.data),
+                                        self.n_records, int(max_motif_cap), int(bool(on_device)),
+                                        ctypes.byref(self._h)))
+        del keep
+
+    def info(self):
+        out = SeqInfo()
+        _check(lib().crf_seq_info(self._h, ctypes.byref(out)))
+        return out
+
+    def scan(self, min_motif_size, max_motif_size, min_repeats, min_span, **knobs):
+        pr = ScanParams(int(min_motif_size), int(max_motif_size), int(min_repeats), int(min_span),
+                        int(knobs.get("words_per_thread", 0)), int(knobs.get("tile_out_cap", 0)),
+                        int(knobs.get("walk_limit_words", 0)), int(knobs.get("result_cap", 0)),
+                        int(knobs.get("flags", 0)))
+        n = ctypes.c_uint64()
+        _check(lib().crf_scan(self._h, ctypes.byref(pr), ctypes.byref(n)))
+        return n.value
+
+    def fetch(self, n):
+        rec, start, end, k = (np.empty(n, np.uint32) for _ in range(4))
+        _check(lib().crf_fetch(self._h, rec.ctypes.data, start.ctypes.data, end.ctypes.data, k.ctypes.data, n, 0))
+        return rec, start, end, k
+
+    def fetch_device(self, rec_ptr, start_ptr, end_ptr, k_ptr, capacity):
+        _check(lib().crf_fetch(self._h, rec_ptr, start_ptr, end_ptr, k_ptr, capacity, 1))
+
+    def stats(self):
+        out = ScanStats()
+        _check(lib().crf_scan_stats(self._h, ctypes.byref(out)))
+        return out
+
+    def run_end(self, record, pos, k):
+        out = ctypes.c_uint32()
+        _check(lib().crf_run_end(self._h, int(record), int(pos), int(k), ctypes.byref(out)))
+        return out.value
+
+    def close(self):
+        if self._h:
+            lib().crf_seq_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

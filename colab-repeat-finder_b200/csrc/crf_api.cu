@@ -1,0 +1,576 @@
+// crf_api.cu -- host side of libcrf.so: the C ABI declared in include/crf.h.
+//
+// Product path only: there is no CPU implementation of the scan in this library; every entry
+// point either runs the CUDA kernels or fails with a message.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/crf.h"
+#include "crf_aux.cuh"
+#include "crf_scan.cuh"
+
+using namespace crf;
+
+// ---- error plumbing -----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define CU(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            set_err("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return CRF_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+#define CHECK(call)            \
+    do {                       \
+        int rc_ = (call);      \
+        if (rc_) return rc_;   \
+    } while (0)
+
+struct crf_ctx {
+    int device;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+};
+
+struct crf_seq {
+    crf_ctx *ctx = nullptr;
+    uint32_t n_records = 0;
+    uint32_t layout_len = 0, n_words = 0, n_words_alloc = 0, cap = 0;
+    uint32_t *H = nullptr, *L = nullptr, *NM = nullptr, *X = nullptr;
+    uint32_t *d_rec_dev_off = nullptr;
+    std::vector<uint32_t> h_rec_dev_off;
+    std::vector<uint64_t> h_rec_len;
+    uint64_t *ex_key = nullptr;
+    uint32_t n_exotic = 0, ex_cap = 0;
+    // scan scratch
+    KEntry *d_ktab = nullptr;
+    uint32_t ktab_cap = 0;
+    crf_scan_params ktab_for = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t *stage_key = nullptr, *spill_key = nullptr, *fin_key = nullptr;
+    uint16_t *stage_k = nullptr, *spill_k = nullptr, *fin_k = nullptr;
+    uint32_t res_cap = 0;
+    uint32_t *o_rec = nullptr, *o_start = nullptr, *o_end = nullptr, *o_k = nullptr;
+    uint32_t *tile_cnt = nullptr, *tile_base = nullptr, *tile_off = nullptr;
+    uint32_t tiles_cap = 0;
+    unsigned long long *d_counters = nullptr, *h_counters = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    crf_scan_stats_t stats = {};
+    crf_seq_info_t info = {};
+    uint64_t n_results = 0;
+    bool have_results = false;
+};
+
+template <typename T>
+static int dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    CU(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return CRF_OK;
+}
+template <typename T>
+static void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+extern "C" const char *crf_last_error(void) { return g_err; }
+extern "C" int crf_abi_version(void) { return 1; }
+
+// ---- context ------------------------------------------------------------------------------------
+extern "C" int crf_ctx_create(int device, crf_ctx **out) {
+    if (!out) { set_err("crf_ctx_create: null out pointer"); return CRF_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) { set_err("crf_ctx_create: device %d not in [0, %d)", device, n); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_err("crf_ctx_create: libcrf is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        return CRF_ERR_UNSUPPORTED;
+    }
+    crf_ctx *c = new (std::nothrow) crf_ctx;
+    if (!c) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; set_err("cudaStreamCreate failed: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
+    c->stream = c->own_stream;
+    *out = c;
+    return CRF_OK;
+}
+
+extern "C" int crf_ctx_destroy(crf_ctx *c) {
+    if (!c) return CRF_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return CRF_OK;
+}
+
+extern "C" int crf_ctx_set_stream(crf_ctx *c, void *stream) {
+    if (!c) { set_err("null context"); return CRF_ERR_ARG; }
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return CRF_OK;
+}
+
+extern "C" int crf_ctx_synchronize(crf_ctx *c) {
+    if (!c) { set_err("null context"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return CRF_OK;
+}
+
+// ---- fallback sort (global bitonic network) -------------------------------------------------
+static uint32_t next_pow2(uint32_t n) {
+    uint32_t p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// sorts key[0..n) (and val) ascending; the arrays must have room for next_pow2(n) elements
+static int bitonic_sort(cudaStream_t st, uint64_t *key, uint16_t *val, uint32_t n, uint32_t *launches) {
+    if (n < 2) return CRF_OK;
+    const uint32_t np = next_pow2(n);
+    if (np > n) {
+        fill_u64_kernel<<<(np - n + 255) / 256, 256, 0, st>>>(key, ~0ull, n, np);
+        if (val) CU(cudaMemsetAsync(val + n, 0xFF, (size_t)(np - n) * 2, st));
+        if (launches) ++*launches;
+    }
+    for (uint32_t kk = 2; kk <= np; kk <<= 1)
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            bitonic_step_kernel<<<(np + 255) / 256, 256, 0, st>>>(key, val, np, j, kk);
+            if (launches) ++*launches;
+        }
+    CU(cudaGetLastError());
+    return CRF_OK;
+}
+
+// ---- sequence upload ------------------------------------------------------------------------
+static void free_seq(crf_seq *s) {
+    if (!s) return;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    dev_free(s->H); dev_free(s->L); dev_free(s->NM); dev_free(s->X);
+    dev_free(s->d_rec_dev_off); dev_free(s->ex_key); dev_free(s->d_ktab);
+    dev_free(s->stage_key); dev_free(s->spill_key); dev_free(s->fin_key);
+    dev_free(s->stage_k); dev_free(s->spill_k); dev_free(s->fin_k);
+    dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
+    dev_free(s->tile_cnt); dev_free(s->tile_base); dev_free(s->tile_off);
+    dev_free(s->d_counters);
+    if (s->h_counters) cudaFreeHost(s->h_counters);
+    for (auto &e : s->ev)
+        if (e) cudaEventDestroy(e);
+    delete s;
+}
+
+static const uint32_t EX_CAP = 1u << 22;       // exotic symbols kept per load
+static const uint32_t TILE_WORDS_MAX = 4096;   // THREADS * 16
+static const uint32_t MAX_K = 65535;
+
+static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
+                     uint32_t max_motif_cap, int on_device, crf_seq *s) {
+    cudaStream_t st = c->stream;
+    s->ctx = c;
+    s->n_records = n_records;
+    s->cap = max_motif_cap;
+    for (auto &e : s->ev) CU(cudaEventCreate(&e));
+    CU(cudaMallocHost((void **)&s->h_counters, C_COUNT * sizeof(unsigned long long)));
+    CHECK(dev_alloc(&s->d_counters, C_COUNT));
+
+    // layout: record r at dev_off[r], followed by a gap of max_motif_cap masked positions
+    s->h_rec_dev_off.resize(n_records);
+    s->h_rec_len.resize(n_records);
+    uint64_t pos = 0;
+    const uint64_t total = offsets[n_records] - offsets[0];
+    for (uint32_t r = 0; r < n_records; ++r) {
+        if (offsets[r + 1] < offsets[r]) { set_err("crf_seq_load_ascii: offsets must be non-decreasing"); return CRF_ERR_ARG; }
+        const uint64_t len = offsets[r + 1] - offsets[r];
+        if (pos > 0xFFFFFFFFull) break;
+        s->h_rec_dev_off[r] = (uint32_t)pos;
+        s->h_rec_len[r] = len;
+        pos += len + max_motif_cap;
+    }
+    const uint64_t limit = 0xFFFFFFFFull - 32ull * (2ull * TILE_WORDS_MAX + (max_motif_cap >> 5) + 64);
+    if (pos > limit) {
+        set_err("crf_seq_load_ascii: %llu layout positions exceed the per-load limit of %llu; split the records over "
+                "several loads", (unsigned long long)pos, (unsigned long long)limit);
+        return CRF_ERR_UNSUPPORTED;
+    }
+    s->layout_len = (uint32_t)pos;
+    s->n_words = (s->layout_len + 31) / 32;
+    s->n_words_alloc = (s->n_words + TILE_WORDS_MAX - 1) / TILE_WORDS_MAX * TILE_WORDS_MAX + (max_motif_cap >> 5) + 8;
+
+    CU(cudaEventRecord(s->ev[0], st));
+    const uint8_t *d_src = bases;
+    uint8_t *d_src_own = nullptr;
+    uint64_t *d_src_off = nullptr;
+    if (!on_device) {
+        CHECK(dev_alloc(&d_src_own, (size_t)total));
+        if (total) CU(cudaMemcpyAsync(d_src_own, bases + offsets[0], total, cudaMemcpyHostToDevice, st));
+        d_src = d_src_own;
+    } else {
+        d_src = bases + offsets[0];
+    }
+    std::vector<uint64_t> rel(n_records + 1);
+    for (uint32_t r = 0; r <= n_records; ++r) rel[r] = offsets[r] - offsets[0];
+    int rc = dev_alloc(&d_src_off, (size_t)n_records + 1);
+    if (!rc) rc = dev_alloc(&s->d_rec_dev_off, n_records);
+    if (!rc) rc = dev_alloc(&s->H, s->n_words_alloc);
+    if (!rc) rc = dev_alloc(&s->L, s->n_words_alloc);
+    if (!rc) rc = dev_alloc(&s->NM, s->n_words_alloc);
+    if (!rc) rc = dev_alloc(&s->X, s->n_words_alloc);
+    s->ex_cap = std::min<uint32_t>(EX_CAP, next_pow2((uint32_t)std::min<uint64_t>(std::max<uint64_t>(total, 16), EX_CAP)));
+    if (!rc) rc = dev_alloc(&s->ex_key, s->ex_cap);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        e = cudaMemcpyAsync(d_src_off, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && n_records)
+            e = cudaMemcpyAsync(s->d_rec_dev_off, s->h_rec_dev_off.data(), (size_t)n_records * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st);
+    }
+    if (!rc && e == cudaSuccess) {
+        PackParams pp;
+        pp.src = d_src; pp.rec_src_off = d_src_off; pp.rec_dev_off = s->d_rec_dev_off; pp.n_records = n_records;
+        pp.n_words_alloc = s->n_words_alloc; pp.H = s->H; pp.L = s->L; pp.NM = s->NM; pp.X = s->X;
+        pp.ex_key = s->ex_key; pp.ex_cap = s->ex_cap; pp.ex_count = s->d_counters;
+        pack_kernel<<<(s->n_words_alloc + 255) / 256, 256, 0, st>>>(pp);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (d_src_own) cudaFree(d_src_own);
+    if (d_src_off) cudaFree(d_src_off);
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_err("crf_seq_load_ascii: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
+
+    const unsigned long long nex = s->h_counters[0];
+    if (nex > s->ex_cap) {
+        set_err("crf_seq_load_ascii: %llu symbols other than A,C,G,T,N; at most %u are supported per load", nex, EX_CAP);
+        return CRF_ERR_UNSUPPORTED;
+    }
+    s->n_exotic = (uint32_t)nex;
+    if (s->n_exotic > 1) CHECK(bitonic_sort(st, s->ex_key, nullptr, s->n_exotic, nullptr));
+    CU(cudaEventRecord(s->ev[1], st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+
+    s->info.n_records = n_records;
+    s->info.total_bases = total;
+    s->info.layout_bases = s->layout_len;
+    s->info.packed_bytes = (uint64_t)((total + 3) / 4) + (total + 7) / 8;
+    s->info.n_exotic = s->n_exotic;
+    s->info.max_motif_cap = max_motif_cap;
+    s->info.load_ms = ms;
+    return CRF_OK;
+}
+
+extern "C" int crf_seq_load_ascii(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
+                                  uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
+    if (!c || !out || !offsets) { set_err("crf_seq_load_ascii: null argument"); return CRF_ERR_ARG; }
+    *out = nullptr;
+    if (n_records == 0) { set_err("crf_seq_load_ascii: n_records must be >= 1"); return CRF_ERR_ARG; }
+    if (!bases && offsets[n_records] != offsets[0]) { set_err("crf_seq_load_ascii: null bases"); return CRF_ERR_ARG; }
+    if (max_motif_cap < 1 || max_motif_cap > MAX_K) {
+        set_err("crf_seq_load_ascii: max_motif_cap %u not in [1, %u]", max_motif_cap, MAX_K);
+        return max_motif_cap < 1 ? CRF_ERR_ARG : CRF_ERR_UNSUPPORTED;
+    }
+    CU(cudaSetDevice(c->device));
+    crf_seq *s = new (std::nothrow) crf_seq;
+    if (!s) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    int rc;
+    try {
+        rc = load_impl(c, bases, offsets, n_records, max_motif_cap, bases_on_device, s);
+    } catch (const std::bad_alloc &) {
+        set_err("out of host memory");
+        rc = CRF_ERR_NOMEM;
+    }
+    if (rc) { free_seq(s); return rc; }
+    *out = s;
+    return CRF_OK;
+}
+
+extern "C" int crf_seq_destroy(crf_seq *s) {
+    if (!s) return CRF_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    free_seq(s);
+    return CRF_OK;
+}
+
+extern "C" int crf_seq_info(const crf_seq *s, crf_seq_info_t *info) {
+    if (!s || !info) { set_err("crf_seq_info: null argument"); return CRF_ERR_ARG; }
+    *info = s->info;
+    return CRF_OK;
+}
+
+// ---- scan ---------------------------------------------------------------------------------------
+static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab) {
+    tab.assign((size_t)pr.max_motif_size + 1, KEntry{});
+    for (uint32_t k = 1; k <= pr.max_motif_size; ++k) {
+        KEntry &e = tab[k];
+        // r_min: trk:86 and trk:91 in closed form
+        const uint64_t a = pr.min_span > k ? (uint64_t)pr.min_span - k : 0;
+        const uint64_t b = (uint64_t)(pr.min_repeats - 1) * k;
+        const uint64_t rmin = std::max<uint64_t>(std::max(a, b), 1);
+        e.rmin = (uint32_t)std::min<uint64_t>(rmin, 0xFFFFFF00u);
+        e.rexact = std::min<uint32_t>(e.rmin, 32);
+        if (e.rmin >= 63) e.mode = MODE_WORD;
+        else if (e.rmin >= 31) e.mode = MODE_HALF;
+        else if (e.rmin >= 15) e.mode = MODE_BYTE;
+        else {
+            e.mode = MODE_ERODE;
+            const uint32_t r = std::min<uint32_t>(e.rmin, 8);
+            int n = 0;
+            for (uint32_t covered = 1; covered < r;) {
+                const uint32_t sh = std::min(covered, r - covered);
+                e.sh[n++] = (uint8_t)sh;
+                covered += sh;
+            }
+        }
+        int nd = 0;
+        uint32_t m = k;
+        for (uint32_t p = 2; p * p <= m; ++p)
+            if (m % p == 0) {
+                e.div[nd++] = (uint16_t)(k / p);
+                while (m % p == 0) m /= p;
+            }
+        if (m > 1 && m < k) e.div[nd++] = (uint16_t)(k / m);  // m == k: k itself is prime -> d = 1
+        else if (m > 1 && k > 1) e.div[nd++] = 1;
+        if (pr.flags & CRF_SCAN_NO_PRIMITIVITY)
+            for (int j = 0; j < 6; ++j) e.div[j] = 0;
+    }
+}
+
+static int ensure_result_buffers(crf_seq *s, uint32_t cap) {
+    if (cap <= s->res_cap) return CRF_OK;
+    dev_free(s->stage_key); dev_free(s->spill_key); dev_free(s->fin_key);
+    dev_free(s->stage_k); dev_free(s->spill_k); dev_free(s->fin_k);
+    dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
+    s->res_cap = 0;
+    CHECK(dev_alloc(&s->stage_key, cap)); CHECK(dev_alloc(&s->stage_k, cap));
+    CHECK(dev_alloc(&s->spill_key, cap)); CHECK(dev_alloc(&s->spill_k, cap));
+    CHECK(dev_alloc(&s->fin_key, cap)); CHECK(dev_alloc(&s->fin_k, cap));
+    CHECK(dev_alloc(&s->o_rec, cap)); CHECK(dev_alloc(&s->o_start, cap));
+    CHECK(dev_alloc(&s->o_end, cap)); CHECK(dev_alloc(&s->o_k, cap));
+    s->res_cap = cap;
+    return CRF_OK;
+}
+
+template <int T>
+static int launch_scan(const ScanParams &sp, uint32_t n_tiles, size_t smem, cudaStream_t st) {
+    CU(cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan_kernel<T><<<n_tiles, THREADS, smem, st>>>(sp);
+    CU(cudaGetLastError());
+    return CRF_OK;
+}
+
+extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_results) {
+    if (!s || !pr) { set_err("crf_scan: null argument"); return CRF_ERR_ARG; }
+    // the four checks of perfect_repeat_finder.py:23-30
+    if (pr->min_motif_size < 1) { set_err("min_motif_size is set to %u. It must be at least 1.", pr->min_motif_size); return CRF_ERR_ARG; }
+    if (pr->max_motif_size < pr->min_motif_size) { set_err("max_motif_size is set to %u. It must be at least min_motif_size.", pr->max_motif_size); return CRF_ERR_ARG; }
+    if (pr->min_repeats < 1) { set_err("min_repeats is set to %u. It must be at least 1.", pr->min_repeats); return CRF_ERR_ARG; }
+    if (pr->min_span < 1) { set_err("min_span is set to %u. It must be at least 1.", pr->min_span); return CRF_ERR_ARG; }
+    if (pr->min_repeats == 1) {
+        set_err("min_repeats == 1 (the reference's wrap-around quirk path, perfect_repeat_tracker.py:86-91) is not implemented on the GPU path");
+        return CRF_ERR_UNSUPPORTED;
+    }
+    if (pr->max_motif_size > s->cap) {
+        set_err("max_motif_size %u exceeds the max_motif_cap %u this sequence was loaded with", pr->max_motif_size, s->cap);
+        return CRF_ERR_ARG;
+    }
+    const int T = pr->words_per_thread ? (int)pr->words_per_thread : 8;
+    if (T != 1 && T != 8 && T != 16) { set_err("words_per_thread must be 1, 8 or 16"); return CRF_ERR_ARG; }
+    crf_ctx *c = s->ctx;
+    cudaStream_t st = c->stream;
+    CU(cudaSetDevice(c->device));
+    s->have_results = false;
+
+    // per-k table
+    if (s->ktab_cap < pr->max_motif_size + 1) {
+        dev_free(s->d_ktab);
+        s->ktab_cap = 0;
+        CHECK(dev_alloc(&s->d_ktab, (size_t)pr->max_motif_size + 1));
+        s->ktab_cap = pr->max_motif_size + 1;
+        s->ktab_for.max_motif_size = 0;
+    }
+    if (s->ktab_for.max_motif_size != pr->max_motif_size || s->ktab_for.min_repeats != pr->min_repeats ||
+        s->ktab_for.min_span != pr->min_span || s->ktab_for.flags != pr->flags) {
+        std::vector<KEntry> tab;
+        build_ktab(*pr, tab);
+        CU(cudaMemcpyAsync(s->d_ktab, tab.data(), tab.size() * sizeof(KEntry), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // tab is a local
+        s->ktab_for = *pr;
+    }
+
+    const uint32_t TW = THREADS * T;
+    const uint32_t n_tiles = (s->n_words + TW - 1) / TW;
+    if (s->tiles_cap < n_tiles + 1) {
+        dev_free(s->tile_cnt); dev_free(s->tile_base); dev_free(s->tile_off);
+        s->tiles_cap = 0;
+        CHECK(dev_alloc(&s->tile_cnt, (size_t)n_tiles + 1));
+        CHECK(dev_alloc(&s->tile_base, (size_t)n_tiles + 1));
+        CHECK(dev_alloc(&s->tile_off, (size_t)n_tiles + 1));
+        s->tiles_cap = n_tiles + 1;
+    }
+    uint32_t cap = pr->result_cap ? pr->result_cap : std::max<uint32_t>(1u << 16, s->layout_len / 96);
+    cap = std::max(cap, s->res_cap);
+    const uint32_t outcap = pr->tile_out_cap ? pr->tile_out_cap : 1024;
+    if (outcap > 4096) { set_err("tile_out_cap must be <= 4096"); return CRF_ERR_ARG; }
+    const size_t smem = scan_smem_bytes(T, pr->max_motif_size, outcap);
+
+    uint32_t reruns = 0, launches = 0;
+    for (;;) {
+        CHECK(ensure_result_buffers(s, cap));
+        ScanParams sp;
+        sp.H = s->H; sp.L = s->L; sp.NM = s->NM; sp.X = s->X;
+        sp.ktab = s->d_ktab;
+        sp.ex_key = s->ex_key; sp.n_exotic = s->n_exotic;
+        sp.n_words = s->n_words;
+        sp.kmin = pr->min_motif_size; sp.kmax = pr->max_motif_size;
+        sp.outcap = outcap;
+        sp.walk_limit = pr->walk_limit_words ? pr->walk_limit_words : 64;
+        sp.stage_key = s->stage_key; sp.stage_k = s->stage_k; sp.stage_cap = s->res_cap;
+        sp.tile_cnt = s->tile_cnt; sp.tile_base = s->tile_base;
+        sp.spill_key = s->spill_key; sp.spill_k = s->spill_k; sp.spill_cap = s->res_cap;
+        sp.counters = s->d_counters;
+
+        CU(cudaEventRecord(s->ev[0], st));
+        CU(cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
+        CU(cudaEventRecord(s->ev[1], st));
+        if (T == 1) CHECK(launch_scan<1>(sp, n_tiles, smem, st));
+        else if (T == 8) CHECK(launch_scan<8>(sp, n_tiles, smem, st));
+        else CHECK(launch_scan<16>(sp, n_tiles, smem, st));
+        CU(cudaEventRecord(s->ev[2], st));
+        tile_offsets_kernel<<<1, 1024, 0, st>>>(s->tile_cnt, s->tile_off, n_tiles, s->d_counters);
+        GatherParams g;
+        g.stage_key = s->stage_key; g.stage_k = s->stage_k;
+        g.tile_cnt = s->tile_cnt; g.tile_base = s->tile_base; g.tile_off = s->tile_off;
+        g.spill_key = s->spill_key; g.spill_k = s->spill_k;
+        g.fin_key = s->fin_key; g.fin_k = s->fin_k;
+        g.n_tiles = n_tiles; g.fin_cap = s->res_cap; g.stage_cap = s->res_cap; g.spill_cap = s->res_cap;
+        g.counters = s->d_counters;
+        gather_kernel<<<(n_tiles * 32 + 255) / 256, 256, 0, st>>>(g);
+        const uint32_t tgrid = std::min<uint32_t>(148 * 8, (s->res_cap + 255) / 256);
+        translate_kernel<<<tgrid, 256, 0, st>>>(s->fin_key, s->fin_k, s->d_rec_dev_off, s->n_records, s->d_counters,
+                                               s->res_cap, s->o_rec, s->o_start, s->o_end, s->o_k);
+        CU(cudaGetLastError());
+        launches += 4;
+        CU(cudaEventRecord(s->ev[3], st));
+        CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+
+        const unsigned long long n_stage = s->h_counters[C_STAGE], n_spill = s->h_counters[C_SPILL];
+        const unsigned long long n_total = n_stage + n_spill;
+        if (n_stage > s->res_cap || n_spill > s->res_cap || n_total > s->res_cap) {
+            if (n_total + 1024 > 0xFFFFFFF0ull) { set_err("crf_scan: more than 2^32 results"); return CRF_ERR_UNSUPPORTED; }
+            cap = (uint32_t)(n_total + n_total / 16 + 1024);
+            ++reruns;
+            continue;
+        }
+        if (n_spill) {  // a tile overflowed its slots: order everything with the fallback network
+            const uint32_t n = (uint32_t)n_total, np = next_pow2(n);
+            uint64_t *tk = nullptr;
+            uint16_t *tv = nullptr;
+            CHECK(dev_alloc(&tk, np));
+            int rc = dev_alloc(&tv, np);
+            if (rc) { cudaFree(tk); return rc; }
+            cudaMemcpyAsync(tk, s->fin_key, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(tv, s->fin_k, (size_t)n * 2, cudaMemcpyDeviceToDevice, st);
+            rc = bitonic_sort(st, tk, tv, n, &launches);
+            cudaMemcpyAsync(s->fin_key, tk, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(s->fin_k, tv, (size_t)n * 2, cudaMemcpyDeviceToDevice, st);
+            translate_kernel<<<tgrid, 256, 0, st>>>(s->fin_key, s->fin_k, s->d_rec_dev_off, s->n_records, s->d_counters,
+                                                   s->res_cap, s->o_rec, s->o_start, s->o_end, s->o_k);
+            ++launches;
+            cudaEventRecord(s->ev[3], st);
+            cudaError_t e = cudaStreamSynchronize(st);
+            cudaFree(tk);
+            cudaFree(tv);
+            if (rc) return rc;
+            if (e != cudaSuccess) { set_err("crf_scan: fallback sort failed: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
+        }
+        float ms_all = 0, ms_k = 0;
+        CU(cudaEventElapsedTime(&ms_all, s->ev[0], s->ev[3]));
+        CU(cudaEventElapsedTime(&ms_k, s->ev[1], s->ev[2]));
+        s->n_results = n_total;
+        s->have_results = true;
+        s->stats.scan_ms = ms_all;
+        s->stats.kernel_ms = ms_k;
+        s->stats.n_results = n_total;
+        s->stats.n_tiles = n_tiles;
+        s->stats.n_spilled = n_spill;
+        s->stats.n_long = s->h_counters[C_LONG];
+        s->stats.n_candidates = s->h_counters[C_CAND];
+        s->stats.word_k_pairs = (uint64_t)s->n_words * (pr->max_motif_size - pr->min_motif_size + 1);
+        s->stats.reruns = reruns;
+        s->stats.launches = launches;
+        break;
+    }
+    if (n_results) *n_results = s->n_results;
+    return CRF_OK;
+}
+
+extern "C" int crf_fetch(crf_seq *s, uint32_t *record, uint32_t *start, uint32_t *end, uint32_t *motif_size,
+                         uint64_t capacity, int dst_on_device) {
+    if (!s) { set_err("crf_fetch: null sequence"); return CRF_ERR_ARG; }
+    if (!s->have_results) { set_err("crf_fetch: no scan results to fetch"); return CRF_ERR_ARG; }
+    if (capacity < s->n_results) {
+        set_err("crf_fetch: capacity %llu < %llu results", (unsigned long long)capacity, (unsigned long long)s->n_results);
+        return CRF_ERR_CAPACITY;
+    }
+    if (!s->n_results) return CRF_OK;
+    if (!record || !start || !end || !motif_size) { set_err("crf_fetch: null output array"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t bytes = (size_t)s->n_results * 4;
+    CU(cudaMemcpyAsync(record, s->o_rec, bytes, kind, st));
+    CU(cudaMemcpyAsync(start, s->o_start, bytes, kind, st));
+    CU(cudaMemcpyAsync(end, s->o_end, bytes, kind, st));
+    CU(cudaMemcpyAsync(motif_size, s->o_k, bytes, kind, st));
+    CU(cudaStreamSynchronize(st));
+    return CRF_OK;
+}
+
+extern "C" int crf_scan_stats(const crf_seq *s, crf_scan_stats_t *stats) {
+    if (!s || !stats) { set_err("crf_scan_stats: null argument"); return CRF_ERR_ARG; }
+    *stats = s->stats;
+    return CRF_OK;
+}
+
+extern "C" int crf_run_end(crf_seq *s, uint32_t record, uint32_t pos, uint32_t k, uint32_t *run_end) {
+    if (!s || !run_end) { set_err("crf_run_end: null argument"); return CRF_ERR_ARG; }
+    if (record >= s->n_records || pos >= s->h_rec_len[record]) { set_err("crf_run_end: position out of range"); return CRF_ERR_ARG; }
+    if (k < 1 || k > s->cap) { set_err("crf_run_end: k %u not in [1, max_motif_cap %u]", k, s->cap); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    ScanParams sp = {};
+    sp.H = s->H; sp.L = s->L; sp.NM = s->NM; sp.X = s->X;
+    sp.ex_key = s->ex_key; sp.n_exotic = s->n_exotic; sp.n_words = s->n_words;
+    uint32_t *d_out = reinterpret_cast<uint32_t *>(s->d_counters + C_COUNT - 1);
+    const uint32_t d0 = s->h_rec_dev_off[record];
+    run_end_kernel<<<1, THREADS, 0, st>>>(sp, k, d0 + pos, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->h_counters, d_out, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *run_end = *reinterpret_cast<uint32_t *>(s->h_counters) - d0;
+    return CRF_OK;
+}

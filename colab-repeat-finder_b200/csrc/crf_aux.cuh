@@ -1,0 +1,225 @@
+// crf_aux.cuh -- kernels around the scan: packing, result assembly, fallback sort, run-end query.
+#pragma once
+#include "crf_device.cuh"
+
+namespace crf {
+
+// ---- pack: ASCII records -> H/L/NM/X planes (replaces input_sequence.upper(), prf:33, and the
+// per-base str compares of trk:53 by a 2-bit code + mask) ---------------------------------------
+struct PackParams {
+    const uint8_t *src;           // all records back to back
+    const uint64_t *rec_src_off;  // n_records + 1
+    const uint32_t *rec_dev_off;  // n_records (layout position of each record's first base)
+    uint32_t n_records;
+    uint32_t n_words_alloc;
+    uint32_t *H, *L, *NM, *X;
+    uint64_t *ex_key;
+    uint32_t ex_cap;
+    unsigned long long *ex_count;
+};
+
+__global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= p.n_words_alloc) return;
+    const uint32_t p0 = w << 5;
+    // record containing (or preceding) p0: last r with rec_dev_off[r] <= p0
+    uint32_t lo = 0, hi = p.n_records ? p.n_records - 1 : 0;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (p.rec_dev_off[mid] <= p0) lo = mid; else hi = mid - 1;
+    }
+    uint32_t r = lo;
+    uint64_t src0 = 0;
+    uint32_t dev0 = 0, rec_end = 0, next_start = NOPOS;
+    if (p.n_records) {
+        src0 = p.rec_src_off[r];
+        dev0 = p.rec_dev_off[r];
+        rec_end = dev0 + (uint32_t)(p.rec_src_off[r + 1] - src0);
+        next_start = (r + 1 < p.n_records) ? p.rec_dev_off[r + 1] : NOPOS;
+    }
+    uint32_t h = 0, l = 0, nm = 0, x = 0;
+#pragma unroll 4
+    for (uint32_t b = 0; b < 32; ++b) {
+        const uint32_t pos = p0 + b;
+        if (pos >= next_start) {
+            ++r;
+            src0 = p.rec_src_off[r];
+            dev0 = p.rec_dev_off[r];
+            rec_end = dev0 + (uint32_t)(p.rec_src_off[r + 1] - src0);
+            next_start = (r + 1 < p.n_records) ? p.rec_dev_off[r + 1] : NOPOS;
+        }
+        uint32_t code, masked = 1, exo = 0;
+        if (pos >= dev0 && pos < rec_end) {
+            uint32_t c = p.src[src0 + (pos - dev0)];
+            if (c >= 'a' && c <= 'z') c -= 32;  // upper() for ASCII (prf:33)
+            if (c == 'A') { code = 0; masked = 0; }
+            else if (c == 'C') { code = 1; masked = 0; }
+            else if (c == 'G') { code = 2; masked = 0; }
+            else if (c == 'T') { code = 3; masked = 0; }
+            else if (c == 'N') { code = hash32(pos) & 3; }
+            else {
+                code = hash32(c * 0x9E3779B1u) & 3;  // equal letters -> equal filler code
+                exo = 1;
+                const unsigned long long idx = atomicAdd(p.ex_count, 1ull);
+                if (idx < p.ex_cap) p.ex_key[idx] = ((uint64_t)pos << 8) | c;
+            }
+        } else {
+            code = hash32(pos) & 3;  // inter-record gap / tail pad: masked, aperiodic filler
+        }
+        h |= (code >> 1) << b;
+        l |= (code & 1) << b;
+        nm |= masked << b;
+        x |= exo << b;
+    }
+    p.H[w] = h;
+    p.L[w] = l;
+    p.NM[w] = nm;
+    p.X[w] = x;
+}
+
+// ---- assembly: tile segments -> one (start, end)-sorted list --------------------------------
+// exclusive prefix sum of tile_cnt (single block; n_tiles is tens of thousands at most)
+__global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t *tile_cnt, uint32_t *tile_off,
+                                                            uint32_t n_tiles, unsigned long long *counters) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t v = (i < n_tiles) ? tile_cnt[i] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+        for (uint32_t j = 0; j < 32; ++j) {
+            const uint32_t t = warp_sum[j];
+            if (j < warp) woff += t;
+            total += t;
+        }
+        const uint32_t carry = carry_s;
+        if (i < n_tiles) tile_off[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (tid == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        tile_off[n_tiles] = carry_s;
+        const unsigned long long spill = counters[C_SPILL];
+        counters[C_TOTAL] = (unsigned long long)carry_s + spill;
+    }
+}
+
+struct GatherParams {
+    const uint64_t *stage_key;
+    const uint16_t *stage_k;
+    const uint32_t *tile_cnt, *tile_base, *tile_off;
+    const uint64_t *spill_key;
+    const uint16_t *spill_k;
+    uint64_t *fin_key;
+    uint16_t *fin_k;
+    uint32_t n_tiles, fin_cap, stage_cap, spill_cap;
+    const unsigned long long *counters;
+};
+
+// one warp per tile copies its sorted segment to its final place; spilled rows go to the tail
+__global__ void __launch_bounds__(256) gather_kernel(const GatherParams g) {
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g.counters[C_STAGE] > g.stage_cap || g.counters[C_TOTAL] > g.fin_cap) return;  // host re-runs
+    if (warp_global < g.n_tiles) {
+        const uint32_t n = g.tile_cnt[warp_global], src = g.tile_base[warp_global], dst = g.tile_off[warp_global];
+        for (uint32_t i = lane; i < n; i += 32) {
+            g.fin_key[dst + i] = g.stage_key[src + i];
+            g.fin_k[dst + i] = g.stage_k[src + i];
+        }
+    }
+    const unsigned long long nspill = g.counters[C_SPILL];
+    if (nspill && nspill <= g.spill_cap) {
+        const uint32_t dst = g.tile_off[g.n_tiles];
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nspill; i += stride) {
+            g.fin_key[dst + i] = g.spill_key[i];
+            g.fin_k[dst + i] = g.spill_k[i];
+        }
+    }
+}
+
+// layout coordinates -> (record, start, end, k)  (the re-offsetting of prf:81, per record)
+__global__ void __launch_bounds__(256) translate_kernel(const uint64_t *fin_key, const uint16_t *fin_k,
+                                                        const uint32_t *rec_dev_off, uint32_t n_records,
+                                                        const unsigned long long *counters, uint32_t fin_cap,
+                                                        uint32_t *o_rec, uint32_t *o_start, uint32_t *o_end,
+                                                        uint32_t *o_k) {
+    const unsigned long long n = counters[C_TOTAL];
+    if (n > fin_cap) return;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = fin_key[i];
+        const uint32_t st = (uint32_t)(key >> 32), en = (uint32_t)key;
+        uint32_t lo = 0, hi = n_records - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (rec_dev_off[mid] <= st) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t d0 = rec_dev_off[lo];
+        o_rec[i] = lo;
+        o_start[i] = st - d0;
+        o_end[i] = en - d0;
+        o_k[i] = fin_k[i];
+    }
+}
+
+// ---- fallback ordering: global bitonic network on (key, k); n_pow2 elements, tail padded with
+// all-ones keys.  Only used when a tile overflowed its sorted-output slots, and for the (tiny)
+// list of exotic symbols. -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bitonic_step_kernel(uint64_t *key, uint16_t *val, uint32_t n_pow2, uint32_t j,
+                                                           uint32_t kk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pow2) return;
+    const uint32_t ixj = i ^ j;
+    if (ixj <= i) return;
+    const bool asc = (i & kk) == 0;
+    const uint64_t a = key[i], b = key[ixj];
+    const uint16_t va = val ? val[i] : 0, vb = val ? val[ixj] : 0;
+    const bool gt = (a > b) || (a == b && va > vb);
+    if (gt == asc) {
+        key[i] = b;
+        key[ixj] = a;
+        if (val) { val[i] = vb; val[ixj] = va; }
+    }
+}
+__global__ void __launch_bounds__(256) fill_u64_kernel(uint64_t *dst, uint64_t v, uint32_t from, uint32_t to) {
+    const uint32_t i = from + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < to) dst[i] = v;
+}
+
+// ---- run-end query (crf_run_end): one block walks 256 words per step ---------------------------
+__global__ void __launch_bounds__(THREADS) run_end_kernel(const ScanParams p, uint32_t k, uint32_t pos, uint32_t *out) {
+    __shared__ uint32_t minpos;
+    const uint32_t tid = threadIdx.x;
+    uint32_t wcur = pos >> 5;
+    for (;;) {
+        if (tid == 0) minpos = NOPOS;
+        __syncthreads();
+        const uint32_t w = wcur + tid;
+        uint32_t m = (w < p.n_words) ? exact_mask(p, k, w) : 0u;
+        if (w == (pos >> 5)) m |= (1u << (pos & 31)) - 1u;
+        if (m != 0xFFFFFFFFu) atomicMin(&minpos, (w << 5) + (__ffs(~m) - 1));
+        __syncthreads();
+        const uint32_t r = minpos;
+        __syncthreads();
+        if (r != NOPOS) {
+            if (tid == 0) *out = r;
+            return;
+        }
+        wcur += THREADS;
+    }
+}
+
+}  // namespace crf

@@ -1,0 +1,148 @@
+// crf_device.cuh -- device-side data model and exact match-mask primitives (sm_100a).
+//
+// Data layout in HBM (see DESIGN.md "Data layout"): every record of a load is laid out in one
+// position space ("layout"), records separated by >= max_motif_cap masked positions so that no
+// compare S[j] vs S[j+k] can pair two records.  Position p lives in word p>>5, bit p&31 of
+//   H, L : the two bits of the base code (A=00 C=01 G=10 T=11)            -- 0.25 B/bp
+//   NM   : 1 = not one of A,C,G,T (N, gap, any other symbol)              -- 0.125 B/bp
+//   X    : 1 = "exotic" symbol: neither ACGT nor N (IUPAC codes ...), read only by the exact path
+// Masked positions carry a filler code in H/L: a position hash for N/gap (aperiodic, so the
+// unmasked H/L compare has no long runs inside N blocks), a letter hash for exotic symbols
+// (equal letters get equal codes, so the unmasked compare is a superset of the true mask).
+//
+// The match mask the reference's tracker evaluates one base at a time
+// (utils/perfect_repeat_tracker.py:53:  seq[i] == seq[i+k] and seq[i] != "N") is, for 32
+// positions at once,  M_k[w] = ~((H^H>>k) | (L^L>>k)) & ~(NM | NM>>k)  (+ exotic equal letters).
+#pragma once
+#include <stdint.h>
+
+namespace crf {
+
+constexpr int THREADS = 256;     // threads per scan block
+constexpr int LONGCAP = 32;      // per-tile queue of runs handed to the block-cooperative walker
+constexpr uint32_t NOPOS = 0xFFFFFFFFu;
+
+enum FilterMode : uint8_t {
+    MODE_ERODE = 0,  // r_min < 15 : dilate the mismatch word by min(r_min, 8)
+    MODE_BYTE = 1,   // r_min >= 15: a run contains an aligned all-match byte
+    MODE_HALF = 2,   // r_min >= 31: ... an aligned all-match half-word (H plane only)
+    MODE_WORD = 3,   // r_min >= 63: ... an aligned all-match word (H plane only)
+};
+
+// Per motif size k (index = k).  r_min = max(min_span - k, (min_repeats-1)*k) is the number of
+// consecutive ones of M_k a run needs (trk:86,91 in closed form).
+struct __align__(16) KEntry {
+    uint32_t rmin;
+    uint32_t rexact;   // min(rmin, 32): erosion width used by the exact phase
+    uint8_t mode;      // FilterMode
+    uint8_t sh[3];     // dilation shifts of the ERODE filter (0 = unused)
+    uint16_t div[6];   // k/p for the distinct primes p | k (0-terminated): primitivity, trk:108-142
+    uint32_t pad_;
+};
+static_assert(sizeof(KEntry) == 32, "KEntry layout");
+
+struct ScanParams {
+    const uint32_t *H, *L, *NM, *X;
+    const KEntry *ktab;
+    const uint64_t *ex_key;  // sorted (pos << 8 | letter) of exotic symbols
+    uint32_t n_exotic;
+    uint32_t n_words;        // words holding layout positions (reads beyond are allocated pads)
+    uint32_t kmin, kmax;
+    uint32_t outcap;         // per-tile sorted-output slots
+    uint32_t walk_limit;     // words one thread walks before the block takes over
+    uint64_t *stage_key;     // (start << 32 | end), tile-sorted segments
+    uint16_t *stage_k;
+    uint32_t stage_cap;
+    uint32_t *tile_cnt, *tile_base;
+    uint64_t *spill_key;     // results that overflowed a tile's slots (unsorted)
+    uint16_t *spill_k;
+    uint32_t spill_cap;
+    unsigned long long *counters;  // see CounterIdx
+};
+
+enum CounterIdx { C_STAGE = 0, C_SPILL = 1, C_LONG = 2, C_CAND = 3, C_TOTAL = 4, C_COUNT = 8 };
+
+__device__ __forceinline__ uint32_t plane_at(const uint32_t *__restrict__ P, uint32_t w, uint32_t q, uint32_t s) {
+    return __funnelshift_r(__ldg(P + w + q), __ldg(P + w + q + 1), s);
+}
+
+// letter of the exotic symbol at layout position pos (0 if none)
+__device__ inline uint32_t exotic_letter(const ScanParams &p, uint32_t pos) {
+    uint32_t lo = 0, hi = p.n_exotic;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)(p.ex_key[mid] >> 8) < pos) lo = mid + 1; else hi = mid;
+    }
+    if (lo < p.n_exotic && (uint32_t)(p.ex_key[lo] >> 8) == pos) return (uint32_t)(p.ex_key[lo] & 0xFF);
+    return 0;
+}
+
+// Exact M_k for the 32 positions of word w.
+__device__ inline uint32_t exact_mask(const ScanParams &p, uint32_t k, uint32_t w) {
+    const uint32_t q = k >> 5, s = k & 31;
+    const uint32_t dh = __ldg(p.H + w) ^ plane_at(p.H, w, q, s);
+    const uint32_t dl = __ldg(p.L + w) ^ plane_at(p.L, w, q, s);
+    const uint32_t nm = __ldg(p.NM + w) | plane_at(p.NM, w, q, s);
+    const uint32_t eq = ~(dh | dl);
+    uint32_t m = eq & ~nm;
+    if (p.n_exotic) {  // equal exotic letters match too (only "N" is special, trk:53)
+        uint32_t x = __ldg(p.X + w) & plane_at(p.X, w, q, s) & eq;
+        while (x) {
+            const uint32_t b = __ffs(x) - 1;
+            x &= x - 1;
+            const uint32_t pos = (w << 5) + b;
+            if (exotic_letter(p, pos) == exotic_letter(p, pos + k)) m |= 1u << b;
+        }
+    }
+    return m;
+}
+
+// First position >= from with M_k == 0, looking at no more than `limit` further words.
+// Returns true and the position; or false with *i0 = first position not yet examined.
+__device__ inline bool walk_run(const ScanParams &p, uint32_t k, uint32_t from, uint32_t limit, uint32_t *i0) {
+    uint32_t w = from >> 5;
+    uint32_t m = exact_mask(p, k, w) | ((1u << (from & 31)) - 1u);
+    for (uint32_t n = 0;; ++n) {
+        if (m != 0xFFFFFFFFu) { *i0 = (w << 5) + (__ffs(~m) - 1); return true; }
+        ++w;
+        if (n >= limit || w >= p.n_words) {  // beyond n_words everything is masked
+            *i0 = w << 5;
+            return w >= p.n_words;
+        }
+        m = exact_mask(p, k, w);
+    }
+}
+
+// M_d[a .. a+len) all ones?
+__device__ inline bool all_match(const ScanParams &p, uint32_t d, uint32_t a, uint32_t len) {
+    uint32_t pos = a;
+    const uint32_t end = a + len;
+    while (pos < end) {
+        const uint32_t b = pos & 31;
+        const uint32_t n = min(32u - b, end - pos);
+        const uint32_t mask = (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)) << b;
+        if ((exact_mask(p, d, pos >> 5) & mask) != mask) return false;
+        pos += n;
+    }
+    return true;
+}
+
+// The motif S[st:st+k] is primitive iff it is not u^n, n >= 2 (consists_of_perfect_repeats,
+// trk:108-142).  u^n with |u| = d | k  <=>  S[j] == S[j+d] on [st, st+k-d); it suffices to try
+// d = k/p for the primes p | k.
+__device__ inline bool motif_is_primitive(const ScanParams &p, const KEntry &ke, uint32_t k, uint32_t st) {
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) {
+        const uint32_t d = ke.div[j];
+        if (!d) break;
+        if (all_match(p, d, st, k - d)) return false;
+    }
+    return true;
+}
+
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+}  // namespace crf

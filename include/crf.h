@@ -1,0 +1,126 @@
+/*
+ * crf.h -- C ABI of libcrf.so, the B200 (sm_100a) perfect-tandem-repeat scan.
+ *
+ * The reference (broadinstitute/colab-repeat-finder) has no FFI of its own: its hot path is the
+ * Python function detect_repeats() (perfect_repeat_finder.py:10-81) driving one
+ * PerfectRepeatTracker per motif size (utils/perfect_repeat_tracker.py:3-105).  These entry
+ * points are what a ctypes binding under that function binds instead of the tracker loop
+ * (INTEGRATION.md shows the stub).  Plain C types only, no exceptions cross the boundary, every
+ * call returns an int status (0 = ok) and leaves a message for crf_last_error() on failure.
+ *
+ * Threading: one crf_ctx per GPU; calls on one context (and on its sequences) must be
+ * serialised by the caller.  Different contexts may be driven from different threads/processes.
+ *
+ * Coordinates are 0-based, half-open, per record -- the (start_0based, end) convention of
+ * perfect_repeat_finder.py:81.
+ */
+#ifndef CRF_H
+#define CRF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRF_OK 0
+#define CRF_ERR_CUDA 1        /* a CUDA runtime call failed                               */
+#define CRF_ERR_ARG 2         /* invalid argument (the ValueError cases of prf:23-30 too)  */
+#define CRF_ERR_NOMEM 3
+#define CRF_ERR_UNSUPPORTED 4 /* valid for the reference, not implemented here (loud)     */
+#define CRF_ERR_CAPACITY 5    /* caller-provided buffer too small                          */
+
+typedef struct crf_ctx crf_ctx; /* one CUDA device + stream + scratch                      */
+typedef struct crf_seq crf_seq; /* a set of records resident in HBM as packed bit-planes   */
+
+/* Last error message of the calling thread ("" if none). */
+const char *crf_last_error(void);
+/* ABI version of the library (bumped on incompatible change). */
+int crf_abi_version(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int crf_ctx_create(int device, crf_ctx **ctx);
+int crf_ctx_destroy(crf_ctx *ctx);
+/* Run all work of this context on `cuda_stream` (a cudaStream_t; NULL = the context's own). */
+int crf_ctx_set_stream(crf_ctx *ctx, void *cuda_stream);
+int crf_ctx_synchronize(crf_ctx *ctx);
+
+/* ---- sequence upload ----------------------------------------------------------------------
+ * Replaces the `input_sequence` str handed to detect_repeats (prf:10,33): `bases` holds
+ * n_records records back to back, record r = bases[offsets[r] .. offsets[r+1]); any case, any
+ * byte value.  Upper-casing (prf:33) happens on the device.  The records are packed into two
+ * 2-bit planes plus a not-ACGT mask; runs never cross a record boundary.  `max_motif_cap` is the
+ * largest max_motif_size later scans may use (it sizes the inter-record gap and the halo).
+ * bases_on_device != 0: `bases` is a device pointer (offsets stay on the host).
+ */
+int crf_seq_load_ascii(crf_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
+                       uint32_t max_motif_cap, int bases_on_device, crf_seq **seq);
+int crf_seq_destroy(crf_seq *seq);
+
+typedef struct {
+    uint64_t n_records;
+    uint64_t total_bases;  /* sum of record lengths                                    */
+    uint64_t layout_bases; /* device layout incl. inter-record gaps                    */
+    uint64_t packed_bytes; /* bytes of the two base planes + mask plane (algorithmic)   */
+    uint64_t n_exotic;     /* symbols other than A,C,G,T,N after upper-casing           */
+    uint32_t max_motif_cap;
+    uint32_t reserved;
+    double load_ms;        /* device time of the last upload+pack                       */
+} crf_seq_info_t;
+int crf_seq_info(const crf_seq *seq, crf_seq_info_t *info);
+
+/* ---- scan ----------------------------------------------------------------------------------
+ * One call = the whole of prf:49-81 for every record: all motif sizes in
+ * [min_motif_size, max_motif_size], filters min_repeats / min_span (trk:86,91), primitivity
+ * (trk:98, 108-142), ordering by (record, start, end) (prf:81).  Results stay in HBM until
+ * fetched.  The argument checks and messages of prf:23-30 map to CRF_ERR_ARG.
+ * min_repeats == 1 (the reference's wrap-around quirk, trk:86-91) is CRF_ERR_UNSUPPORTED.
+ */
+/* keep runs whose motif is not primitive too (used to find where the reference's interval-mode
+ * loop stops, prf:70-74: is_in_middle_of_repeat() does not look at the motif) */
+#define CRF_SCAN_NO_PRIMITIVITY 1u
+
+typedef struct {
+    uint32_t min_motif_size;
+    uint32_t max_motif_size;
+    uint32_t min_repeats;
+    uint32_t min_span;
+    /* test / tuning knobs; 0 = library default */
+    uint32_t words_per_thread; /* tile shape: 8 or 16 32-base words per thread            */
+    uint32_t tile_out_cap;     /* per-tile sorted-output slots before spilling           */
+    uint32_t walk_limit_words; /* words a single thread walks before the block takes over */
+    uint32_t result_cap;       /* initial result capacity (grown and re-run on overflow)  */
+    uint32_t flags;            /* CRF_SCAN_* bits                                         */
+} crf_scan_params;
+
+int crf_scan(crf_seq *seq, const crf_scan_params *params, uint64_t *n_results);
+
+/* Copy the results of the last scan into caller arrays of `capacity` entries each
+ * (dst_on_device != 0: device pointers).  record = index into the load's records;
+ * start/end per record; motif_size = k, the motif is record[start:start+k] upper-cased. */
+int crf_fetch(crf_seq *seq, uint32_t *record, uint32_t *start, uint32_t *end, uint32_t *motif_size,
+              uint64_t capacity, int dst_on_device);
+
+typedef struct {
+    double scan_ms;      /* device time, packed planes resident -> sorted results resident  */
+    double kernel_ms;    /* the scan kernel alone                                          */
+    uint64_t n_results;
+    uint64_t n_tiles;
+    uint64_t n_spilled;  /* results that left the in-order path (sorted by the fallback)   */
+    uint64_t n_long;     /* runs finished by the block-cooperative walker                  */
+    uint64_t n_candidates; /* (strip, k) pairs the filter sent to the exact phase          */
+    uint64_t word_k_pairs; /* 32-base words x motif sizes evaluated                        */
+    uint32_t reruns;     /* scans repeated because the result buffer was too small         */
+    uint32_t launches;   /* kernels launched by the last crf_scan                          */
+} crf_scan_stats_t;
+int crf_scan_stats(const crf_seq *seq, crf_scan_stats_t *stats);
+
+/* End of the maximal run of period k through position `pos` of `record` (pos must satisfy
+ * M_k[pos] == 1, else *run_end = pos).  *run_end = first position >= pos that does not match.
+ * Used to stitch runs that leave a partition (chunk/GPU) -- see DESIGN.md "multi-GPU". */
+int crf_run_end(crf_seq *seq, uint32_t record, uint32_t pos, uint32_t k, uint32_t *run_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRF_H */
