@@ -1,0 +1,418 @@
+#!/usr/bin/env python3
+"""bench.py -- Gbp/s scanned (motif 1-50) on the synthetic hg38-sized genome (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload s38|s22] [--impl reference]
+
+One JSON line on stdout (rank 0).  A step = one full scan (all motif sizes 1..50, thresholds,
+primitivity, ordering) of the whole workload:
+  value   whole-job Gbp/s with the packed planes already resident in HBM (device time, CUDA events,
+          max over ranks);
+  e2e     the same through the public API with HOST buffers: ASCII bases H2D + pack + scan + results D2H
+          every step;
+  roofline / cpu_baseline as described in DESIGN.md "Measurement".
+Under torchrun (N > 1) every rank takes a contiguous share of (record, chunk) units.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "colab-repeat-finder_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+KMIN, KMAX, MIN_REPEATS, MIN_SPAN = 1, 50, 3, 9       # the reference CLI defaults (prf:86-89)
+METRIC = "Gbp/s scanned (motif 1-50)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---- clocks ----------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU baseline (oracle port of the reference's tracker loop) ----------------------------------
+def cpu_baseline_run(sample_bytes, threads=0):
+    from oracle import oracle
+    fs = argparse.Namespace(min_motif_size=KMIN, max_motif_size=KMAX, min_repeats=MIN_REPEATS, min_span=MIN_SPAN)
+    threads = threads or oracle.max_threads()
+    t0 = time.perf_counter()
+    start, end, mlen, steps = oracle.detect_repeats_by_k(sample_bytes, fs, threads=threads, arrays=True)
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "bp": int(len(sample_bytes)), "rows": (start, end, mlen), "threads": min(threads, KMAX - KMIN + 1)}
+
+
+def make_workload(name, device, scale):
+    from crf_b200 import synth
+    if name == "s38":
+        return synth.s38(device=device, scale=scale)
+    if name == "s22":
+        return synth.s22(device=device, scale=scale)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU algorithm (C port in oracle/, all host threads) on a
+    bounded sample of the same workload.  The Python reference itself cannot travel to the GPU box."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    dev = "cuda:0" if torch.cuda.is_available() else None
+    if dev:
+        bases, offsets, meta = make_workload(args.workload, dev, args.scale)
+        r = min(20, len(offsets) - 2)            # chr21 of S38 (46.7 Mbp); the only record of S22
+        sample = bases[int(offsets[r]):int(offsets[r + 1])].cpu().numpy()
+        sample_name = f"record {r} of the workload"
+    else:
+        from crf_b200 import synth
+        sample, _, _ = synth.generate_records([int(46_709_983 * args.scale)], 38, device=None)
+        meta = {"workload": "S38-like single record (no GPU to generate the full genome)"}
+        sample_name = "standalone 46.7 Mbp record"
+    from oracle import oracle
+    times = []
+    for i in range(args.warmup + args.steps):
+        res = cpu_baseline_run(sample)
+        if i >= args.warmup:
+            times.append(res["seconds"])
+    dt = float(np.mean(times))
+    gbps = sample.size / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbps, "unit": "Gbp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": meta["workload"], "motif_sizes": [KMIN, KMAX], "min_repeats": MIN_REPEATS,
+                   "min_span": MIN_SPAN},
+        "cpu_baseline": {"value": gbps, "unit": "Gbp/s", "cores": res["threads"], "kind": "port",
+                         "sample": f"{sample_name}, {sample.size} bp x {KMAX - KMIN + 1} motif sizes per step; "
+                                   f"C port of the tracker loop (oracle/crf_oracle.c), one thread per motif size; "
+                                   f"host has {oracle.max_threads()} cores"},
+        "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="s38", choices=["s38", "s22"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--words-per-thread", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from crf_b200 import _cabi, partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = _cabi.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- workload: generated in HBM, deterministic, identical on every rank ----
+    t0 = time.time()
+    bases, offsets, meta = make_workload(args.workload, dev, args.scale)
+    torch.cuda.synchronize()
+    lengths = [int(offsets[i + 1] - offsets[i]) for i in range(len(offsets) - 1)]
+    total_bp = int(offsets[-1])
+    log(f"[rank {rank}] generated {meta['workload']} in {time.time() - t0:.1f}s")
+
+    # ---- this rank's share: contiguous (record, chunk) units with halo ----
+    plan = partition.Plan(lengths, world, chunk=args_chunk(world), halo=partition.DEFAULT_HALO,
+                          kmax=KMAX, min_repeats=MIN_REPEATS, min_span=MIN_SPAN)
+    mine = plan.units_of(rank)
+    starts, lens, own_lo, own_hi = plan.load_args(rank, offsets)
+    if world == 1:
+        own_lo = own_hi = None                      # whole records: nothing to own or stitch
+    knobs = {"words_per_thread": args.words_per_thread} if args.words_per_thread else {}
+
+    seq = ctx.load_ranges(bases.data_ptr(), starts, lens, own_lo, own_hi, max_motif_cap=KMAX, on_device=True)
+    info = seq.info()
+    unit_len = torch.from_numpy(lens.astype(np.int64)).to(dev)
+    unit_open_ok = torch.tensor([u.d1 < u.rec_len for u in mine], dtype=torch.bool, device=dev)
+    unit_d0 = torch.tensor([u.d0 for u in mine], dtype=torch.int32, device=dev)
+    unit_rec = torch.tensor([u.record for u in mine], dtype=torch.int32, device=dev)
+
+    def one_step():
+        return seq.scan(KMIN, KMAX, MIN_REPEATS, MIN_SPAN, **knobs)
+
+    def gather_to_rank0(n):
+        """N > 1: compacted results -> rank 0 (the only collective of the path); runs that left their unit's
+        data (longer than the halo) are stitched first.  Returns the whole-job result count."""
+        if world == 1:
+            return n
+        rec = torch.empty(n, dtype=torch.int32, device=dev)
+        st, en, kk = torch.empty_like(rec), torch.empty_like(rec), torch.empty_like(rec)
+        seq.fetch_device(rec.data_ptr(), st.data_ptr(), en.data_ptr(), kk.data_ptr(), n)
+        ul = rec.long()
+        is_open = (en.long() == unit_len[ul]) & unit_open_ok[ul]
+        flag = torch.tensor([int(is_open.any().item())], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        g_rec, g_st, g_en = unit_rec[ul], st + unit_d0[ul], en + unit_d0[ul]
+        if int(flag.item()):                       # rare: a repeat longer than the halo crossed a unit end
+            idx = torch.nonzero(is_open).flatten()
+            open_mine = [tuple(int(x) for x in row) for row in
+                         torch.stack([g_rec[idx], g_st[idx], g_en[idx], kk[idx]], 1).cpu().tolist()]
+            parts = [None] * world
+            dist.all_gather_object(parts, open_mine)
+            open_all = [x for part in parts for x in part]
+
+            def exchange(ans):
+                out = [None] * world
+                dist.all_gather_object(out, ans)
+                merged = {}
+                for part in out:
+                    merged.update(part)
+                return merged
+            fixed = partition.stitch(plan, open_all, lambda unit, lp, k: seq.run_end(unit.index - plan.bounds[rank], lp, k),
+                                     exchange, rank)
+            mine_fixed = {(r_, s_, k_): e_ for (r_, s_, e_, k_) in fixed}
+            for j in idx.tolist():
+                key = (int(g_rec[j]), int(g_st[j]), int(kk[j]))
+                g_en[j] = mine_fixed[key]
+        packed = torch.stack([g_rec, g_st, g_en, kk])
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev))
+        counts = [int(c.item()) for c in counts]
+        mx = max(counts)
+        pad = torch.zeros((4, mx), dtype=torch.int32, device=dev)
+        pad[:, :n] = packed
+        out = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, out, dst=0)     # rank order == genome order: concatenation is the sorted result
+        return sum(counts)
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        n_res = one_step()
+        gather_to_rank0(n_res)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, scan_ms, launches = [], [], 0
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        n_res = one_step()
+        st_ = seq.stats()
+        kernel_ms.append(st_.kernel_ms)
+        scan_ms.append(st_.scan_ms)
+        launches += st_.launches
+        total_results = gather_to_rank0(n_res)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    time.sleep(0.3)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        dist.barrier()
+    ms_per_step = elapsed_ms / args.steps
+    value = total_bp / (ms_per_step * 1e-3) / 1e9
+    stats = seq.stats()
+
+    # ---- end to end: host buffers in, results out, every step ----
+    e2e = None
+    span_lo, span_hi = int(starts.min()), int((starts + lens).max())   # this rank's contiguous share (+halo)
+    host = torch.empty(span_hi - span_lo, dtype=torch.uint8, pin_memory=True)
+    host.copy_(bases[span_lo:span_hi])
+    h_starts = starts - np.uint64(span_lo)
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+    e2e_times = []
+    d2h = 0
+    for i in range(1 + args.e2e_steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with ctx.load_ranges(host_np, h_starts, lens, own_lo, own_hi, max_motif_cap=KMAX, on_device=False) as s2:
+            n2 = s2.scan(KMIN, KMAX, MIN_REPEATS, MIN_SPAN, **knobs)
+            out = s2.fetch(n2)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        d2h = 16 * n2
+        if i > 0:
+            e2e_times.append(dt)
+    e2e_dt = float(np.mean(e2e_times))
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+        tb = torch.tensor([float(host.numel()), float(d2h)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        h2d_total, d2h_total = int(tb[0].item()), int(tb[1].item())
+    else:
+        h2d_total, d2h_total = host.numel(), d2h
+    e2e = {"value": total_bp / e2e_dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d_total,
+           "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_dt * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (scan_kernel) ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    import ctypes
+    tools = ctypes.CDLL(os.path.join(ROOT, "colab-repeat-finder_b200", "crf_b200", "libcrf_tools.so"))
+    ops = ctypes.c_double()
+    tools.crf_tools_alu_peak(local_rank, ctypes.byref(ops), None)
+    alu_peak_tops = ops.value / 1e12
+    k_ms = float(np.mean(kernel_ms))
+    my_bp = int(sum(u.d1 - u.d0 for u in mine))
+    n_k = KMAX - KMIN + 1
+    alg_bytes = (my_bp + 3) // 4 + (my_bp + 7) // 8 + 12 * int(stats.n_results)
+    alg_ops = 6 * ((my_bp + 31) // 32) * n_k
+    hbm_ach = alg_bytes / (k_ms * 1e-3) / 1e9
+    int_ach = alg_ops / (k_ms * 1e-3) / 1e12
+    t_hbm = alg_bytes / (hbm_peak * 1e9)
+    t_int = alg_ops / (alu_peak_tops * 1e12)
+    bound_int = t_int >= t_hbm
+    roofline = {
+        "bound": "int32-alu" if bound_int else "hbm",
+        "achieved": int_ach if bound_int else hbm_ach,
+        "peak": alu_peak_tops if bound_int else hbm_peak,
+        "unit": "Tops/s" if bound_int else "GB/s",
+        "frac": (int_ach / alu_peak_tops) if bound_int else (hbm_ach / hbm_peak),
+        "traffic": None,
+        "kernel": "crf::scan_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+        "algorithmic_ops_per_launch": alg_ops, "algorithmic_bytes_per_launch": alg_bytes,
+        "peak_source": "INT32 ALU pipe (LOP3+SHF) measured live by crf_tools_alu_peak" if bound_int else hbm_src,
+        "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": hbm_src},
+        "stated_roofline_ms": max(t_hbm, t_int) * 1e3,
+        "note": "stated roofline = slower of one pass of packed bytes at HBM peak and 6 INT32 ops per 32-base word "
+                "per motif size at the ALU-pipe peak (SURVEY.md 8d); no tensor-core work on this path",
+    }
+
+    # ---- CPU baseline on a bounded sample of the same workload + parity on that sample ----
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = 0 if len(lengths) == 1 else 20          # chr21 of S38 (46.7 Mbp x 50 motif sizes)
+        sample = bases[int(offsets[r]):int(offsets[r + 1])].cpu().numpy()
+        res = cpu_baseline_run(sample)
+        rec, st, en, kk = seq.fetch(int(stats.n_results))
+        unit_of_r = [i for i, u in enumerate(mine) if u.record == r]
+        parity = None
+        if len(unit_of_r) == 1:                      # record scanned as one unit: compare row by row
+            sel = rec == unit_of_r[0]
+            o_s, o_e, o_m = res["rows"]
+            parity = bool(np.array_equal(st[sel], o_s) and np.array_equal(en[sel], o_e) and
+                          np.array_equal(kk[sel], o_m))
+        from oracle import oracle
+        cpu = {"value": res["bp"] / res["seconds"] / 1e9, "unit": "Gbp/s", "cores": res["threads"], "kind": "port",
+               "sample": f"record {r} of the workload, {res['bp']} bp x {n_k} motif sizes, {res['seconds']:.2f} s; "
+                         f"C port of the reference's tracker loop (oracle/crf_oracle.c), one thread per motif size, "
+                         f"host has {oracle.max_threads()} cores",
+               "parity_on_sample": parity}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": meta["workload"], "motif_sizes": [KMIN, KMAX], "min_repeats": MIN_REPEATS,
+                   "min_span": MIN_SPAN, "total_bp": total_bp, "results_per_step": int(total_results),
+                   "l2": "inputs larger than L2 (packed planes %.0f MB per GPU)" % (info.packed_bytes / 1e6),
+                   "partition": f"{len(plan.units)} (record, chunk) units over {world} rank(s)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "scan_stats": {"scan_ms": float(np.mean(scan_ms)), "kernel_ms": k_ms, "candidates": int(stats.n_candidates),
+                       "long_runs": int(stats.n_long), "spilled": int(stats.n_spilled), "tiles": int(stats.n_tiles)},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def args_chunk(world):
+    from crf_b200 import partition
+    return partition.DEFAULT_CHUNK if world > 1 else (1 << 62)   # one GPU: whole records, nothing to stitch
+
+
+if __name__ == "__main__":
+    main()

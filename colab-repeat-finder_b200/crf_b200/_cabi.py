@@ -18,7 +18,7 @@ CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_C
 #: every symbol include/crf.h declares (tests check the library exports all of them)
 EXPORTS = [
     "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
-    "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
+    "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
     "crf_scan_stats", "crf_run_end",
 ]
 
@@ -70,6 +70,7 @@ def lib():
         L.crf_ctx_set_stream.argtypes = [vp, vp]
         L.crf_ctx_synchronize.argtypes = [vp]
         L.crf_seq_load_ascii.argtypes = [vp, vp, vp, u32, u32, i, P(vp)]
+        L.crf_seq_load_ascii_ranges.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, i, P(vp)]
         L.crf_seq_destroy.argtypes = [vp]
         L.crf_seq_info.argtypes = [vp, P(SeqInfo)]
         L.crf_scan.argtypes = [vp, P(ScanParams), P(u64)]
@@ -115,6 +116,11 @@ class Context:
         offsets: uint64 array of n_records+1 record boundaries (default: one record)."""
         return Sequence(self, bases, offsets, max_motif_cap, on_device)
 
+    def load_ranges(self, bases, starts, lengths, own_lo=None, own_hi=None, max_motif_cap=50, on_device=False):
+        """Records given as (start, length) ranges of `bases` (may overlap); optional owned
+        sub-range per record (crf_seq_load_ascii_ranges)."""
+        return Sequence(self, bases, None, max_motif_cap, on_device, ranges=(starts, lengths, own_lo, own_hi))
+
     def close(self):
         if self._h:
             lib().crf_ctx_destroy(self._h)
@@ -130,13 +136,13 @@ class Context:
 class Sequence:
     """Records resident in HBM as packed planes (crf_seq)."""
 
-    def __init__(self, ctx, bases, offsets, max_motif_cap, on_device):
+    def __init__(self, ctx, bases, offsets, max_motif_cap, on_device, ranges=None):
         self.ctx = ctx
         self._h = ctypes.c_void_p()
         keep = None
         if on_device:
             ptr = int(bases)
-            if offsets is None:
+            if offsets is None and ranges is None:
                 raise ValueError("offsets are required with a device pointer")
         else:
             if isinstance(bases, np.ndarray):
@@ -149,8 +155,21 @@ class Sequence:
                 keep = bytes(bases) if not isinstance(bases, bytes) else bases
                 ptr = ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p).value or 0
                 nbytes = len(keep)
-            if offsets is None:
+            if offsets is None and ranges is None:
                 offsets = np.array([0, nbytes], dtype=np.uint64)
+        if ranges is not None:
+            starts, lengths, own_lo, own_hi = (None if a is None else np.ascontiguousarray(a, dtype=np.uint64)
+                                               for a in ranges)
+            if starts.shape != lengths.shape or starts.ndim != 1:
+                raise ValueError("starts and lengths must be 1-d arrays of equal size")
+            self.n_records = starts.size
+            self.lengths = lengths
+            _check(lib().crf_seq_load_ascii_ranges(
+                ctx._h, ctypes.c_void_p(ptr), ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(lengths.ctypes.data),
+                ctypes.c_void_p(own_lo.ctypes.data if own_lo is not None else 0),
+                ctypes.c_void_p(own_hi.ctypes.data if own_hi is not None else 0),
+                self.n_records, int(max_motif_cap), int(bool(on_device)), ctypes.byref(self._h)))
+            return
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         if offsets.ndim != 1 or offsets.size < 2:
             raise ValueError("offsets must hold n_records + 1 entries")

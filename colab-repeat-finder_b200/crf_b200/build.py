@@ -11,22 +11,33 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-shared", "-Xcompiler", "-fPIC"]
 
 
-def _stale():
-    if not os.path.exists(OUT):
+TOOLS_OUT = os.path.join(_HERE, "libcrf_tools.so")   # bench-only helpers (INT32 peak micro-benchmark)
+TOOLS_SOURCES = ["crf_tools.cu"]
+
+
+def _stale(out, deps):
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    deps.append(os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "crf.h"))
+    t = os.path.getmtime(out)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
-        return OUT
+def _nvcc(out, sources, verbose):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
-          [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
+          [os.path.join(CSRC, f) for f in sources]
     subprocess.check_call(cmd)
+
+
+def build(force=False, verbose=False):
+    """libcrf.so (the product) and libcrf_tools.so (bench helpers)."""
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps.append(os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "crf.h"))
+    if force or _stale(OUT, deps):
+        _nvcc(OUT, SOURCES, verbose)
+    tdeps = [os.path.join(CSRC, f) for f in TOOLS_SOURCES]
+    if force or _stale(TOOLS_OUT, tdeps):
+        _nvcc(TOOLS_OUT, TOOLS_SOURCES, verbose)
     return OUT
 
 

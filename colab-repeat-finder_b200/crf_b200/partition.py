@@ -1,0 +1,184 @@
+"""Partitioning a genome over 1/2/4/8 GPUs and stitching the runs that leave a partition.
+
+The B200-native analogue of the reference's scale-out (hail_batch_pipeline/run_hail_batch_pipeline.py:
+76-77, 115-123, 153: 500 kb intervals, one CPU job each, `sort | uniq` + merge afterwards).  Here the
+result is exact by construction, so no uniq/merge pass exists:
+
+  * a record is cut into fixed-size chunks ("units"); unit = owned range [u0, u1) plus one base of
+    left context and `halo` bases on the right, data range [d0, d1);
+  * contiguous runs of units go to ranks, balanced by base pairs;
+  * a rank scans all its units in one launch; a repeat is reported by the unit that owns its
+    START (the kernel drops other starts) and followed to its end inside the unit's data;
+  * only a repeat that reaches the end of its unit's data (i.e. longer than the halo) is
+    "right-open"; its true end is found by asking the unit that owns the position where
+    knowledge stopped (crf_run_end), hopping unit to unit if it is longer still.
+
+M_k[j] depends on S[j] and S[j+k] only, so the match masks inside a unit are exact wherever both
+bases are present; the halo only has to cover one qualifying repeat (max(min_span, min_repeats*kmax)).
+"""
+from collections import namedtuple
+
+import numpy as np
+
+Unit = namedtuple("Unit", "index record u0 u1 d0 d1 rec_len")
+
+DEFAULT_CHUNK = 1 << 25     # 33.5 Mbp owned per unit
+DEFAULT_HALO = 1 << 16      # 64 kbp: repeats shorter than this never need stitching
+
+
+class Plan:
+    def __init__(self, lengths, n_ranks, chunk=DEFAULT_CHUNK, halo=DEFAULT_HALO, kmax=50, min_repeats=3, min_span=9):
+        need = max(min_span, min_repeats * kmax) + kmax + 2
+        if halo < need:
+            raise ValueError(f"halo {halo} is shorter than one qualifying repeat of the largest motif ({need})")
+        if chunk < 1:
+            raise ValueError("chunk must be positive")
+        self.lengths = [int(x) for x in lengths]
+        self.n_ranks = n_ranks
+        self.chunk, self.halo = chunk, halo
+        units = []
+        for r, length in enumerate(self.lengths):
+            if length == 0:
+                continue
+            for u0 in range(0, length, chunk):
+                u1 = min(length, u0 + chunk)
+                units.append(Unit(len(units), r, u0, u1, max(0, u0 - 1), min(length, u1 + halo), length))
+        self.units = units
+        # contiguous split balanced by owned base pairs
+        owned = np.array([u.u1 - u.u0 for u in units], dtype=np.int64)
+        csum = np.concatenate([[0], np.cumsum(owned)])
+        total = int(csum[-1])
+        bounds = [0]
+        for i in range(1, n_ranks):
+            target = total * i / n_ranks
+            j = int(np.searchsorted(csum, target, side="left"))
+            if j > 0 and abs(csum[j - 1] - target) <= abs(csum[min(j, len(units))] - target):
+                j -= 1
+            bounds.append(min(max(j, bounds[-1]), len(units)))
+        bounds.append(len(units))
+        self.bounds = bounds
+        self._first_of_record = {}
+        for u in units:
+            self._first_of_record.setdefault(u.record, u.index)
+
+    def units_of(self, rank):
+        return self.units[self.bounds[rank]:self.bounds[rank + 1]]
+
+    def rank_of_unit(self, index):
+        return int(np.searchsorted(np.array(self.bounds[1:]), index, side="right"))
+
+    def unit_owning(self, record, pos):
+        first = self._first_of_record[record]
+        return self.units[first + pos // self.chunk]
+
+    def load_args(self, rank, record_starts):
+        """(starts, lengths, own_lo, own_hi) for Context.load_ranges; record_starts[r] = offset of
+        record r inside the caller's base buffer."""
+        mine = self.units_of(rank)
+        starts = np.array([int(record_starts[u.record]) + u.d0 for u in mine], dtype=np.uint64)
+        lens = np.array([u.d1 - u.d0 for u in mine], dtype=np.uint64)
+        own_lo = np.array([u.u0 - u.d0 for u in mine], dtype=np.uint64)
+        own_hi = np.array([u.u1 - u.d0 for u in mine], dtype=np.uint64)
+        return starts, lens, own_lo, own_hi
+
+
+def localize(plan, rank, unit_local, start, end, k):
+    """Per-unit results of one rank -> record coordinates + the right-open subset.
+
+    Returns (record, start, end, k, open_mask): open_mask marks runs that reached the end of their
+    unit's data although the record continues (their `end` is a lower bound)."""
+    mine = plan.units_of(rank)
+    if len(mine) == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z, z, np.zeros(0, dtype=bool)
+    d0 = np.array([u.d0 for u in mine], dtype=np.int64)
+    d1 = np.array([u.d1 for u in mine], dtype=np.int64)
+    rec = np.array([u.record for u in mine], dtype=np.int64)
+    rlen = np.array([u.rec_len for u in mine], dtype=np.int64)
+    ul = np.asarray(unit_local, dtype=np.int64)
+    g_start = np.asarray(start, dtype=np.int64) + d0[ul]
+    g_end = np.asarray(end, dtype=np.int64) + d0[ul]
+    open_mask = (g_end == d1[ul]) & (d1[ul] < rlen[ul])
+    return rec[ul], g_start, g_end, np.asarray(k, dtype=np.int64), open_mask
+
+
+def stitch(plan, open_runs, run_end_fn, exchange_fn=None, rank=0):
+    """Finish right-open runs.
+
+    open_runs : list of (record, start, end_lower_bound, k) -- the same list on every rank.
+    run_end_fn(unit, local_pos, k) -> local run end, callable for units of *this* rank only.
+    exchange_fn(dict) -> merged dict over ranks (None on a single rank).
+    Returns the list of (record, start, end, k) with true ends, in input order."""
+    pending = {i: (rec, end - k, k) for i, (rec, _s, end, k) in enumerate(open_runs)}   # position p: M_k[p] unknown
+    final_i0 = {}
+    while pending:
+        answers = {}
+        for i, (rec, p, k) in pending.items():
+            unit = plan.unit_owning(rec, p)
+            if plan.rank_of_unit(unit.index) == rank:
+                answers[i] = int(run_end_fn(unit, p - unit.d0, k)) + unit.d0
+        if exchange_fn is not None:
+            answers = exchange_fn(answers)
+        nxt = {}
+        for i, (rec, p, k) in pending.items():
+            e = answers[i]
+            unit = plan.unit_owning(rec, p)
+            if e + k == unit.d1 and unit.d1 < unit.rec_len and e > p:
+                nxt[i] = (rec, e, k)       # still inside a run at the end of this unit's data: hop on
+            else:
+                final_i0[i] = e
+        pending = nxt
+    return [(rec, s, final_i0[i] + k, k) for i, (rec, s, _e, k) in enumerate(open_runs)]
+
+
+def scan_partitioned(ctx, bases, record_starts, lengths, kmin, kmax, min_repeats, min_span, rank=0, world=1,
+                     chunk=DEFAULT_CHUNK, halo=DEFAULT_HALO, on_device=False, dist=None, **knobs):
+    """Scan `lengths` records split over `world` ranks; every rank returns the full, stitched,
+    (record, start, end)-sorted result as numpy arrays (record, start, end, k).
+
+    dist: torch.distributed (initialised) when world > 1; results travel with all_gather_object
+    (bench.py uses a device-side gather instead)."""
+    plan = Plan(lengths, world, chunk, halo, kmax, min_repeats, min_span)
+    starts, lens, own_lo, own_hi = plan.load_args(rank, record_starts)
+    mine = plan.units_of(rank)
+    if len(mine):
+        seq = ctx.load_ranges(bases, starts, lens, own_lo, own_hi, max_motif_cap=kmax, on_device=on_device)
+        n = seq.scan(kmin, kmax, min_repeats, min_span, **knobs)
+        ul, st, en, kk = seq.fetch(n)
+    else:
+        seq = None
+        ul = st = en = kk = np.zeros(0, dtype=np.uint32)
+    rec, g_st, g_en, g_k, open_mask = localize(plan, rank, ul, st, en, kk)
+    open_mine = [(int(a), int(b), int(c), int(d)) for a, b, c, d in
+                 zip(rec[open_mask], g_st[open_mask], g_en[open_mask], g_k[open_mask])]
+    closed = np.stack([rec[~open_mask], g_st[~open_mask], g_en[~open_mask], g_k[~open_mask]]) if len(rec) else \
+        np.zeros((4, 0), dtype=np.int64)
+
+    def gather_obj(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    open_all = [x for part in gather_obj(open_mine) for x in part]
+
+    def run_end_fn(unit, local_pos, k):
+        return seq.run_end(unit.index - plan.bounds[rank], local_pos, k)
+
+    def exchange(answers):
+        merged = {}
+        for part in gather_obj(answers):
+            merged.update(part)
+        return merged
+
+    stitched = stitch(plan, open_all, run_end_fn, exchange if world > 1 else None, rank)
+    parts = gather_obj(closed)
+    rows = np.concatenate(parts, axis=1) if parts else closed
+    if stitched:
+        rows = np.concatenate([rows, np.array(stitched, dtype=np.int64).T], axis=1)
+        order = np.lexsort((rows[2], rows[1], rows[0]))
+        rows = rows[:, order]
+    if seq is not None:
+        seq.close()
+    return rows[0], rows[1], rows[2], rows[3]

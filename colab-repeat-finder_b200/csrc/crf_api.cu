@@ -53,7 +53,7 @@ struct crf_seq {
     uint32_t n_records = 0;
     uint32_t layout_len = 0, n_words = 0, n_words_alloc = 0, cap = 0;
     uint32_t *H = nullptr, *L = nullptr, *NM = nullptr, *X = nullptr;
-    uint32_t *d_rec_dev_off = nullptr;
+    uint32_t *d_rec_dev_off = nullptr, *d_own_lo = nullptr, *d_own_hi = nullptr;
     std::vector<uint32_t> h_rec_dev_off;
     std::vector<uint64_t> h_rec_len;
     uint64_t *ex_key = nullptr;
@@ -167,7 +167,7 @@ static void free_seq(crf_seq *s) {
     if (!s) return;
     if (s->ctx) cudaSetDevice(s->ctx->device);
     dev_free(s->H); dev_free(s->L); dev_free(s->NM); dev_free(s->X);
-    dev_free(s->d_rec_dev_off); dev_free(s->ex_key); dev_free(s->d_ktab);
+    dev_free(s->d_rec_dev_off); dev_free(s->d_own_lo); dev_free(s->d_own_hi); dev_free(s->ex_key); dev_free(s->d_ktab);
     dev_free(s->stage_key); dev_free(s->spill_key); dev_free(s->fin_key);
     dev_free(s->stage_k); dev_free(s->spill_k); dev_free(s->fin_k);
     dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
@@ -183,8 +183,9 @@ static const uint32_t EX_CAP = 1u << 22;       // exotic symbols kept per load
 static const uint32_t TILE_WORDS_MAX = 4096;   // THREADS * 16
 static const uint32_t MAX_K = 65535;
 
-static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
-                     uint32_t max_motif_cap, int on_device, crf_seq *s) {
+static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, const uint64_t *lengths,
+                     const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
+                     int on_device, crf_seq *s) {
     cudaStream_t st = c->stream;
     s->ctx = c;
     s->n_records = n_records;
@@ -196,41 +197,65 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, 
     // layout: record r at dev_off[r], followed by a gap of max_motif_cap masked positions
     s->h_rec_dev_off.resize(n_records);
     s->h_rec_len.resize(n_records);
-    uint64_t pos = 0;
-    const uint64_t total = offsets[n_records] - offsets[0];
+    std::vector<uint32_t> len32(n_records);
+    uint64_t pos = 0, total = 0, src_lo = ~0ull, src_hi = 0;
+    const uint64_t limit = 0xFFFFFFFFull - 32ull * (2ull * TILE_WORDS_MAX + (max_motif_cap >> 5) + 64);
     for (uint32_t r = 0; r < n_records; ++r) {
-        if (offsets[r + 1] < offsets[r]) { set_err("crf_seq_load_ascii: offsets must be non-decreasing"); return CRF_ERR_ARG; }
-        const uint64_t len = offsets[r + 1] - offsets[r];
-        if (pos > 0xFFFFFFFFull) break;
+        const uint64_t len = lengths[r];
+        if (pos > limit || len > limit) { pos = limit + 1; break; }
         s->h_rec_dev_off[r] = (uint32_t)pos;
         s->h_rec_len[r] = len;
+        len32[r] = (uint32_t)len;
         pos += len + max_motif_cap;
+        total += len;
+        if (len) {
+            src_lo = std::min(src_lo, starts[r]);
+            src_hi = std::max(src_hi, starts[r] + len);
+        }
     }
-    const uint64_t limit = 0xFFFFFFFFull - 32ull * (2ull * TILE_WORDS_MAX + (max_motif_cap >> 5) + 64);
     if (pos > limit) {
-        set_err("crf_seq_load_ascii: %llu layout positions exceed the per-load limit of %llu; split the records over "
-                "several loads", (unsigned long long)pos, (unsigned long long)limit);
+        set_err("crf_seq_load_ascii: the records need more than %llu layout positions (per-load limit); split them "
+                "over several loads", (unsigned long long)limit);
         return CRF_ERR_UNSUPPORTED;
     }
+    if (src_lo > src_hi) src_lo = src_hi = 0;
     s->layout_len = (uint32_t)pos;
     s->n_words = (s->layout_len + 31) / 32;
     s->n_words_alloc = (s->n_words + TILE_WORDS_MAX - 1) / TILE_WORDS_MAX * TILE_WORDS_MAX + (max_motif_cap >> 5) + 8;
 
     CU(cudaEventRecord(s->ev[0], st));
-    const uint8_t *d_src = bases;
+    const uint8_t *d_src = bases;   // device view; record r starts at d_src[starts[r] - src_base]
+    uint64_t src_base = 0;
     uint8_t *d_src_own = nullptr;
-    uint64_t *d_src_off = nullptr;
-    if (!on_device) {
-        CHECK(dev_alloc(&d_src_own, (size_t)total));
-        if (total) CU(cudaMemcpyAsync(d_src_own, bases + offsets[0], total, cudaMemcpyHostToDevice, st));
+    uint64_t *d_src_start = nullptr;
+    uint32_t *d_len = nullptr;
+    if (!on_device) {               // one H2D copy of the span the records cover (units may overlap)
+        CHECK(dev_alloc(&d_src_own, (size_t)(src_hi - src_lo)));
+        if (src_hi > src_lo) CU(cudaMemcpyAsync(d_src_own, bases + src_lo, src_hi - src_lo, cudaMemcpyHostToDevice, st));
         d_src = d_src_own;
-    } else {
-        d_src = bases + offsets[0];
+        src_base = src_lo;
     }
-    std::vector<uint64_t> rel(n_records + 1);
-    for (uint32_t r = 0; r <= n_records; ++r) rel[r] = offsets[r] - offsets[0];
-    int rc = dev_alloc(&d_src_off, (size_t)n_records + 1);
+    std::vector<uint64_t> rel(n_records);
+    for (uint32_t r = 0; r < n_records; ++r) rel[r] = s->h_rec_len[r] ? starts[r] - src_base : 0;
+    std::vector<uint32_t> olo, ohi;
+    if (own_lo && own_hi) {
+        olo.resize(n_records);
+        ohi.resize(n_records);
+        for (uint32_t r = 0; r < n_records; ++r) {
+            if (own_lo[r] > own_hi[r] || own_hi[r] > lengths[r]) {
+                set_err("crf_seq_load_ascii_ranges: own range of record %u is not inside the record", r);
+                if (d_src_own) cudaFree(d_src_own);
+                return CRF_ERR_ARG;
+            }
+            olo[r] = s->h_rec_dev_off[r] + (uint32_t)own_lo[r];
+            ohi[r] = s->h_rec_dev_off[r] + (uint32_t)own_hi[r];
+        }
+    }
+    int rc = dev_alloc(&d_src_start, n_records);
+    if (!rc) rc = dev_alloc(&d_len, n_records);
     if (!rc) rc = dev_alloc(&s->d_rec_dev_off, n_records);
+    if (!rc && !olo.empty()) rc = dev_alloc(&s->d_own_lo, n_records);
+    if (!rc && !olo.empty()) rc = dev_alloc(&s->d_own_hi, n_records);
     if (!rc) rc = dev_alloc(&s->H, s->n_words_alloc);
     if (!rc) rc = dev_alloc(&s->L, s->n_words_alloc);
     if (!rc) rc = dev_alloc(&s->NM, s->n_words_alloc);
@@ -239,23 +264,28 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, 
     if (!rc) rc = dev_alloc(&s->ex_key, s->ex_cap);
     cudaError_t e = cudaSuccess;
     if (!rc) {
-        e = cudaMemcpyAsync(d_src_off, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess && n_records)
-            e = cudaMemcpyAsync(s->d_rec_dev_off, s->h_rec_dev_off.data(), (size_t)n_records * 4, cudaMemcpyHostToDevice, st);
+        const size_t n4 = (size_t)n_records * 4;
+        e = cudaMemcpyAsync(d_src_start, rel.data(), (size_t)n_records * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_len, len32.data(), n4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_rec_dev_off, s->h_rec_dev_off.data(), n4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && !olo.empty()) e = cudaMemcpyAsync(s->d_own_lo, olo.data(), n4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && !olo.empty()) e = cudaMemcpyAsync(s->d_own_hi, ohi.data(), n4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st);
     }
     if (!rc && e == cudaSuccess) {
         PackParams pp;
-        pp.src = d_src; pp.rec_src_off = d_src_off; pp.rec_dev_off = s->d_rec_dev_off; pp.n_records = n_records;
+        pp.src = d_src; pp.rec_src_start = d_src_start; pp.rec_len = d_len; pp.rec_dev_off = s->d_rec_dev_off;
+        pp.n_records = n_records;
         pp.n_words_alloc = s->n_words_alloc; pp.H = s->H; pp.L = s->L; pp.NM = s->NM; pp.X = s->X;
         pp.ex_key = s->ex_key; pp.ex_cap = s->ex_cap; pp.ex_count = s->d_counters;
         pack_kernel<<<(s->n_words_alloc + 255) / 256, 256, 0, st>>>(pp);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // also keeps rel/len32/olo alive long enough
     }
     if (d_src_own) cudaFree(d_src_own);
-    if (d_src_off) cudaFree(d_src_off);
+    if (d_src_start) cudaFree(d_src_start);
+    if (d_len) cudaFree(d_len);
     if (rc) return rc;
     if (e != cudaSuccess) { set_err("crf_seq_load_ascii: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
 
@@ -281,22 +311,27 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, 
     return CRF_OK;
 }
 
-extern "C" int crf_seq_load_ascii(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
-                                  uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
-    if (!c || !out || !offsets) { set_err("crf_seq_load_ascii: null argument"); return CRF_ERR_ARG; }
+extern "C" int crf_seq_load_ascii_ranges(crf_ctx *c, const uint8_t *bases, const uint64_t *starts,
+                                         const uint64_t *lengths, const uint64_t *own_lo, const uint64_t *own_hi,
+                                         uint32_t n_records, uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
+    if (!c || !out || !starts || !lengths) { set_err("crf_seq_load_ascii: null argument"); return CRF_ERR_ARG; }
     *out = nullptr;
     if (n_records == 0) { set_err("crf_seq_load_ascii: n_records must be >= 1"); return CRF_ERR_ARG; }
-    if (!bases && offsets[n_records] != offsets[0]) { set_err("crf_seq_load_ascii: null bases"); return CRF_ERR_ARG; }
+    if ((own_lo == nullptr) != (own_hi == nullptr)) { set_err("crf_seq_load_ascii_ranges: own_lo and own_hi go together"); return CRF_ERR_ARG; }
     if (max_motif_cap < 1 || max_motif_cap > MAX_K) {
         set_err("crf_seq_load_ascii: max_motif_cap %u not in [1, %u]", max_motif_cap, MAX_K);
         return max_motif_cap < 1 ? CRF_ERR_ARG : CRF_ERR_UNSUPPORTED;
+    }
+    if (!bases) {
+        for (uint32_t r = 0; r < n_records; ++r)
+            if (lengths[r]) { set_err("crf_seq_load_ascii: null bases"); return CRF_ERR_ARG; }
     }
     CU(cudaSetDevice(c->device));
     crf_seq *s = new (std::nothrow) crf_seq;
     if (!s) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
     int rc;
     try {
-        rc = load_impl(c, bases, offsets, n_records, max_motif_cap, bases_on_device, s);
+        rc = load_impl(c, bases, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, bases_on_device, s);
     } catch (const std::bad_alloc &) {
         set_err("out of host memory");
         rc = CRF_ERR_NOMEM;
@@ -304,6 +339,22 @@ extern "C" int crf_seq_load_ascii(crf_ctx *c, const uint8_t *bases, const uint64
     if (rc) { free_seq(s); return rc; }
     *out = s;
     return CRF_OK;
+}
+
+extern "C" int crf_seq_load_ascii(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
+                                  uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
+    if (!offsets) { set_err("crf_seq_load_ascii: null argument"); return CRF_ERR_ARG; }
+    if (n_records == 0) { set_err("crf_seq_load_ascii: n_records must be >= 1"); return CRF_ERR_ARG; }
+    std::vector<uint64_t> lengths;
+    try {
+        lengths.resize(n_records);
+    } catch (const std::bad_alloc &) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    for (uint32_t r = 0; r < n_records; ++r) {
+        if (offsets[r + 1] < offsets[r]) { set_err("crf_seq_load_ascii: offsets must be non-decreasing"); return CRF_ERR_ARG; }
+        lengths[r] = offsets[r + 1] - offsets[r];
+    }
+    return crf_seq_load_ascii_ranges(c, bases, offsets, lengths.data(), nullptr, nullptr, n_records, max_motif_cap,
+                                     bases_on_device, out);
 }
 
 extern "C" int crf_seq_destroy(crf_seq *s) {
@@ -443,6 +494,7 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         sp.H = s->H; sp.L = s->L; sp.NM = s->NM; sp.X = s->X;
         sp.ktab = s->d_ktab;
         sp.ex_key = s->ex_key; sp.n_exotic = s->n_exotic;
+        sp.rec_dev_off = s->d_rec_dev_off; sp.own_lo = s->d_own_lo; sp.own_hi = s->d_own_hi; sp.n_records = s->n_records;
         sp.n_words = s->n_words;
         sp.kmin = pr->min_motif_size; sp.kmax = pr->max_motif_size;
         sp.outcap = outcap;

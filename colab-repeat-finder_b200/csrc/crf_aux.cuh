@@ -7,8 +7,9 @@ namespace crf {
 // ---- pack: ASCII records -> H/L/NM/X planes (replaces input_sequence.upper(), prf:33, and the
 // per-base str compares of trk:53 by a 2-bit code + mask) ---------------------------------------
 struct PackParams {
-    const uint8_t *src;           // all records back to back
-    const uint64_t *rec_src_off;  // n_records + 1
+    const uint8_t *src;           // source bytes; record r = src[rec_src_start[r] .. + rec_len[r])
+    const uint64_t *rec_src_start;
+    const uint32_t *rec_len;
     const uint32_t *rec_dev_off;  // n_records (layout position of each record's first base)
     uint32_t n_records;
     uint32_t n_words_alloc;
@@ -32,9 +33,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     uint64_t src0 = 0;
     uint32_t dev0 = 0, rec_end = 0, next_start = NOPOS;
     if (p.n_records) {
-        src0 = p.rec_src_off[r];
+        src0 = p.rec_src_start[r];
         dev0 = p.rec_dev_off[r];
-        rec_end = dev0 + (uint32_t)(p.rec_src_off[r + 1] - src0);
+        rec_end = dev0 + p.rec_len[r];
         next_start = (r + 1 < p.n_records) ? p.rec_dev_off[r + 1] : NOPOS;
     }
     uint32_t h = 0, l = 0, nm = 0, x = 0;
@@ -43,9 +44,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
         const uint32_t pos = p0 + b;
         if (pos >= next_start) {
             ++r;
-            src0 = p.rec_src_off[r];
+            src0 = p.rec_src_start[r];
             dev0 = p.rec_dev_off[r];
-            rec_end = dev0 + (uint32_t)(p.rec_src_off[r + 1] - src0);
+            rec_end = dev0 + p.rec_len[r];
             next_start = (r + 1 < p.n_records) ? p.rec_dev_off[r + 1] : NOPOS;
         }
         uint32_t code, masked = 1, exo = 0;

@@ -46,6 +46,9 @@ struct ScanParams {
     const KEntry *ktab;
     const uint64_t *ex_key;  // sorted (pos << 8 | letter) of exotic symbols
     uint32_t n_exotic;
+    const uint32_t *rec_dev_off;  // layout position of each record's first base
+    const uint32_t *own_lo, *own_hi;  // per record: layout range of run starts this load owns
+    uint32_t n_records;
     uint32_t n_words;        // words holding layout positions (reads beyond are allocated pads)
     uint32_t kmin, kmax;
     uint32_t outcap;         // per-tile sorted-output slots

@@ -53,6 +53,14 @@ __device__ inline void emit_result(const ScanParams &p, const TileOut &to, uint3
 // A qualifying-run start candidate: M_k[st .. st+known) are ones and M_k[st-1] is zero.
 __device__ inline void handle_start(const ScanParams &p, const TileOut &to, const KEntry &ke, uint32_t k,
                                     uint32_t st, uint32_t known) {
+    if (p.own_lo) {  // partitioned load: a run belongs to the unit that owns its start
+        uint32_t lo = 0, hi = p.n_records - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (__ldg(p.rec_dev_off + mid) <= st) lo = mid; else hi = mid - 1;
+        }
+        if (st < __ldg(p.own_lo + lo) || st >= __ldg(p.own_hi + lo)) return;
+    }
     uint32_t i0;
     bool found = walk_run(p, k, st + known, p.walk_limit, &i0);
     while (!found && i0 - st < ke.rmin) found = walk_run(p, k, i0, p.walk_limit, &i0);

@@ -55,6 +55,13 @@ int crf_ctx_synchronize(crf_ctx *ctx);
  */
 int crf_seq_load_ascii(crf_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
                        uint32_t max_motif_cap, int bases_on_device, crf_seq **seq);
+/* Same, with each record given as its own (start, length) range of `bases` (ranges may overlap:
+ * partition units share their halo) and, optionally, the sub-range [own_lo, own_hi) of each record
+ * whose run STARTS this load reports (NULL, NULL = whole records).  A run that starts in the owned
+ * range is followed to its end anywhere in the record.  See DESIGN.md "Multi-GPU". */
+int crf_seq_load_ascii_ranges(crf_ctx *ctx, const uint8_t *bases, const uint64_t *starts, const uint64_t *lengths,
+                              const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records,
+                              uint32_t max_motif_cap, int bases_on_device, crf_seq **seq);
 int crf_seq_destroy(crf_seq *seq);
 
 typedef struct {
