@@ -60,7 +60,8 @@ struct crf_seq {
     uint32_t n_exotic = 0, ex_cap = 0;
     // scan scratch
     KEntry *d_ktab = nullptr;
-    uint32_t ktab_cap = 0;
+    Seg *d_segs = nullptr;
+    uint32_t ktab_cap = 0, segs_cap = 0, n_segs = 0;
     crf_scan_params ktab_for = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t *stage_key = nullptr, *spill_key = nullptr, *fin_key = nullptr;
     uint16_t *stage_k = nullptr, *spill_k = nullptr, *fin_k = nullptr;
@@ -167,7 +168,7 @@ static void free_seq(crf_seq *s) {
     if (!s) return;
     if (s->ctx) cudaSetDevice(s->ctx->device);
     dev_free(s->H); dev_free(s->L); dev_free(s->NM); dev_free(s->X);
-    dev_free(s->d_rec_dev_off); dev_free(s->d_own_lo); dev_free(s->d_own_hi); dev_free(s->ex_key); dev_free(s->d_ktab);
+    dev_free(s->d_rec_dev_off); dev_free(s->d_own_lo); dev_free(s->d_own_hi); dev_free(s->ex_key); dev_free(s->d_ktab); dev_free(s->d_segs);
     dev_free(s->stage_key); dev_free(s->spill_key); dev_free(s->fin_key);
     dev_free(s->stage_k); dev_free(s->spill_k); dev_free(s->fin_k);
     dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
@@ -372,8 +373,9 @@ extern "C" int crf_seq_info(const crf_seq *s, crf_seq_info_t *info) {
 }
 
 // ---- scan ---------------------------------------------------------------------------------------
-static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab) {
+static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab, std::vector<Seg> &segs) {
     tab.assign((size_t)pr.max_motif_size + 1, KEntry{});
+    static const uint32_t UMASK[6] = {0xFFFFFFFFu, 0x55555555u, 0x11111111u, 0x01010101u, 0x00010001u, 0x00000001u};
     for (uint32_t k = 1; k <= pr.max_motif_size; ++k) {
         KEntry &e = tab[k];
         // r_min: trk:86 and trk:91 in closed form
@@ -381,7 +383,10 @@ static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab) {
         const uint64_t b = (uint64_t)(pr.min_repeats - 1) * k;
         const uint64_t rmin = std::max<uint64_t>(std::max(a, b), 1);
         e.rmin = (uint32_t)std::min<uint64_t>(rmin, 0xFFFFFF00u);
-        e.rexact = std::min<uint32_t>(e.rmin, 32);
+        uint32_t ulog = 0;  // largest u = 2^ulog <= 32 with 2u - 1 <= r_min
+        while (ulog < 5 && 2 * (2u << ulog) - 1 <= e.rmin) ++ulog;
+        e.ulog = ulog;
+        e.umask = UMASK[ulog];
         if (e.rmin >= 63) e.mode = MODE_WORD;
         else if (e.rmin >= 31) e.mode = MODE_HALF;
         else if (e.rmin >= 15) e.mode = MODE_BYTE;
@@ -407,6 +412,20 @@ static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab) {
         if (pr.flags & CRF_SCAN_NO_PRIMITIVITY)
             for (int j = 0; j < 6; ++j) e.div[j] = 0;
     }
+    // segments: maximal k ranges with the same k >> 5 and the same fast-phase filter
+    segs.clear();
+    for (uint32_t k = pr.min_motif_size; k <= pr.max_motif_size; ++k) {
+        const KEntry &e = tab[k];
+        if (!segs.empty()) {
+            Seg &g = segs.back();
+            if ((uint32_t)(g.k_hi >> 5) == (k >> 5) && g.mode == e.mode && g.sh0 == e.sh[0] && g.sh1 == e.sh[1] &&
+                g.sh2 == e.sh[2]) {
+                g.k_hi = (uint16_t)k;
+                continue;
+            }
+        }
+        segs.push_back(Seg{(uint16_t)k, (uint16_t)k, e.mode, e.sh[0], e.sh[1], e.sh[2]});
+    }
 }
 
 static int ensure_result_buffers(crf_seq *s, uint32_t cap) {
@@ -416,7 +435,7 @@ static int ensure_result_buffers(crf_seq *s, uint32_t cap) {
     dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
     s->res_cap = 0;
     CHECK(dev_alloc(&s->stage_key, cap)); CHECK(dev_alloc(&s->stage_k, cap));
-    CHECK(dev_alloc(&s->spill_key, cap)); CHECK(dev_alloc(&s->spill_k, cap));
+    CHECK(dev_alloc(&s->spill_key, next_pow2(cap))); CHECK(dev_alloc(&s->spill_k, next_pow2(cap)));
     CHECK(dev_alloc(&s->fin_key, cap)); CHECK(dev_alloc(&s->fin_k, cap));
     CHECK(dev_alloc(&s->o_rec, cap)); CHECK(dev_alloc(&s->o_start, cap));
     CHECK(dev_alloc(&s->o_end, cap)); CHECK(dev_alloc(&s->o_k, cap));
@@ -463,11 +482,21 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         s->ktab_for.max_motif_size = 0;
     }
     if (s->ktab_for.max_motif_size != pr->max_motif_size || s->ktab_for.min_repeats != pr->min_repeats ||
-        s->ktab_for.min_span != pr->min_span || s->ktab_for.flags != pr->flags) {
+        s->ktab_for.min_span != pr->min_span || s->ktab_for.flags != pr->flags ||
+        s->ktab_for.min_motif_size != pr->min_motif_size) {
         std::vector<KEntry> tab;
-        build_ktab(*pr, tab);
+        std::vector<Seg> segs;
+        build_ktab(*pr, tab, segs);
+        if (s->segs_cap < segs.size()) {
+            dev_free(s->d_segs);
+            s->segs_cap = 0;
+            CHECK(dev_alloc(&s->d_segs, segs.size()));
+            s->segs_cap = (uint32_t)segs.size();
+        }
+        s->n_segs = (uint32_t)segs.size();
         CU(cudaMemcpyAsync(s->d_ktab, tab.data(), tab.size() * sizeof(KEntry), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));  // tab is a local
+        CU(cudaMemcpyAsync(s->d_segs, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // tab / segs are locals
         s->ktab_for = *pr;
     }
 
@@ -492,13 +521,14 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         CHECK(ensure_result_buffers(s, cap));
         ScanParams sp;
         sp.H = s->H; sp.L = s->L; sp.NM = s->NM; sp.X = s->X;
-        sp.ktab = s->d_ktab;
+        sp.ktab = s->d_ktab; sp.segs = s->d_segs; sp.n_segs = s->n_segs;
         sp.ex_key = s->ex_key; sp.n_exotic = s->n_exotic;
         sp.rec_dev_off = s->d_rec_dev_off; sp.own_lo = s->d_own_lo; sp.own_hi = s->d_own_hi; sp.n_records = s->n_records;
         sp.n_words = s->n_words;
         sp.kmin = pr->min_motif_size; sp.kmax = pr->max_motif_size;
         sp.outcap = outcap;
         sp.walk_limit = pr->walk_limit_words ? pr->walk_limit_words : 64;
+        sp.debug_flags = (pr->flags >> 16) & 0xFFFFu;
         sp.stage_key = s->stage_key; sp.stage_k = s->stage_k; sp.stage_cap = s->res_cap;
         sp.tile_cnt = s->tile_cnt; sp.tile_base = s->tile_base;
         sp.spill_key = s->spill_key; sp.spill_k = s->spill_k; sp.spill_cap = s->res_cap;
@@ -512,19 +542,22 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         else CHECK(launch_scan<16>(sp, n_tiles, smem, st));
         CU(cudaEventRecord(s->ev[2], st));
         tile_offsets_kernel<<<1, 1024, 0, st>>>(s->tile_cnt, s->tile_off, n_tiles, s->d_counters);
+        spill_sort_small_kernel<<<1, 1024, 0, st>>>(s->spill_key, s->spill_k, s->res_cap, s->d_counters);
         GatherParams g;
         g.stage_key = s->stage_key; g.stage_k = s->stage_k;
         g.tile_cnt = s->tile_cnt; g.tile_base = s->tile_base; g.tile_off = s->tile_off;
         g.spill_key = s->spill_key; g.spill_k = s->spill_k;
         g.fin_key = s->fin_key; g.fin_k = s->fin_k;
         g.n_tiles = n_tiles; g.fin_cap = s->res_cap; g.stage_cap = s->res_cap; g.spill_cap = s->res_cap;
+        g.tile_words = TW; g.spill_sorted = 0;
         g.counters = s->d_counters;
-        gather_kernel<<<(n_tiles * 32 + 255) / 256, 256, 0, st>>>(g);
+        const uint32_t ggrid = (n_tiles * 32 + 255) / 256;
+        gather_kernel<<<ggrid, 256, 0, st>>>(g);
         const uint32_t tgrid = std::min<uint32_t>(148 * 8, (s->res_cap + 255) / 256);
         translate_kernel<<<tgrid, 256, 0, st>>>(s->fin_key, s->fin_k, s->d_rec_dev_off, s->n_records, s->d_counters,
                                                s->res_cap, s->o_rec, s->o_start, s->o_end, s->o_k);
         CU(cudaGetLastError());
-        launches += 4;
+        launches += 5;
         CU(cudaEventRecord(s->ev[3], st));
         CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -537,27 +570,16 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
             ++reruns;
             continue;
         }
-        if (n_spill) {  // a tile overflowed its slots: order everything with the fallback network
-            const uint32_t n = (uint32_t)n_total, np = next_pow2(n);
-            uint64_t *tk = nullptr;
-            uint16_t *tv = nullptr;
-            CHECK(dev_alloc(&tk, np));
-            int rc = dev_alloc(&tv, np);
-            if (rc) { cudaFree(tk); return rc; }
-            cudaMemcpyAsync(tk, s->fin_key, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
-            cudaMemcpyAsync(tv, s->fin_k, (size_t)n * 2, cudaMemcpyDeviceToDevice, st);
-            rc = bitonic_sort(st, tk, tv, n, &launches);
-            cudaMemcpyAsync(s->fin_key, tk, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
-            cudaMemcpyAsync(s->fin_k, tv, (size_t)n * 2, cudaMemcpyDeviceToDevice, st);
+        if (n_spill > SPILL_SMALL) {  // a long spill list: sort it with the global network, then gather again
+            CHECK(bitonic_sort(st, s->spill_key, s->spill_k, (uint32_t)n_spill, &launches));
+            g.spill_sorted = 1;
+            gather_kernel<<<ggrid, 256, 0, st>>>(g);
             translate_kernel<<<tgrid, 256, 0, st>>>(s->fin_key, s->fin_k, s->d_rec_dev_off, s->n_records, s->d_counters,
                                                    s->res_cap, s->o_rec, s->o_start, s->o_end, s->o_k);
-            ++launches;
-            cudaEventRecord(s->ev[3], st);
-            cudaError_t e = cudaStreamSynchronize(st);
-            cudaFree(tk);
-            cudaFree(tv);
-            if (rc) return rc;
-            if (e != cudaSuccess) { set_err("crf_scan: fallback sort failed: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
+            CU(cudaGetLastError());
+            launches += 2;
+            CU(cudaEventRecord(s->ev[3], st));
+            CU(cudaStreamSynchronize(st));
         }
         float ms_all = 0, ms_k = 0;
         CU(cudaEventElapsedTime(&ms_all, s->ev[0], s->ev[3]));

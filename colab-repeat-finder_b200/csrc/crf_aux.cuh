@@ -117,6 +117,49 @@ __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t *tile
     }
 }
 
+// Results that overflowed a tile's sorted-output slots ("spill") are sorted on their own and merged
+// with the tile-ordered main list while it is gathered: final index = own index + rank in the other
+// list.  Up to SPILL_SMALL rows are sorted by one block in shared memory (no host round trip); more
+// than that, the host sorts the spill list with the global bitonic network and gathers again.
+constexpr uint32_t SPILL_SMALL = 4096;
+
+__device__ __forceinline__ bool row_less(uint64_t ka, uint16_t va, uint64_t kb, uint16_t vb) {
+    return ka < kb || (ka == kb && va < vb);
+}
+
+__global__ void __launch_bounds__(1024) spill_sort_small_kernel(uint64_t *spill_key, uint16_t *spill_k, uint32_t spill_cap,
+                                                                const unsigned long long *counters) {
+    __shared__ uint64_t sk[SPILL_SMALL];
+    __shared__ uint16_t sv[SPILL_SMALL];
+    const unsigned long long n64 = counters[C_SPILL];
+    if (n64 < 2 || n64 > SPILL_SMALL || n64 > spill_cap) return;
+    const uint32_t n = (uint32_t)n64;
+    uint32_t np = 1;
+    while (np < n) np <<= 1;
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+        sk[i] = i < n ? spill_key[i] : ~0ull;
+        sv[i] = i < n ? spill_k[i] : (uint16_t)0xFFFF;
+    }
+    __syncthreads();
+    for (uint32_t kk = 2; kk <= np; kk <<= 1)
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const bool asc = (i & kk) == 0;
+                    const uint64_t a = sk[i], b = sk[ixj];
+                    const uint16_t va = sv[i], vb = sv[ixj];
+                    if (row_less(b, vb, a, va) == asc) { sk[i] = b; sk[ixj] = a; sv[i] = vb; sv[ixj] = va; }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        spill_key[i] = sk[i];
+        spill_k[i] = sv[i];
+    }
+}
+
 struct GatherParams {
     const uint64_t *stage_key;
     const uint16_t *stage_k;
@@ -126,27 +169,48 @@ struct GatherParams {
     uint64_t *fin_key;
     uint16_t *fin_k;
     uint32_t n_tiles, fin_cap, stage_cap, spill_cap;
+    uint32_t tile_words;     // words per tile (a spilled row's tile = (start >> 5) / tile_words)
+    uint32_t spill_sorted;   // host says: the spill list is sorted even though it is longer than SPILL_SMALL
     const unsigned long long *counters;
 };
 
-// one warp per tile copies its sorted segment to its final place; spilled rows go to the tail
+// one warp per tile copies its sorted segment to its final place, leaving room for the spilled
+// rows that sort before each element; the spilled rows are placed by the tail of the grid
 __global__ void __launch_bounds__(256) gather_kernel(const GatherParams g) {
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g.counters[C_STAGE] > g.stage_cap || g.counters[C_TOTAL] > g.fin_cap) return;  // host re-runs
+    const unsigned long long nspill64 = g.counters[C_SPILL];
+    if (nspill64 > g.spill_cap) return;
+    if (nspill64 > SPILL_SMALL && !g.spill_sorted) return;  // host sorts the spill list and gathers again
+    const uint32_t m = (uint32_t)nspill64;
     if (warp_global < g.n_tiles) {
         const uint32_t n = g.tile_cnt[warp_global], src = g.tile_base[warp_global], dst = g.tile_off[warp_global];
         for (uint32_t i = lane; i < n; i += 32) {
-            g.fin_key[dst + i] = g.stage_key[src + i];
-            g.fin_k[dst + i] = g.stage_k[src + i];
+            const uint64_t key = g.stage_key[src + i];
+            const uint16_t kk = g.stage_k[src + i];
+            uint32_t lo = 0, hi = m;  // spilled rows that sort before this one
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (row_less(g.spill_key[mid], g.spill_k[mid], key, kk)) lo = mid + 1; else hi = mid;
+            }
+            g.fin_key[dst + i + lo] = key;
+            g.fin_k[dst + i + lo] = kk;
         }
     }
-    const unsigned long long nspill = g.counters[C_SPILL];
-    if (nspill && nspill <= g.spill_cap) {
-        const uint32_t dst = g.tile_off[g.n_tiles];
+    if (m) {
         const uint32_t stride = gridDim.x * blockDim.x;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nspill; i += stride) {
-            g.fin_key[dst + i] = g.spill_key[i];
-            g.fin_k[dst + i] = g.spill_k[i];
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+            const uint64_t key = g.spill_key[i];
+            const uint16_t kk = g.spill_k[i];
+            const uint32_t t = (uint32_t)(key >> 37) / g.tile_words;
+            const uint32_t n = g.tile_cnt[t], src = g.tile_base[t];
+            uint32_t lo = 0, hi = n;  // rows of its tile's segment that sort before it
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (row_less(g.stage_key[src + mid], g.stage_k[src + mid], key, kk)) lo = mid + 1; else hi = mid;
+            }
+            g.fin_key[g.tile_off[t] + lo + i] = key;
+            g.fin_k[g.tile_off[t] + lo + i] = kk;
         }
     }
 }

@@ -31,19 +31,30 @@ enum FilterMode : uint8_t {
 
 // Per motif size k (index = k).  r_min = max(min_span - k, (min_repeats-1)*k) is the number of
 // consecutive ones of M_k a run needs (trk:86,91 in closed form).
+// Exact phase: u = 2^ulog is the largest power of two with 2u-1 <= r_min (capped at 32), so every
+// qualifying run contains a fully matching u-aligned unit; umask has the low bit of every unit.
 struct __align__(16) KEntry {
     uint32_t rmin;
-    uint32_t rexact;   // min(rmin, 32): erosion width used by the exact phase
+    uint32_t umask;
     uint8_t mode;      // FilterMode
     uint8_t sh[3];     // dilation shifts of the ERODE filter (0 = unused)
     uint16_t div[6];   // k/p for the distinct primes p | k (0-terminated): primitivity, trk:108-142
-    uint32_t pad_;
+    uint32_t ulog;
 };
 static_assert(sizeof(KEntry) == 32, "KEntry layout");
+
+// A maximal range of motif sizes that share (k >> 5) and the fast-phase filter.
+struct Seg {
+    uint16_t k_lo, k_hi;
+    uint8_t mode, sh0, sh1, sh2;
+};
+static_assert(sizeof(Seg) == 8, "Seg layout");
 
 struct ScanParams {
     const uint32_t *H, *L, *NM, *X;
     const KEntry *ktab;
+    const Seg *segs;
+    uint32_t n_segs;
     const uint64_t *ex_key;  // sorted (pos << 8 | letter) of exotic symbols
     uint32_t n_exotic;
     const uint32_t *rec_dev_off;  // layout position of each record's first base
@@ -53,6 +64,7 @@ struct ScanParams {
     uint32_t kmin, kmax;
     uint32_t outcap;         // per-tile sorted-output slots
     uint32_t walk_limit;     // words one thread walks before the block takes over
+    uint32_t debug_flags;    // bit 0: skip the exact phase (profiling only, results are then empty)
     uint64_t *stage_key;     // (start << 32 | end), tile-sorted segments
     uint16_t *stage_k;
     uint32_t stage_cap;

@@ -2,45 +2,95 @@
 //
 // Replaces the reference's lock-step loop (perfect_repeat_finder.py:66-74) and the tracker state
 // machine (utils/perfect_repeat_tracker.py:43-101).  Closed form being computed (SURVEY App. A.2,
-// checked against the oracle by tests/): for each k, every maximal run [st, i0) of ones of
+// checked against the CPU restatement by tests/): for each k, every maximal run [st, i0) of ones of
 //   M_k[j] = (S[j] == S[j+k]) and S[j] != 'N'
 // with i0 - st >= r_min(k) = max(min_span - k, (min_repeats-1)*k) and a primitive motif S[st:st+k]
 // is reported as (st, i0 + k, k).
 //
 // One CTA owns one tile of 256*T words (T*8192 bases) and emits the runs that START in it:
-//   1. stage the tile (+ a halo of kmax bases) of the H and L planes in shared memory;
-//   2. fast phase -- each thread keeps a strip of T(+1) consecutive words in registers and, for
-//      every k, forms the shifted-compare words with funnel shifts and tests a *necessary*
-//      condition for "a qualifying run starts in my strip" (FilterMode); no branches, the
-//      result is one bit per (strip, k) in a register;
-//   3. exact phase -- the block compacts the (strip, k) hits (prefix sum, no atomics), one
-//      thread per hit re-evaluates the exact mask (N mask, exotic symbols), finds the run
-//      starts by erosion, walks right to the run end, applies the thresholds and the
-//      primitivity rule and appends (start, end, k) to the tile's shared-memory result list;
+//   1. stage the tile (one word of left context, a halo of kmax bases) of the H, L and NM planes in
+//      shared memory (bank-conflict-free padded layout);
+//   2. fast phase -- each thread keeps a strip of T(+1) consecutive words of H and L in registers
+//      and, for every k, forms the shifted-compare words with funnel shifts and tests a
+//      *necessary* condition for "a qualifying run starts in my strip" (FilterMode); the motif
+//      sizes come as segments of constant filter, so the inner loop has no table look-ups and no
+//      branches; the result is one bit per (strip, k) in a register;
+//   3. exact phase -- the block compacts the (strip, k) hits (prefix sum, no atomics); one
+//      thread per hit re-evaluates the exact mask from shared memory (N mask; exotic symbols via
+//      global memory), locates run starts as "first fully matching aligned unit of a run", walks
+//      right to the run end, applies the thresholds and the primitivity rule and appends
+//      (start, end, k) to the tile's shared-memory result list;
 //   4. runs longer than walk_limit words are finished by the whole block (256 words per step);
-//   5. the tile's results are rank-sorted by (start, end) and written as one segment; a later
-//      pass concatenates the segments in tile order, which is global (start, end) order because
-//      a run is owned by the tile of its start.
+//   5. the tile's results are ordered by (start, end) with a counting sort over strips and
+//      written as one segment; a later pass concatenates the segments in tile order, which is
+//      global (start, end) order because a run is owned by the tile of its start.
 #pragma once
 #include "crf_device.cuh"
 
 namespace crf {
 
-struct TileOut {
+__host__ __device__ __forceinline__ uint32_t pad_idx(uint32_t v) { return v + (v >> 5); }
+
+struct TileCtx {
+    const uint32_t *sH, *sL, *sN;  // padded; index j <-> absolute word (wbase + j)
+    uint32_t wbase;                // absolute word of smem index 0, plus 1 (so tile 0 needs no negative)
+    uint32_t nsm;                  // words staged
     uint64_t *key;
     uint16_t *kk;
-    uint32_t *nout;
-    uint32_t *nlong;
-    uint32_t *longq;
+    uint32_t *nout, *nlong, *longq;
     uint32_t cap;
+    uint2 *startq;                 // run starts found by stage A of the exact phase
+    uint32_t *nstart;
 };
 
-__device__ inline void emit_result(const ScanParams &p, const TileOut &to, uint32_t st, uint32_t end, uint32_t k) {
+// Exact M_k word w: from the staged tile when everything needed is there, else from global memory.
+__device__ __forceinline__ uint32_t tile_mask(const ScanParams &p, const TileCtx &t, uint32_t k, uint32_t w) {
+    const uint32_t q = k >> 5, s = k & 31;
+    const uint32_t j = w + 1 - t.wbase;  // wbase = w0, smem index 0 = word w0-1
+    if (p.n_exotic == 0 && w + 1 >= t.wbase && j + q + 1 < t.nsm) {
+        const uint32_t a = pad_idx(j), b = pad_idx(j + q), c = pad_idx(j + q + 1);
+        const uint32_t dh = t.sH[a] ^ __funnelshift_r(t.sH[b], t.sH[c], s);
+        const uint32_t dl = t.sL[a] ^ __funnelshift_r(t.sL[b], t.sL[c], s);
+        const uint32_t nm = t.sN[a] | __funnelshift_r(t.sN[b], t.sN[c], s);
+        return ~(dh | dl | nm);
+    }
+    return exact_mask(p, k, w);
+}
+
+__device__ inline bool tile_walk(const ScanParams &p, const TileCtx &t, uint32_t k, uint32_t from, uint32_t limit,
+                                 uint32_t *i0) {
+    uint32_t w = from >> 5;
+    uint32_t m = tile_mask(p, t, k, w) | ((1u << (from & 31)) - 1u);
+    for (uint32_t n = 0;; ++n) {
+        if (m != 0xFFFFFFFFu) { *i0 = (w << 5) + (__ffs(~m) - 1); return true; }
+        ++w;
+        if (n >= limit || w >= p.n_words) {  // beyond n_words everything is masked
+            *i0 = w << 5;
+            return w >= p.n_words;
+        }
+        m = tile_mask(p, t, k, w);
+    }
+}
+
+__device__ inline bool tile_all_match(const ScanParams &p, const TileCtx &t, uint32_t d, uint32_t a, uint32_t len) {
+    uint32_t pos = a;
+    const uint32_t end = a + len;
+    while (pos < end) {
+        const uint32_t b = pos & 31;
+        const uint32_t n = min(32u - b, end - pos);
+        const uint32_t mask = (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)) << b;
+        if ((tile_mask(p, t, d, pos >> 5) & mask) != mask) return false;
+        pos += n;
+    }
+    return true;
+}
+
+__device__ inline void emit_result(const ScanParams &p, const TileCtx &t, uint32_t st, uint32_t end, uint32_t k) {
     const uint64_t key = ((uint64_t)st << 32) | end;
-    const uint32_t idx = atomicAdd(to.nout, 1u);
-    if (idx < to.cap) {
-        to.key[idx] = key;
-        to.kk[idx] = (uint16_t)k;
+    const uint32_t idx = atomicAdd(t.nout, 1u);
+    if (idx < t.cap) {
+        t.key[idx] = key;
+        t.kk[idx] = (uint16_t)k;
     } else {
         const unsigned long long g = atomicAdd(p.counters + C_SPILL, 1ull);
         if (g < p.spill_cap) {
@@ -50,9 +100,9 @@ __device__ inline void emit_result(const ScanParams &p, const TileOut &to, uint3
     }
 }
 
-// A qualifying-run start candidate: M_k[st .. st+known) are ones and M_k[st-1] is zero.
-__device__ inline void handle_start(const ScanParams &p, const TileOut &to, const KEntry &ke, uint32_t k,
-                                    uint32_t st, uint32_t known) {
+// A run start: M_k[st .. st+known) are ones and M_k[st-1] is zero.
+__device__ inline void handle_start(const ScanParams &p, const TileCtx &t, const KEntry &ke, uint32_t k, uint32_t st,
+                                    uint32_t known) {
     if (p.own_lo) {  // partitioned load: a run belongs to the unit that owns its start
         uint32_t lo = 0, hi = p.n_records - 1;
         while (lo < hi) {
@@ -62,50 +112,101 @@ __device__ inline void handle_start(const ScanParams &p, const TileOut &to, cons
         if (st < __ldg(p.own_lo + lo) || st >= __ldg(p.own_hi + lo)) return;
     }
     uint32_t i0;
-    bool found = walk_run(p, k, st + known, p.walk_limit, &i0);
-    while (!found && i0 - st < ke.rmin) found = walk_run(p, k, i0, p.walk_limit, &i0);
-    if (found && i0 - st < ke.rmin) return;                    // trk:86/91 thresholds
-    if (!motif_is_primitive(p, ke, k, st)) return;              // trk:98
+    bool found = tile_walk(p, t, k, st + known, p.walk_limit, &i0);
+    while (!found && i0 - st < ke.rmin) found = tile_walk(p, t, k, i0, p.walk_limit, &i0);
+    if (found && i0 - st < ke.rmin) return;                       // trk:86/91 thresholds
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) {                                 // primitivity, trk:98,108-142
+        const uint32_t d = ke.div[j];
+        if (!d) break;
+        if (tile_all_match(p, t, d, st, k - d)) return;
+    }
     if (found) {
-        emit_result(p, to, st, i0 + k, k);                      // end = i0 + k (trk:87-92)
+        emit_result(p, t, st, i0 + k, k);                         // end = i0 + k (trk:87-92)
         return;
     }
-    const uint32_t slot = atomicAdd(to.nlong, 1u);
+    const uint32_t slot = atomicAdd(t.nlong, 1u);
     if (slot < LONGCAP) {
-        to.longq[3 * slot] = st;
-        to.longq[3 * slot + 1] = k;
-        to.longq[3 * slot + 2] = i0 >> 5;
+        t.longq[3 * slot] = st;
+        t.longq[3 * slot + 1] = k;
+        t.longq[3 * slot + 2] = i0 >> 5;
     } else {  // queue full: finish it alone (correct, slow, practically never)
-        while (!walk_run(p, k, i0, 0x7FFFFFFFu, &i0)) {}
-        emit_result(p, to, st, i0 + k, k);
+        while (!tile_walk(p, t, k, i0, 0x7FFFFFFFu, &i0)) {}
+        emit_result(p, t, st, i0 + k, k);
     }
 }
 
-// Exact phase for one (strip, k) hit: all qualifying run starts inside the strip's nw words.
-__device__ inline void exact_item(const ScanParams &p, const TileOut &to, uint32_t wfirst, int nw, uint32_t k) {
+constexpr uint32_t STARTQ_CAP = 1024;
+constexpr uint32_t NBATCH = 4;  // groups of 32 motif sizes whose hits share one exact phase
+// (declared before use below)  // run starts queued per exact phase before falling back to in-line handling
+
+__device__ __forceinline__ void push_start(const ScanParams &p, const TileCtx &t, const KEntry &ke, uint32_t k,
+                                           uint32_t st, uint32_t known) {
+    const uint32_t slot = atomicAdd(t.nstart, 1u);
+    if (slot < STARTQ_CAP) t.startq[slot] = make_uint2(st, k | (known << 16));
+    else handle_start(p, t, ke, k, st, known);
+}
+
+// Exact phase, stage A, for one (strip, k) hit: every run that starts inside the strip's nw words
+// and contains a fully matching aligned unit (all runs of >= r_min do) is queued as
+// (start, k, matches known so far).  A run is found through the FIRST fully matching unit it
+// contains: that unit is preceded by a unit that is not fully matching, and the run start is the
+// unit start minus the matches directly below it.
+__device__ inline void exact_find(const ScanParams &p, const TileCtx &t, uint32_t wfirst, uint32_t nw, uint32_t k) {
     const KEntry ke = p.ktab[k];
-    const uint32_t rex = ke.rexact;
-    uint32_t prevtop = wfirst ? (exact_mask(p, k, wfirst - 1) >> 31) : 0u;
-    uint32_t cur = exact_mask(p, k, wfirst);
-    for (int i = 0; i < nw; ++i) {
-        const uint32_t w = wfirst + i;
-        const uint32_t nxt = exact_mask(p, k, w + 1);
-        if (cur) {
-            uint64_t v = ((uint64_t)nxt << 32) | cur;  // erode by rex: bit j <- bits j..j+rex-1 all set
-            for (uint32_t covered = 1; covered < rex;) {
-                const uint32_t sh = min(covered, rex - covered);
-                v &= v >> sh;
-                covered += sh;
-            }
-            uint32_t starts = (uint32_t)v & ~((cur << 1) | prevtop);
-            while (starts) {
-                const uint32_t b = __ffs(starts) - 1;
-                starts &= starts - 1;
-                handle_start(p, to, ke, k, (w << 5) + b, rex);
-            }
+    const uint32_t ulog = ke.ulog, u = 1u << ulog, um = ke.umask;
+    const uint32_t lo_pos = wfirst << 5, hi_pos = (wfirst + nw) << 5;
+    auto fold = [&](uint32_t m) {  // bit at a unit's lowest position <- the unit is all ones
+        if (ulog >= 1) m &= m >> 1;
+        if (ulog >= 2) m &= m >> 2;
+        if (ulog >= 3) m &= m >> 4;
+        if (ulog >= 4) m &= m >> 8;
+        if (ulog >= 5) m &= m >> 16;
+        return m & um;
+    };
+    const uint32_t q = k >> 5, s = k & 31;
+    const bool in_smem = (p.n_exotic == 0);  // strip + look-ahead + halo are always staged
+    uint32_t j = wfirst - t.wbase;           // smem index of word wfirst - 1
+    uint32_t hb = 0, lb = 0, nb = 0;
+    if (in_smem) {
+        const uint32_t b0 = pad_idx(j + q);
+        hb = t.sH[b0]; lb = t.sL[b0]; nb = t.sN[b0];
+    }
+    uint32_t wnext = wfirst - 1;             // absolute word the next call returns (wraps for wfirst == 0)
+    auto next_mask = [&]() -> uint32_t {
+        uint32_t m;
+        if (in_smem) {
+            const uint32_t a = pad_idx(j), c = pad_idx(j + q + 1);
+            const uint32_t hc = t.sH[c], lc = t.sL[c], nc = t.sN[c];
+            m = ~((t.sH[a] ^ __funnelshift_r(hb, hc, s)) | (t.sL[a] ^ __funnelshift_r(lb, lc, s)) |
+                  (t.sN[a] | __funnelshift_r(nb, nc, s)));
+            hb = hc; lb = lc; nb = nc;
+            ++j;
+        } else {
+            m = (wnext == 0xFFFFFFFFu) ? 0u : exact_mask(p, k, wnext);
         }
-        prevtop = cur >> 31;
-        cur = nxt;
+        ++wnext;
+        return m;
+    };
+    uint32_t prev = next_mask();  // word wfirst-1 (tile 0 stages an all-masked word there)
+    uint32_t cur = next_mask();
+    uint32_t carry = (fold(prev) >> (32 - u)) & 1u;  // previous word's last unit is full
+#pragma unroll 1
+    for (uint32_t i = 0; i <= nw; ++i) {
+        const uint32_t w = wfirst + i;
+        const uint32_t f = fold(cur);
+        uint32_t g = f & ~(((ulog < 5) ? (f << u) : 0u) | carry);  // first full unit of its run
+        while (g) {
+            const uint32_t b = __ffs(g) - 1;
+            g &= g - 1;
+            const uint32_t below = __funnelshift_r(prev, cur, b);  // the 32 positions just below b
+            const uint32_t cnt = __clz(~below);                     // matches directly below the unit
+            const uint32_t st = (w << 5) + b - cnt;
+            if (st >= lo_pos && st < hi_pos) push_start(p, t, ke, k, st, cnt + u);
+        }
+        carry = (f >> (32 - u)) & 1u;
+        prev = cur;
+        if (i < nw) cur = next_mask();
     }
 }
 
@@ -139,7 +240,8 @@ __device__ __forceinline__ bool filter_byte(const uint32_t (&NH)[T + 1], const u
     }
     return (acc & 0x80808080u) != 0;
 }
-template <int T>
+// NSH = number of dilation steps (compile time), shifts at run time
+template <int T, int NSH>
 __device__ __forceinline__ bool filter_erode(const uint32_t (&NH)[T + 1], const uint32_t (&NL)[T + 1],
                                              const uint32_t (&FH)[T + 2], const uint32_t (&FL)[T + 2], uint32_t s,
                                              uint32_t sh0, uint32_t sh1, uint32_t sh2) {
@@ -147,17 +249,17 @@ __device__ __forceinline__ bool filter_erode(const uint32_t (&NH)[T + 1], const 
 #pragma unroll
     for (int i = 0; i <= T; ++i)
         x[i] = (NH[i] ^ __funnelshift_r(FH[i], FH[i + 1], s)) | (NL[i] ^ __funnelshift_r(FL[i], FL[i + 1], s));
-    if (sh0) {
+    if (NSH >= 1) {
 #pragma unroll
         for (int i = 0; i < T; ++i) x[i] |= __funnelshift_r(x[i], x[i + 1], sh0);
         x[T] |= x[T] >> sh0;
     }
-    if (sh1) {
+    if (NSH >= 2) {
 #pragma unroll
         for (int i = 0; i < T; ++i) x[i] |= __funnelshift_r(x[i], x[i + 1], sh1);
         x[T] |= x[T] >> sh1;
     }
-    if (sh2) {
+    if (NSH >= 3) {
 #pragma unroll
         for (int i = 0; i < T; ++i) x[i] |= __funnelshift_r(x[i], x[i + 1], sh2);
     }
@@ -168,11 +270,14 @@ __device__ __forceinline__ bool filter_erode(const uint32_t (&NH)[T + 1], const 
 }
 
 // dynamic shared memory a scan block needs
+__host__ __device__ inline uint32_t scan_tile_words(int T, uint32_t kmax) {
+    return (uint32_t)THREADS * T + (kmax >> 5) + 4;  // 1 word of left context + tile + halo (q+3)
+}
 __host__ __device__ inline size_t scan_smem_bytes(int T, uint32_t kmax, uint32_t outcap) {
-    const size_t tile_words = (size_t)THREADS * T + (kmax >> 5) + 3;
-    size_t words = 2 * tile_words + 2 * THREADS + 16 + 3 * LONGCAP;
+    const size_t plane = pad_idx(scan_tile_words(T, kmax)) + 1;
+    size_t words = 3 * plane + (NBATCH + 1) * THREADS + 16 + 3 * LONGCAP;
     words = (words + 1) & ~(size_t)1;
-    return words * 4 + (size_t)outcap * 8 + (((size_t)outcap * 2 + 7) & ~(size_t)7);
+    return words * 4 + (size_t)STARTQ_CAP * 8 + (size_t)outcap * 8 + (((size_t)outcap * 2 + 7) & ~(size_t)7);
 }
 
 template <int T>
@@ -180,63 +285,102 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
     constexpr int TW = THREADS * T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t qmin = p.kmin >> 5, qmax = p.kmax >> 5;
-    const uint32_t tile_words = TW + qmax + 3;
+    const uint32_t nsm = scan_tile_words(T, p.kmax);
+    const uint32_t plane = pad_idx(nsm) + 1;
 
     uint32_t *sH = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *sL = sH + tile_words;
-    uint32_t *s_hit = sL + tile_words;
-    uint32_t *s_pre = s_hit + THREADS;
-    uint32_t *s_misc = s_pre + THREADS;  // [0..7] warp sums [8] nout [9] nlong [10] minpos [11] base
+    uint32_t *sL = sH + plane;
+    uint32_t *sN = sL + plane;
+    uint32_t *s_hit = sN + plane;               // NBATCH x THREADS hit masks (later: strip histogram)
+    uint32_t *s_pre = s_hit + NBATCH * THREADS;
+    uint32_t *s_misc = s_pre + THREADS;  // [0..7] warp sums [8] nout [9] nlong [10] nstart/minpos [11] base [12..15] q
     uint32_t *s_long = s_misc + 16;
-    size_t off_words = 2 * (size_t)tile_words + 2 * THREADS + 16 + 3 * LONGCAP;
+    size_t off_words = 3 * (size_t)plane + (NBATCH + 1) * THREADS + 16 + 3 * LONGCAP;
     off_words = (off_words + 1) & ~(size_t)1;
-    uint64_t *s_key = reinterpret_cast<uint64_t *>(smem_raw + off_words * 4);
+    uint2 *s_startq = reinterpret_cast<uint2 *>(smem_raw + off_words * 4);
+    uint64_t *s_key = reinterpret_cast<uint64_t *>(s_startq + STARTQ_CAP);
     uint16_t *s_k = reinterpret_cast<uint16_t *>(s_key + p.outcap);
 
     const uint32_t tile = blockIdx.x;
     const uint32_t w0 = tile * TW;
-    for (uint32_t i = tid; i < tile_words; i += THREADS) {
-        sH[i] = __ldg(p.H + w0 + i);
-        sL[i] = __ldg(p.L + w0 + i);
+    // smem index j <-> absolute word w0 - 1 + j
+    for (uint32_t j = tid; j < nsm; j += THREADS) {
+        const bool real = (w0 + j) != 0;
+        const uint32_t w = w0 + j - 1;
+        const uint32_t a = pad_idx(j);
+        sH[a] = real ? __ldg(p.H + w) : 0u;
+        sL[a] = real ? __ldg(p.L + w) : 0u;
+        sN[a] = real ? __ldg(p.NM + w) : 0xFFFFFFFFu;
     }
     if (tid < 16) s_misc[tid] = 0;
     __syncthreads();
 
-    const TileOut to{s_key, s_k, &s_misc[8], &s_misc[9], s_long, p.outcap};
+    TileCtx tc;
+    tc.sH = sH; tc.sL = sL; tc.sN = sN; tc.wbase = w0; tc.nsm = nsm;
+    tc.key = s_key; tc.kk = s_k; tc.nout = &s_misc[8]; tc.nlong = &s_misc[9]; tc.longq = s_long; tc.cap = p.outcap;
+    tc.startq = s_startq; tc.nstart = &s_misc[10];
 
     uint32_t NH[T + 1], NL[T + 1];
 #pragma unroll
     for (int i = 0; i <= T; ++i) {
-        NH[i] = sH[tid * T + i];
-        NL[i] = sL[tid * T + i];
+        NH[i] = sH[pad_idx(1 + tid * T + i)];
+        NL[i] = sL[pad_idx(1 + tid * T + i)];
     }
 
     unsigned long long ncand = 0;
-    for (uint32_t qb = qmin; qb <= qmax; ++qb) {
-        uint32_t FH[T + 2], FL[T + 2];
+    uint32_t si = 0;
+    while (si < p.n_segs) {
+        // ---- fast phase: up to NBATCH groups of <= 32 motif sizes (one group per k >> 5)
+        uint32_t nb = 0;
+        uint32_t cnt = 0;
+        for (; nb < NBATCH && si < p.n_segs; ++nb) {
+            const uint32_t qb = (uint32_t)p.segs[si].k_lo >> 5;
+            uint32_t FH[T + 2], FL[T + 2];
 #pragma unroll
-        for (int i = 0; i <= T + 1; ++i) {
-            FH[i] = sH[tid * T + qb + i];
-            FL[i] = sL[tid * T + qb + i];
-        }
-        const uint32_t s_lo = (qb == qmin) ? (p.kmin & 31) : 0u;
-        const uint32_t s_hi = (qb == qmax) ? (p.kmax & 31) : 31u;
-        uint32_t hitmask = 0;
+            for (int i = 0; i <= T + 1; ++i) {
+                FH[i] = sH[pad_idx(1 + tid * T + qb + i)];
+                FL[i] = sL[pad_idx(1 + tid * T + qb + i)];
+            }
+            uint32_t hitmask = 0;
+            for (; si < p.n_segs; ++si) {
+                const Seg sg = p.segs[si];
+                if (((uint32_t)sg.k_lo >> 5) != qb) break;
+                const uint32_t s_lo = sg.k_lo & 31, s_hi = sg.k_hi & 31;
+                const uint32_t sh0 = sg.sh0, sh1 = sg.sh1, sh2 = sg.sh2;
+                if (sg.mode == MODE_WORD) {
 #pragma unroll 1
-        for (uint32_t s = s_lo; s <= s_hi; ++s) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.ktab + (qb * 32 + s)));
-            const uint32_t mode = raw.z & 0xFF;
-            bool hit;
-            if (mode == MODE_WORD) hit = filter_word<T>(NH, FH, s);
-            else if (mode == MODE_HALF) hit = filter_half<T>(NH, FH, s);
-            else if (mode == MODE_BYTE) hit = filter_byte<T>(NH, NL, FH, FL, s);
-            else hit = filter_erode<T>(NH, NL, FH, FL, s, (raw.z >> 8) & 0xFF, (raw.z >> 16) & 0xFF, raw.z >> 24);
-            hitmask |= (hit ? 1u : 0u) << s;
+                    for (uint32_t s = s_lo; s <= s_hi; ++s) hitmask |= (filter_word<T>(NH, FH, s) ? 1u : 0u) << s;
+                } else if (sg.mode == MODE_HALF) {
+#pragma unroll 1
+                    for (uint32_t s = s_lo; s <= s_hi; ++s) hitmask |= (filter_half<T>(NH, FH, s) ? 1u : 0u) << s;
+                } else if (sg.mode == MODE_BYTE) {
+#pragma unroll 1
+                    for (uint32_t s = s_lo; s <= s_hi; ++s)
+                        hitmask |= (filter_byte<T>(NH, NL, FH, FL, s) ? 1u : 0u) << s;
+                } else if (sh2) {
+#pragma unroll 1
+                    for (uint32_t s = s_lo; s <= s_hi; ++s)
+                        hitmask |= (filter_erode<T, 3>(NH, NL, FH, FL, s, sh0, sh1, sh2) ? 1u : 0u) << s;
+                } else if (sh1) {
+#pragma unroll 1
+                    for (uint32_t s = s_lo; s <= s_hi; ++s)
+                        hitmask |= (filter_erode<T, 2>(NH, NL, FH, FL, s, sh0, sh1, 0) ? 1u : 0u) << s;
+                } else if (sh0) {
+#pragma unroll 1
+                    for (uint32_t s = s_lo; s <= s_hi; ++s)
+                        hitmask |= (filter_erode<T, 1>(NH, NL, FH, FL, s, sh0, 0, 0) ? 1u : 0u) << s;
+                } else {
+#pragma unroll 1
+                    for (uint32_t s = s_lo; s <= s_hi; ++s)
+                        hitmask |= (filter_erode<T, 0>(NH, NL, FH, FL, s, 0, 0, 0) ? 1u : 0u) << s;
+                }
+            }
+            s_hit[nb * THREADS + tid] = hitmask;
+            if (tid == 0) s_misc[12 + nb] = qb;
+            cnt += __popc(hitmask);
         }
 
-        // ---- compact the hits of this group of <= 32 motif sizes and run the exact phase
-        const uint32_t cnt = __popc(hitmask);
+        // ---- exact phase over the hits of these groups: compact (prefix sum, no atomics) ...
         uint32_t incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -244,7 +388,7 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
             if (lane >= (uint32_t)o) incl += v;
         }
         if (lane == 31) s_misc[warp] = incl;
-        s_hit[tid] = hitmask;
+        if (tid == 0) s_misc[10] = 0;  // start-queue fill
         __syncthreads();
         uint32_t woff = 0, total = 0;
 #pragma unroll
@@ -256,16 +400,32 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
         s_pre[tid] = woff + incl - cnt;
         __syncthreads();
         if (tid == 0) ncand += total;
+        if (p.debug_flags & 1u) total = 0;  // profiling only: fast phase alone
+        // ... stage A: one thread per (strip, k) hit finds the run starts and queues them
         for (uint32_t item = tid; item < total; item += THREADS) {
             uint32_t lo = 0, hi = THREADS - 1;  // last strip whose exclusive prefix is <= item
             while (lo < hi) {
                 const uint32_t mid = (lo + hi + 1) >> 1;
                 if (s_pre[mid] <= item) lo = mid; else hi = mid - 1;
             }
-            uint32_t mask = s_hit[lo];
-            for (uint32_t n = item - s_pre[lo]; n; --n) mask &= mask - 1;
-            const uint32_t k = qb * 32 + (__ffs(mask) - 1);
-            exact_item(p, to, w0 + lo * T, T, k);
+            uint32_t n = item - s_pre[lo], k = 0;
+            for (uint32_t b = 0; b < nb; ++b) {
+                const uint32_t mask = s_hit[b * THREADS + lo];
+                const uint32_t c = __popc(mask);
+                if (n < c) { k = s_misc[12 + b] * 32 + __fns(mask, 0, n + 1); break; }
+                n -= c;
+            }
+            exact_find(p, tc, w0 + lo * T, T, k);
+        }
+        __syncthreads();
+        // ... stage B: one thread per run start walks to the run end, applies thresholds and
+        //     primitivity, and appends the result
+        const uint32_t nst = min(s_misc[10], STARTQ_CAP);
+        for (uint32_t e = tid; e < nst; e += THREADS) {
+            const uint2 q = s_startq[e];
+            const uint32_t k = q.y & 0xFFFFu;
+            const KEntry ke = p.ktab[k];
+            handle_start(p, tc, ke, k, q.x, q.y >> 16);
         }
         __syncthreads();
     }
@@ -287,12 +447,14 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
             if (i0 != NOPOS) break;
             wcur += THREADS;
         }
-        if (tid == 0) emit_result(p, to, st, i0 + k, k);
+        if (tid == 0) emit_result(p, tc, st, i0 + k, k);
     }
     __syncthreads();
 
-    // ---- rank-sort the tile's results by (start, end) and write them as one segment
+    // ---- order the tile's results by (start, end): counting sort over strips, then each strip's
+    //      few results are put in order by one thread; written as one segment of the staging list
     const uint32_t n = min(s_misc[8], p.outcap);
+    s_hit[tid] = 0;
     if (tid == 0) {
         const unsigned long long base = atomicAdd(p.counters + C_STAGE, (unsigned long long)n);
         s_misc[11] = (base + n <= p.stage_cap) ? (uint32_t)base : NOPOS;
@@ -303,17 +465,57 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
     }
     __syncthreads();
     const uint32_t base = s_misc[11];
-    if (base == NOPOS) return;  // result buffer too small: the host grows it and re-runs
+    if (base == NOPOS || n == 0) return;  // (too small a result buffer: the host grows it and re-runs)
+    for (uint32_t i = tid; i < n; i += THREADS) {
+        const uint32_t bin = ((uint32_t)(s_key[i] >> 37) - w0) / T;  // strip of the start position
+        atomicAdd(&s_hit[bin], 1u);
+    }
+    __syncthreads();
+    {
+        const uint32_t c = s_hit[tid];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
+        }
+        if (lane == 31) s_misc[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < THREADS / 32; ++i)
+            if (i < warp) woff += s_misc[i];
+        s_pre[tid] = woff + incl - c;  // cursor: start of this strip's slots
+    }
+    __syncthreads();
     for (uint32_t i = tid; i < n; i += THREADS) {
         const uint64_t key = s_key[i];
-        const uint32_t kk = s_k[i];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < n; ++j) {
-            const uint64_t kj = s_key[j];
-            rank += (kj < key) || (kj == key && s_k[j] < kk);
+        const uint32_t bin = ((uint32_t)(key >> 37) - w0) / T;
+        const uint32_t pos = atomicAdd(&s_pre[bin], 1u);
+        p.stage_key[base + pos] = key;
+        p.stage_k[base + pos] = s_k[i];
+    }
+    __syncthreads();  // block-wide visibility of the staged rows
+    {
+        const uint32_t c = s_hit[tid];
+        if (c > 1) {  // insertion sort of this strip's rows (in place, by (key, k))
+            const uint32_t first = base + s_pre[tid] - c;
+            for (uint32_t a = 1; a < c; ++a) {
+                const uint64_t key = p.stage_key[first + a];
+                const uint16_t kk = p.stage_k[first + a];
+                uint32_t b = a;
+                while (b > 0) {
+                    const uint64_t kb = p.stage_key[first + b - 1];
+                    const uint16_t vb = p.stage_k[first + b - 1];
+                    if (kb < key || (kb == key && vb <= kk)) break;
+                    p.stage_key[first + b] = kb;
+                    p.stage_k[first + b] = vb;
+                    --b;
+                }
+                p.stage_key[first + b] = key;
+                p.stage_k[first + b] = kk;
+            }
         }
-        p.stage_key[base + rank] = key;
-        p.stage_k[base + rank] = (uint16_t)kk;
     }
 }
 

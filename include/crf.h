@@ -86,6 +86,8 @@ int crf_seq_info(const crf_seq *seq, crf_seq_info_t *info);
 /* keep runs whose motif is not primitive too (used to find where the reference's interval-mode
  * loop stops, prf:70-74: is_in_middle_of_repeat() does not look at the motif) */
 #define CRF_SCAN_NO_PRIMITIVITY 1u
+/* bits 16..31: profiling switches (results are NOT valid when set): 1<<16 = fast phase only */
+#define CRF_SCAN_DEBUG_FAST_ONLY (1u << 16)
 
 typedef struct {
     uint32_t min_motif_size;
