@@ -375,7 +375,6 @@ extern "C" int crf_seq_info(const crf_seq *s, crf_seq_info_t *info) {
 // ---- scan ---------------------------------------------------------------------------------------
 static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab, std::vector<Seg> &segs) {
     tab.assign((size_t)pr.max_motif_size + 1, KEntry{});
-    static const uint32_t UMASK[6] = {0xFFFFFFFFu, 0x55555555u, 0x11111111u, 0x01010101u, 0x00010001u, 0x00000001u};
     for (uint32_t k = 1; k <= pr.max_motif_size; ++k) {
         KEntry &e = tab[k];
         // r_min: trk:86 and trk:91 in closed form
@@ -383,10 +382,15 @@ static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab, std:
         const uint64_t b = (uint64_t)(pr.min_repeats - 1) * k;
         const uint64_t rmin = std::max<uint64_t>(std::max(a, b), 1);
         e.rmin = (uint32_t)std::min<uint64_t>(rmin, 0xFFFFFF00u);
-        uint32_t ulog = 0;  // largest u = 2^ulog <= 32 with 2u - 1 <= r_min
-        while (ulog < 5 && 2 * (2u << ulog) - 1 <= e.rmin) ++ulog;
-        e.ulog = ulog;
-        e.umask = UMASK[ulog];
+        e.re = (uint8_t)std::min<uint32_t>(e.rmin, 32);
+        {
+            int n = 0;
+            for (uint32_t covered = 1; covered < e.re;) {
+                const uint32_t sh = std::min<uint32_t>(covered, e.re - covered);
+                e.esh[n++] = (uint8_t)sh;
+                covered += sh;
+            }
+        }
         if (e.rmin >= 63) e.mode = MODE_WORD;
         else if (e.rmin >= 31) e.mode = MODE_HALF;
         else if (e.rmin >= 15) e.mode = MODE_BYTE;
@@ -467,7 +471,7 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         return CRF_ERR_ARG;
     }
     const int T = pr->words_per_thread ? (int)pr->words_per_thread : 8;
-    if (T != 1 && T != 8 && T != 16) { set_err("words_per_thread must be 1, 8 or 16"); return CRF_ERR_ARG; }
+    if (T != 1 && T != 2 && T != 4 && T != 8 && T != 16) { set_err("words_per_thread must be 1, 2, 4, 8 or 16"); return CRF_ERR_ARG; }
     crf_ctx *c = s->ctx;
     cudaStream_t st = c->stream;
     CU(cudaSetDevice(c->device));
@@ -538,6 +542,8 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         CU(cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
         CU(cudaEventRecord(s->ev[1], st));
         if (T == 1) CHECK(launch_scan<1>(sp, n_tiles, smem, st));
+        else if (T == 2) CHECK(launch_scan<2>(sp, n_tiles, smem, st));
+        else if (T == 4) CHECK(launch_scan<4>(sp, n_tiles, smem, st));
         else if (T == 8) CHECK(launch_scan<8>(sp, n_tiles, smem, st));
         else CHECK(launch_scan<16>(sp, n_tiles, smem, st));
         CU(cudaEventRecord(s->ev[2], st));

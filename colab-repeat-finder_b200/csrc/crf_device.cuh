@@ -31,15 +31,16 @@ enum FilterMode : uint8_t {
 
 // Per motif size k (index = k).  r_min = max(min_span - k, (min_repeats-1)*k) is the number of
 // consecutive ones of M_k a run needs (trk:86,91 in closed form).
-// Exact phase: u = 2^ulog is the largest power of two with 2u-1 <= r_min (capped at 32), so every
-// qualifying run contains a fully matching u-aligned unit; umask has the low bit of every unit.
+// Exact phase: a word of M_k is eroded by re = min(r_min, 32) with the shift schedule esh (unused
+// steps are 0), so only positions followed by >= re matches survive.
 struct __align__(16) KEntry {
     uint32_t rmin;
-    uint32_t umask;
     uint8_t mode;      // FilterMode
     uint8_t sh[3];     // dilation shifts of the ERODE filter (0 = unused)
+    uint8_t esh[5];    // erosion shifts of the exact phase
+    uint8_t re;        // min(rmin, 32)
     uint16_t div[6];   // k/p for the distinct primes p | k (0-terminated): primitivity, trk:108-142
-    uint32_t ulog;
+    uint8_t pad_[6];
 };
 static_assert(sizeof(KEntry) == 32, "KEntry layout");
 

@@ -136,51 +136,42 @@ __device__ inline void handle_start(const ScanParams &p, const TileCtx &t, const
     }
 }
 
-constexpr uint32_t STARTQ_CAP = 1024;
-constexpr uint32_t NBATCH = 4;  // groups of 32 motif sizes whose hits share one exact phase
-// (declared before use below)  // run starts queued per exact phase before falling back to in-line handling
+constexpr uint32_t STARTQ_CAP = 512;  // overflow queue: run starts beyond two per (strip, k) hit
+constexpr uint32_t NBATCH = 4;        // groups of 32 motif sizes whose hits share one exact phase
 
-__device__ __forceinline__ void push_start(const ScanParams &p, const TileCtx &t, const KEntry &ke, uint32_t k,
-                                           uint32_t st, uint32_t known) {
-    const uint32_t slot = atomicAdd(t.nstart, 1u);
-    if (slot < STARTQ_CAP) t.startq[slot] = make_uint2(st, k | (known << 16));
-    else handle_start(p, t, ke, k, st, known);
-}
-
-// Exact phase, stage A, for one (strip, k) hit: every run that starts inside the strip's nw words
-// and contains a fully matching aligned unit (all runs of >= r_min do) is queued as
-// (start, k, matches known so far).  A run is found through the FIRST fully matching unit it
-// contains: that unit is preceded by a unit that is not fully matching, and the run start is the
-// unit start minus the matches directly below it.
-__device__ inline void exact_find(const ScanParams &p, const TileCtx &t, uint32_t wfirst, uint32_t nw, uint32_t k) {
-    const KEntry ke = p.ktab[k];
-    const uint32_t ulog = ke.ulog, u = 1u << ulog, um = ke.umask;
-    const uint32_t lo_pos = wfirst << 5, hi_pos = (wfirst + nw) << 5;
-    auto fold = [&](uint32_t m) {  // bit at a unit's lowest position <- the unit is all ones
-        if (ulog >= 1) m &= m >> 1;
-        if (ulog >= 2) m &= m >> 2;
-        if (ulog >= 3) m &= m >> 4;
-        if (ulog >= 4) m &= m >> 8;
-        if (ulog >= 5) m &= m >> 16;
-        return m & um;
-    };
+// Exact phase for one (strip, k) hit.  The strip's words of the exact mask M_k are rebuilt from the
+// staged planes (HASN = false: the tile has no masked position, the N plane is not read), each
+// word is eroded by re = min(r_min, 32) across the word boundary, and the rising edges of the
+// eroded mask are exactly the starts of runs of >= re matches.  Each start is then followed to the
+// end of its run (handle_start).  All threads of a warp run the same fixed-length loop.
+template <bool HASN>
+__device__ inline void exact_item(const ScanParams &p, const TileCtx &t, uint32_t wfirst, uint32_t nw, uint32_t k) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.ktab + k));  // rmin, mode/sh, esh[0..3], esh[4]/re/div0
+    const uint32_t e0 = raw.z & 0xFF, e1 = (raw.z >> 8) & 0xFF, e2 = (raw.z >> 16) & 0xFF, e3 = raw.z >> 24;
+    const uint32_t e4 = raw.w & 0xFF, re = (raw.w >> 8) & 0xFF;
     const uint32_t q = k >> 5, s = k & 31;
     const bool in_smem = (p.n_exotic == 0);  // strip + look-ahead + halo are always staged
     uint32_t j = wfirst - t.wbase;           // smem index of word wfirst - 1
     uint32_t hb = 0, lb = 0, nb = 0;
     if (in_smem) {
         const uint32_t b0 = pad_idx(j + q);
-        hb = t.sH[b0]; lb = t.sL[b0]; nb = t.sN[b0];
+        hb = t.sH[b0]; lb = t.sL[b0];
+        if (HASN) nb = t.sN[b0];
     }
     uint32_t wnext = wfirst - 1;             // absolute word the next call returns (wraps for wfirst == 0)
     auto next_mask = [&]() -> uint32_t {
         uint32_t m;
         if (in_smem) {
             const uint32_t a = pad_idx(j), c = pad_idx(j + q + 1);
-            const uint32_t hc = t.sH[c], lc = t.sL[c], nc = t.sN[c];
-            m = ~((t.sH[a] ^ __funnelshift_r(hb, hc, s)) | (t.sL[a] ^ __funnelshift_r(lb, lc, s)) |
-                  (t.sN[a] | __funnelshift_r(nb, nc, s)));
-            hb = hc; lb = lc; nb = nc;
+            const uint32_t hc = t.sH[c], lc = t.sL[c];
+            uint32_t x = (t.sH[a] ^ __funnelshift_r(hb, hc, s)) | (t.sL[a] ^ __funnelshift_r(lb, lc, s));
+            if (HASN) {
+                const uint32_t nc = t.sN[c];
+                x |= t.sN[a] | __funnelshift_r(nb, nc, s);
+                nb = nc;
+            }
+            m = ~x;
+            hb = hc; lb = lc;
             ++j;
         } else {
             m = (wnext == 0xFFFFFFFFu) ? 0u : exact_mask(p, k, wnext);
@@ -188,25 +179,33 @@ __device__ inline void exact_find(const ScanParams &p, const TileCtx &t, uint32_
         ++wnext;
         return m;
     };
-    uint32_t prev = next_mask();  // word wfirst-1 (tile 0 stages an all-masked word there)
+    uint32_t prevtop = next_mask() >> 31;  // word wfirst-1 (tile 0 stages an all-masked word there)
     uint32_t cur = next_mask();
-    uint32_t carry = (fold(prev) >> (32 - u)) & 1u;  // previous word's last unit is full
+    uint32_t st0 = NOPOS, st1 = NOPOS;
 #pragma unroll 1
-    for (uint32_t i = 0; i <= nw; ++i) {
-        const uint32_t w = wfirst + i;
-        const uint32_t f = fold(cur);
-        uint32_t g = f & ~(((ulog < 5) ? (f << u) : 0u) | carry);  // first full unit of its run
-        while (g) {
-            const uint32_t b = __ffs(g) - 1;
-            g &= g - 1;
-            const uint32_t below = __funnelshift_r(prev, cur, b);  // the 32 positions just below b
-            const uint32_t cnt = __clz(~below);                     // matches directly below the unit
-            const uint32_t st = (w << 5) + b - cnt;
-            if (st >= lo_pos && st < hi_pos) push_start(p, t, ke, k, st, cnt + u);
+    for (uint32_t i = 0; i < nw; ++i) {
+        const uint32_t nxt = next_mask();
+        uint64_t v = ((uint64_t)nxt << 32) | cur;  // bit j <- bits j .. j+re-1 all set
+        v &= v >> e0; v &= v >> e1; v &= v >> e2; v &= v >> e3; v &= v >> e4;
+        uint32_t starts = (uint32_t)v & ~((cur << 1) | prevtop);
+        while (starts) {  // rare: genuine starts of runs of >= re matches
+            const uint32_t st = ((wfirst + i) << 5) + (__ffs(starts) - 1);
+            starts &= starts - 1;
+            if (st0 == NOPOS) st0 = st;
+            else if (st1 == NOPOS) st1 = st;
+            else {
+                const uint32_t slot = atomicAdd(t.nstart, 1u);
+                if (slot < STARTQ_CAP) t.startq[slot] = make_uint2(st, k | (re << 16));
+                else handle_start(p, t, p.ktab[k], k, st, re);
+            }
         }
-        carry = (f >> (32 - u)) & 1u;
-        prev = cur;
-        if (i < nw) cur = next_mask();
+        prevtop = cur >> 31;
+        cur = nxt;
+    }
+    if (st0 != NOPOS) {
+        const KEntry ke = p.ktab[k];
+        handle_start(p, t, ke, k, st0, re);
+        if (st1 != NOPOS) handle_start(p, t, ke, k, st1, re);
     }
 }
 
@@ -304,16 +303,19 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
     const uint32_t tile = blockIdx.x;
     const uint32_t w0 = tile * TW;
     // smem index j <-> absolute word w0 - 1 + j
+    uint32_t any_mask = 0;
     for (uint32_t j = tid; j < nsm; j += THREADS) {
         const bool real = (w0 + j) != 0;
         const uint32_t w = w0 + j - 1;
         const uint32_t a = pad_idx(j);
         sH[a] = real ? __ldg(p.H + w) : 0u;
         sL[a] = real ? __ldg(p.L + w) : 0u;
-        sN[a] = real ? __ldg(p.NM + w) : 0xFFFFFFFFu;
+        const uint32_t nmw = real ? __ldg(p.NM + w) : 0xFFFFFFFFu;
+        sN[a] = nmw;
+        any_mask |= nmw;
     }
     if (tid < 16) s_misc[tid] = 0;
-    __syncthreads();
+    const bool tile_has_n = __syncthreads_or(any_mask != 0);  // masked positions anywhere in the staged words
 
     TileCtx tc;
     tc.sH = sH; tc.sL = sL; tc.sN = sN; tc.wbase = w0; tc.nsm = nsm;
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
         __syncthreads();
         if (tid == 0) ncand += total;
         if (p.debug_flags & 1u) total = 0;  // profiling only: fast phase alone
-        // ... stage A: one thread per (strip, k) hit finds the run starts and queues them
+        // ... one thread per (strip, k) hit: find the run starts, follow each run, emit
         for (uint32_t item = tid; item < total; item += THREADS) {
             uint32_t lo = 0, hi = THREADS - 1;  // last strip whose exclusive prefix is <= item
             while (lo < hi) {
@@ -415,11 +417,11 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
                 if (n < c) { k = s_misc[12 + b] * 32 + __fns(mask, 0, n + 1); break; }
                 n -= c;
             }
-            exact_find(p, tc, w0 + lo * T, T, k);
+            if (tile_has_n) exact_item<true>(p, tc, w0 + lo * T, T, k);
+            else exact_item<false>(p, tc, w0 + lo * T, T, k);
         }
         __syncthreads();
-        // ... stage B: one thread per run start walks to the run end, applies thresholds and
-        //     primitivity, and appends the result
+        // ... overflow queue (more than two run starts in one strip for one k)
         const uint32_t nst = min(s_misc[10], STARTQ_CAP);
         for (uint32_t e = tid; e < nst; e += THREADS) {
             const uint2 q = s_startq[e];
