@@ -1,0 +1,153 @@
+"""GPU tests at the BASELINE.json workload shapes: CLI files, partitioned scans with stitching, the
+chr22-sized record against the oracle, the hg38-sized genome through size-independent properties
+plus sampled windows against the oracle, and the many-reads path."""
+import argparse
+import gzip
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "colab-repeat-finder_b200"))
+
+from tests.helpers import ns, random_seq  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+DEFAULTS = dict(min_motif_size=1, max_motif_size=50, min_repeats=3, min_span=9)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    import perfect_repeat_finder as prf
+    from crf_b200 import _cabi, api, cli, partition, synth
+    from oracle import oracle
+    return argparse.Namespace(torch=torch, prf=prf, cabi=_cabi, api=api, cli=cli, partition=partition, synth=synth,
+                              oracle=oracle)
+
+
+def _oracle_rows(oracle, seq, **kw):
+    fs = ns(**{**DEFAULTS, **kw})
+    return oracle.detect_repeats_by_k(seq, fs)
+
+
+def test_cli_fasta_to_bed_and_raw_to_tsv(mods, tmp_path, monkeypatch, capsys):
+    rng = random.Random(1)
+    recs = [("chrA", random_seq(rng, 30000)), ("chrB desc", random_seq(rng, 100)), ("e", ""), ("chrC", random_seq(rng, 70000))]
+    fa = tmp_path / "toy.fa.gz"
+    with gzip.open(fa, "wt") as f:
+        for name, seq in recs:
+            f.write(f">{name}\n")
+            for i in range(0, len(seq), 60):
+                f.write(seq[i:i + 60] + "\n")
+    monkeypatch.chdir(tmp_path)
+    assert mods.cli.main([str(fa), "-min", "1", "-max", "20"]) == 0
+    out = capsys.readouterr().out
+    assert "Processing chrA (30,000 bp)" in out and "Wrote results to toy.bed" in out
+    want = []
+    for name, seq in recs:
+        for s, e, m in _oracle_rows(mods.oracle, seq, max_motif_size=20):
+            want.append(f"{name.split()[0]}\t{s}\t{e}\t{m}\n")
+    assert open(tmp_path / "toy.bed").read() == "".join(want)
+    assert len(want) > 50
+
+    # --interval on one record: identical to the reference semantics (oracle with interval attrs)
+    assert mods.cli.main([str(fa), "-max", "20", "--interval", "chrC:1000-9000", "-o", str(tmp_path / "iv")]) == 0
+    fs = ns(**{**DEFAULTS, "max_motif_size": 20}, interval_start_0based=1000, interval_end=9000)
+    want_iv = "".join(f"chrC\t{s}\t{e}\t{m}\n" for s, e, m in mods.oracle.detect_repeats(recs[3][1], fs))
+    assert open(tmp_path / "iv.bed").read() == want_iv and want_iv
+
+    # raw sequence -> TSV with header
+    assert mods.cli.main(["ACGT" * 5 + "nnnn" + "a" * 12, "-o", str(tmp_path / "raw")]) == 0
+    assert open(tmp_path / "raw.tsv").read() == "start_0based\tend\tmotif\n0\t20\tACGT\n24\t36\tA\n"
+
+
+def test_partitioned_scan_with_stitching_on_gpu(mods):
+    """Config C4 in miniature: repeats of 0.5 / 1 / 2.5 chunks around unit boundaries; the chunked,
+    halo-limited scan must equal the whole-record scan."""
+    chunk, halo = 65536, 4096
+    bases, offsets, meta = mods.synth.sx(4_000_000, chunk, device=None)
+    ctx = mods.api.get_context()
+    whole = mods.api.scan_arrays(bases, 1, 50, 3, 9)
+    rec, st, en, k = mods.partition.scan_partitioned(ctx, bases, [0], [bases.size], 1, 50, 3, 9, chunk=chunk, halo=halo)
+    assert np.array_equal(st, whole[0]) and np.array_equal(en, whole[1]) and np.array_equal(k, whole[2])
+    spans = (whole[1].astype(np.int64) - whole[0])
+    assert (spans > chunk + halo).sum() >= 5, "the workload must contain runs that need stitching"
+    # and the whole-record scan itself equals the oracle
+    o_s, o_e, o_m, _ = mods.oracle.detect_repeats_by_k(bases, ns(**DEFAULTS), arrays=True)
+    assert np.array_equal(whole[0], o_s) and np.array_equal(whole[1], o_e) and np.array_equal(whole[2], o_m)
+
+
+def test_chr22_sized_record_bit_exact(mods):
+    """Configs C1 / C2 on the chr22-shaped stand-in (benchmark/chr22.fa.gz is not in the reference checkout)."""
+    bases, offsets, meta = mods.synth.s22(device="cuda:0")
+    host = bases.cpu().numpy()
+    for kw in (dict(min_motif_size=2, max_motif_size=6), dict()):
+        fs = {**DEFAULTS, **kw}
+        st, en, k = mods.api.scan_arrays(host, fs["min_motif_size"], fs["max_motif_size"], 3, 9)
+        o_s, o_e, o_m, _ = mods.oracle.detect_repeats_by_k(host, ns(**fs), arrays=True)
+        assert len(o_s) > 20000
+        assert np.array_equal(st, o_s) and np.array_equal(en, o_e) and np.array_equal(k, o_m)
+
+
+def test_hg38_sized_genome_properties_and_sampled_windows(mods):
+    """Config C3 at full size: ordering / threshold / primitivity properties on every row, and 24 windows
+    compared row by row with the oracle."""
+    torch = mods.torch
+    bases, offsets, meta = mods.synth.s38(device="cuda:0")
+    ctx = mods.api.get_context()
+    with ctx.load(bases.data_ptr(), offsets, max_motif_cap=50, on_device=True) as seq:
+        n = seq.scan(1, 50, 3, 9)
+        rec, st, en, k = seq.fetch(n)
+    assert n > 5_000_000
+    rec64, st64, en64, k64 = (a.astype(np.int64) for a in (rec, st, en, k))
+    key = (rec64 << 40) | st64
+    assert np.all(np.diff(key) >= 0)                                      # sorted by (record, start)
+    same = np.diff(key) == 0
+    assert np.all(np.diff(en64)[same] > 0)                                 # ... then by end, keys unique
+    assert np.all(en64 - st64 >= np.maximum(9, 3 * k64))                   # span >= max(min_span, min_repeats*k)
+    assert k64.min() >= 1 and k64.max() <= 50
+    lengths = np.diff(offsets.astype(np.int64))
+    assert np.all(en64 <= lengths[rec64])
+    rng = np.random.default_rng(5)
+    margin, win = 3000, 400_000
+    checked = 0
+    for _ in range(24):
+        r = int(rng.integers(0, 24))
+        a = int(rng.integers(0, lengths[r] - win))
+        sl = bases[int(offsets[r]) + a:int(offsets[r]) + a + win].cpu().numpy()
+        o_s, o_e, o_m, _ = mods.oracle.detect_repeats_by_k(sl, ns(**DEFAULTS), arrays=True)
+        inside = (o_s >= margin) & (o_e <= win - margin)
+        sel = (rec64 == r) & (st64 >= a + margin) & (en64 <= a + win - margin)
+        assert np.array_equal(st64[sel] - a, o_s[inside]) and np.array_equal(en64[sel] - a, o_e[inside])
+        assert np.array_equal(k64[sel], o_m[inside])
+        checked += int(inside.sum())
+    assert checked > 10_000
+
+
+def test_many_reads_path(mods):
+    """Config C5 in miniature: 200 000 independent 150-bp reads, motif 1-20; coordinates are per read and no
+    repeat may span two reads."""
+    n_reads = 200_000
+    bases, offsets, meta = mods.synth.sr(n_reads, device="cuda:0")
+    ctx = mods.api.get_context()
+    with ctx.load(bases.data_ptr(), offsets, max_motif_cap=20, on_device=True) as seq:
+        n = seq.scan(1, 20, 3, 9)
+        rec, st, en, k = seq.fetch(n)
+    assert n > 10_000 and en.max() <= 150
+    host = bases.cpu().numpy().reshape(n_reads, 150)
+    fs = ns(**{**DEFAULTS, "max_motif_size": 20})
+    rng = np.random.default_rng(9)
+    for r in rng.choice(n_reads, 3000, replace=False).tolist():
+        want = mods.oracle.detect_repeats_by_k(np.ascontiguousarray(host[r]), fs, arrays=True)
+        sel = rec == r
+        assert np.array_equal(st[sel], want[0]) and np.array_equal(en[sel], want[1]) and np.array_equal(k[sel], want[2])
+    # every read with a result: cross-check a few hundred against the oracle too
+    for r in np.unique(rec)[:300].tolist():
+        want = mods.oracle.detect_repeats_by_k(np.ascontiguousarray(host[r]), fs, arrays=True)
+        sel = rec == r
+        assert np.array_equal(st[sel], want[0]) and np.array_equal(en[sel], want[1])
