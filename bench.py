@@ -201,58 +201,55 @@ def main():
 
     seq = ctx.load_ranges(bases.data_ptr(), starts, lens, own_lo, own_hi, max_motif_cap=KMAX, on_device=True)
     info = seq.info()
-    unit_len = torch.from_numpy(lens.astype(np.int64)).to(dev)
-    unit_open_ok = torch.tensor([u.d1 < u.rec_len for u in mine], dtype=torch.bool, device=dev)
-    unit_d0 = torch.tensor([u.d0 for u in mine], dtype=torch.int32, device=dev)
-    unit_rec = torch.tensor([u.record for u in mine], dtype=torch.int32, device=dev)
 
     def one_step():
         return seq.scan(KMIN, KMAX, MIN_REPEATS, MIN_SPAN, **knobs)
 
+    if world > 1:   # results come out in chromosome coordinates; open-ended results are counted by the library
+        seq.set_output_map(out_record=[u.record for u in mine], out_shift=[u.d0 for u in mine],
+                           open_ended=[int(u.d1 < u.rec_len) for u in mine])
+    gstate = {"cap": 0, "buf": None, "out": None}
+    first_t = torch.tensor([plan._first_of_record.get(r, 0) for r in range(len(lengths))], dtype=torch.int64, device=dev)
+    d1_t = torch.tensor([u.d1 for u in plan.units], dtype=torch.int32, device=dev)
+    len_t = torch.tensor(lengths, dtype=torch.int32, device=dev)
+
     def gather_to_rank0(n):
-        """N > 1: compacted results -> rank 0 (the only collective of the path); runs that left their unit's
-        data (longer than the halo) are stitched first.  Returns the whole-job result count."""
+        """N > 1: compacted results -> rank 0 (the only collective of the path: one 16-byte all-gather of
+        (count, open count), one gather of the rows); runs that left their unit's data (longer than the halo)
+        are stitched first.  Returns the whole-job result count."""
         if world == 1:
             return n
-        rec = torch.empty(n, dtype=torch.int32, device=dev)
-        st, en, kk = torch.empty_like(rec), torch.empty_like(rec), torch.empty_like(rec)
+        n_open = int(seq.stats().n_open)
+        hdr = torch.tensor([n, n_open], dtype=torch.int64, device=dev)
+        hdrs = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(hdrs, hdr)
+        hdrs = hdrs.cpu().tolist()
+        counts, any_open = hdrs[0::2], sum(hdrs[1::2])
+        if max(counts) > gstate["cap"]:
+            cap = int(max(counts) * 1.05) + 1024
+            gstate["cap"] = cap
+            gstate["buf"] = torch.zeros(4 * cap, dtype=torch.int32, device=dev)
+            gstate["out"] = [torch.empty_like(gstate["buf"]) for _ in range(world)] if rank == 0 else None
+        cap, buf = gstate["cap"], gstate["buf"]
+        rec, st, en, kk = (buf[i * cap:i * cap + n] for i in range(4))
         seq.fetch_device(rec.data_ptr(), st.data_ptr(), en.data_ptr(), kk.data_ptr(), n)
-        ul = rec.long()
-        is_open = (en.long() == unit_len[ul]) & unit_open_ok[ul]
-        flag = torch.tensor([int(is_open.any().item())], dtype=torch.int64, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        g_rec, g_st, g_en = unit_rec[ul], st + unit_d0[ul], en + unit_d0[ul]
-        if int(flag.item()):                       # rare: a repeat longer than the halo crossed a unit end
-            idx = torch.nonzero(is_open).flatten()
-            open_mine = [tuple(int(x) for x in row) for row in
-                         torch.stack([g_rec[idx], g_st[idx], g_en[idx], kk[idx]], 1).cpu().tolist()]
-            parts = [None] * world
-            dist.all_gather_object(parts, open_mine)
-            open_all = [x for part in parts for x in part]
-
-            def exchange(ans):
-                out = [None] * world
-                dist.all_gather_object(out, ans)
-                merged = {}
-                for part in out:
-                    merged.update(part)
-                return merged
-            fixed = partition.stitch(plan, open_all, lambda unit, lp, k: seq.run_end(unit.index - plan.bounds[rank], lp, k),
-                                     exchange, rank)
+        if any_open:                                  # rare: a repeat longer than the halo crossed a unit end
+            open_idx, rows = [], None
+            if n_open:                                # this rank's open rows: end == end of the owning unit's data
+                unit_idx = first_t[rec.long()] + torch.div(st, plan.chunk, rounding_mode="floor").long()
+                d1 = d1_t[unit_idx]
+                idx_t = torch.nonzero((en == d1) & (d1 < len_t[rec.long()])).flatten()
+                rows = torch.stack([rec[idx_t], st[idx_t], en[idx_t], kk[idx_t]], 1).cpu().numpy().astype(np.int64)
+                open_idx = idx_t.cpu().tolist()
+            open_mine = [tuple(int(x) for x in row) for row in rows] if open_idx else []
+            fixed = partition.stitch_collective(
+                plan, open_mine, lambda unit, lp, k: seq.run_end(unit.index - plan.bounds[rank], lp, k), rank, world,
+                dist, dev)
             mine_fixed = {(r_, s_, k_): e_ for (r_, s_, e_, k_) in fixed}
-            for j in idx.tolist():
-                key = (int(g_rec[j]), int(g_st[j]), int(kk[j]))
-                g_en[j] = mine_fixed[key]
-        packed = torch.stack([g_rec, g_st, g_en, kk])
-        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev))
-        counts = [int(c.item()) for c in counts]
-        mx = max(counts)
-        pad = torch.zeros((4, mx), dtype=torch.int32, device=dev)
-        pad[:, :n] = packed
-        out = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, out, dst=0)     # rank order == genome order: concatenation is the sorted result
-        return sum(counts)
+            for j, row in zip(open_idx, rows if open_idx else []):
+                en[j] = mine_fixed[(int(row[0]), int(row[1]), int(row[3]))]
+        dist.gather(buf, gstate["out"], dst=0)       # rank order == genome order: concatenation is the sorted result
+        return int(sum(counts))
 
     # ---- device-resident timing ----
     for _ in range(args.warmup):

@@ -18,7 +18,7 @@ CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_C
 #: every symbol include/crf.h declares (tests check the library exports all of them)
 EXPORTS = [
     "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
-    "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
+    "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
     "crf_scan_stats", "crf_run_end",
 ]
 
@@ -43,7 +43,7 @@ class ScanStats(ctypes.Structure):
     _fields_ = [("scan_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("n_results", ctypes.c_uint64),
                 ("n_tiles", ctypes.c_uint64), ("n_spilled", ctypes.c_uint64), ("n_long", ctypes.c_uint64),
                 ("n_candidates", ctypes.c_uint64), ("word_k_pairs", ctypes.c_uint64), ("reruns", ctypes.c_uint32),
-                ("launches", ctypes.c_uint32)]
+                ("launches", ctypes.c_uint32), ("n_open", ctypes.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -71,6 +71,7 @@ def lib():
         L.crf_ctx_synchronize.argtypes = [vp]
         L.crf_seq_load_ascii.argtypes = [vp, vp, vp, u32, u32, i, P(vp)]
         L.crf_seq_load_ascii_ranges.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, i, P(vp)]
+        L.crf_seq_set_output_map.argtypes = [vp, vp, vp, vp]
         L.crf_seq_destroy.argtypes = [vp]
         L.crf_seq_info.argtypes = [vp, P(SeqInfo)]
         L.crf_scan.argtypes = [vp, P(ScanParams), P(u64)]
@@ -179,6 +180,16 @@ class Sequence:
                                         self.n_records, int(max_motif_cap), int(bool(on_device)),
                                         ctypes.byref(self._h)))
         del keep
+
+    def set_output_map(self, out_record=None, out_shift=None, open_ended=None):
+        """Report results in the coordinates of the chromosomes the units were cut from (crf_seq_set_output_map)."""
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=dt)
+                for a, dt in ((out_record, np.uint32), (out_shift, np.uint64), (open_ended, np.uint8))]
+        for a in arrs:
+            if a is not None and a.size != self.n_records:
+                raise ValueError("output map arrays need one entry per record of the load")
+        _check(lib().crf_seq_set_output_map(self._h, *(ctypes.c_void_p(a.ctypes.data if a is not None else 0)
+                                                       for a in arrs)))
 
     def info(self):
         out = SeqInfo()

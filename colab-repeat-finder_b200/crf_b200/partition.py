@@ -131,6 +131,38 @@ def stitch(plan, open_runs, run_end_fn, exchange_fn=None, rank=0):
     return [(rec, s, final_i0[i] + k, k) for i, (rec, s, _e, k) in enumerate(open_runs)]
 
 
+MAX_OPEN_PER_RANK = 256
+
+
+def stitch_collective(plan, open_mine, run_end_fn, rank, world, dist, device):
+    """stitch() for world > 1 with fixed-size tensor collectives (two small all-gathers + one all-reduce
+    per hop) instead of pickled objects.  open_mine: this rank's (record, start, end_lower_bound, k) rows.
+    Returns the stitched rows of ALL ranks, identical on every rank."""
+    import torch
+    if len(open_mine) > MAX_OPEN_PER_RANK:
+        raise RuntimeError(f"{len(open_mine)} open runs on one rank (limit {MAX_OPEN_PER_RANK})")
+    mine = torch.full((MAX_OPEN_PER_RANK + 1, 4), -1, dtype=torch.int64)
+    mine[0, 0] = len(open_mine)
+    if open_mine:
+        mine[1:1 + len(open_mine)] = torch.tensor(open_mine, dtype=torch.int64)
+    mine = mine.to(device)
+    allrows = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allrows, mine)
+    allrows = allrows.cpu().numpy()
+    open_all = [tuple(int(x) for x in allrows[r, 1 + i]) for r in range(world) for i in range(int(allrows[r, 0, 0]))]
+
+    def exchange(answers):
+        t = torch.full((max(len(open_all), 1),), -1, dtype=torch.int64)
+        for i, v in answers.items():
+            t[i] = v
+        t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = t.cpu().tolist()
+        return {i: v for i, v in enumerate(t) if v >= 0}
+
+    return stitch(plan, open_all, run_end_fn, exchange, rank)
+
+
 def scan_partitioned(ctx, bases, record_starts, lengths, kmin, kmax, min_repeats, min_span, rank=0, world=1,
                      chunk=DEFAULT_CHUNK, halo=DEFAULT_HALO, on_device=False, dist=None, **knobs):
     """Scan `lengths` records split over `world` ranks; every rank returns the full, stitched,

@@ -53,7 +53,9 @@ struct crf_seq {
     uint32_t n_records = 0;
     uint32_t layout_len = 0, n_words = 0, n_words_alloc = 0, cap = 0;
     uint32_t *H = nullptr, *L = nullptr, *NM = nullptr, *X = nullptr;
-    uint32_t *d_rec_dev_off = nullptr, *d_own_lo = nullptr, *d_own_hi = nullptr;
+    uint32_t *d_rec_dev_off = nullptr, *d_own_lo = nullptr, *d_own_hi = nullptr, *d_rec_len = nullptr;
+    uint32_t *d_map_rec = nullptr, *d_map_shift = nullptr;
+    uint8_t *d_map_open = nullptr;
     std::vector<uint32_t> h_rec_dev_off;
     std::vector<uint64_t> h_rec_len;
     uint64_t *ex_key = nullptr;
@@ -168,7 +170,8 @@ static void free_seq(crf_seq *s) {
     if (!s) return;
     if (s->ctx) cudaSetDevice(s->ctx->device);
     dev_free(s->H); dev_free(s->L); dev_free(s->NM); dev_free(s->X);
-    dev_free(s->d_rec_dev_off); dev_free(s->d_own_lo); dev_free(s->d_own_hi); dev_free(s->ex_key); dev_free(s->d_ktab); dev_free(s->d_segs);
+    dev_free(s->d_rec_dev_off); dev_free(s->d_own_lo); dev_free(s->d_own_hi); dev_free(s->d_rec_len);
+    dev_free(s->d_map_rec); dev_free(s->d_map_shift); dev_free(s->d_map_open); dev_free(s->ex_key); dev_free(s->d_ktab); dev_free(s->d_segs);
     dev_free(s->stage_key); dev_free(s->spill_key); dev_free(s->fin_key);
     dev_free(s->stage_k); dev_free(s->spill_k); dev_free(s->fin_k);
     dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
@@ -229,7 +232,6 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     uint64_t src_base = 0;
     uint8_t *d_src_own = nullptr;
     uint64_t *d_src_start = nullptr;
-    uint32_t *d_len = nullptr;
     if (!on_device) {               // one H2D copy of the span the records cover (units may overlap)
         CHECK(dev_alloc(&d_src_own, (size_t)(src_hi - src_lo)));
         if (src_hi > src_lo) CU(cudaMemcpyAsync(d_src_own, bases + src_lo, src_hi - src_lo, cudaMemcpyHostToDevice, st));
@@ -253,7 +255,7 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
         }
     }
     int rc = dev_alloc(&d_src_start, n_records);
-    if (!rc) rc = dev_alloc(&d_len, n_records);
+    if (!rc) rc = dev_alloc(&s->d_rec_len, n_records);
     if (!rc) rc = dev_alloc(&s->d_rec_dev_off, n_records);
     if (!rc && !olo.empty()) rc = dev_alloc(&s->d_own_lo, n_records);
     if (!rc && !olo.empty()) rc = dev_alloc(&s->d_own_hi, n_records);
@@ -267,7 +269,7 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     if (!rc) {
         const size_t n4 = (size_t)n_records * 4;
         e = cudaMemcpyAsync(d_src_start, rel.data(), (size_t)n_records * 8, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_len, len32.data(), n4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_rec_len, len32.data(), n4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_rec_dev_off, s->h_rec_dev_off.data(), n4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess && !olo.empty()) e = cudaMemcpyAsync(s->d_own_lo, olo.data(), n4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess && !olo.empty()) e = cudaMemcpyAsync(s->d_own_hi, ohi.data(), n4, cudaMemcpyHostToDevice, st);
@@ -275,7 +277,7 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     }
     if (!rc && e == cudaSuccess) {
         PackParams pp;
-        pp.src = d_src; pp.rec_src_start = d_src_start; pp.rec_len = d_len; pp.rec_dev_off = s->d_rec_dev_off;
+        pp.src = d_src; pp.rec_src_start = d_src_start; pp.rec_len = s->d_rec_len; pp.rec_dev_off = s->d_rec_dev_off;
         pp.n_records = n_records;
         pp.n_words_alloc = s->n_words_alloc; pp.H = s->H; pp.L = s->L; pp.NM = s->NM; pp.X = s->X;
         pp.ex_key = s->ex_key; pp.ex_cap = s->ex_cap; pp.ex_count = s->d_counters;
@@ -286,7 +288,6 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     }
     if (d_src_own) cudaFree(d_src_own);
     if (d_src_start) cudaFree(d_src_start);
-    if (d_len) cudaFree(d_len);
     if (rc) return rc;
     if (e != cudaSuccess) { set_err("crf_seq_load_ascii: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
 
@@ -363,6 +364,34 @@ extern "C" int crf_seq_destroy(crf_seq *s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     free_seq(s);
+    return CRF_OK;
+}
+
+extern "C" int crf_seq_set_output_map(crf_seq *s, const uint32_t *out_record, const uint64_t *out_shift,
+                                      const uint8_t *open_ended) {
+    if (!s) { set_err("crf_seq_set_output_map: null sequence"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    CU(cudaStreamSynchronize(st));
+    dev_free(s->d_map_rec); dev_free(s->d_map_shift); dev_free(s->d_map_open);
+    const uint32_t n = s->n_records;
+    if (out_record) {
+        CHECK(dev_alloc(&s->d_map_rec, n));
+        CU(cudaMemcpy(s->d_map_rec, out_record, (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    if (out_shift) {
+        std::vector<uint32_t> sh(n);
+        for (uint32_t r = 0; r < n; ++r) {
+            if (out_shift[r] > 0xFFFFFFFFull - s->h_rec_len[r]) { set_err("crf_seq_set_output_map: shifted coordinates exceed 32 bits"); return CRF_ERR_UNSUPPORTED; }
+            sh[r] = (uint32_t)out_shift[r];
+        }
+        CHECK(dev_alloc(&s->d_map_shift, n));
+        CU(cudaMemcpy(s->d_map_shift, sh.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    if (open_ended) {
+        CHECK(dev_alloc(&s->d_map_open, n));
+        CU(cudaMemcpy(s->d_map_open, open_ended, n, cudaMemcpyHostToDevice));
+    }
     return CRF_OK;
 }
 
@@ -560,8 +589,12 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         const uint32_t ggrid = (n_tiles * 32 + 255) / 256;
         gather_kernel<<<ggrid, 256, 0, st>>>(g);
         const uint32_t tgrid = std::min<uint32_t>(148 * 8, (s->res_cap + 255) / 256);
-        translate_kernel<<<tgrid, 256, 0, st>>>(s->fin_key, s->fin_k, s->d_rec_dev_off, s->n_records, s->d_counters,
-                                               s->res_cap, s->o_rec, s->o_start, s->o_end, s->o_k);
+        TranslateParams tp;
+        tp.fin_key = s->fin_key; tp.fin_k = s->fin_k; tp.rec_dev_off = s->d_rec_dev_off; tp.rec_len = s->d_rec_len;
+        tp.map_rec = s->d_map_rec; tp.map_shift = s->d_map_shift; tp.map_open = s->d_map_open;
+        tp.n_records = s->n_records; tp.fin_cap = s->res_cap; tp.counters = s->d_counters;
+        tp.o_rec = s->o_rec; tp.o_start = s->o_start; tp.o_end = s->o_end; tp.o_k = s->o_k;
+        translate_kernel<<<tgrid, 256, 0, st>>>(tp);
         CU(cudaGetLastError());
         launches += 5;
         CU(cudaEventRecord(s->ev[3], st));
@@ -580,11 +613,12 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
             CHECK(bitonic_sort(st, s->spill_key, s->spill_k, (uint32_t)n_spill, &launches));
             g.spill_sorted = 1;
             gather_kernel<<<ggrid, 256, 0, st>>>(g);
-            translate_kernel<<<tgrid, 256, 0, st>>>(s->fin_key, s->fin_k, s->d_rec_dev_off, s->n_records, s->d_counters,
-                                                   s->res_cap, s->o_rec, s->o_start, s->o_end, s->o_k);
+            CU(cudaMemsetAsync(s->d_counters + C_OPEN, 0, sizeof(unsigned long long), st));
+            translate_kernel<<<tgrid, 256, 0, st>>>(tp);
             CU(cudaGetLastError());
             launches += 2;
             CU(cudaEventRecord(s->ev[3], st));
+            CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
         }
         float ms_all = 0, ms_k = 0;
@@ -598,6 +632,7 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         s->stats.n_tiles = n_tiles;
         s->stats.n_spilled = n_spill;
         s->stats.n_long = s->h_counters[C_LONG];
+        s->stats.n_open = s->h_counters[C_OPEN];
         s->stats.n_candidates = s->h_counters[C_CAND];
         s->stats.word_k_pairs = (uint64_t)s->n_words * (pr->max_motif_size - pr->min_motif_size + 1);
         s->stats.reruns = reruns;

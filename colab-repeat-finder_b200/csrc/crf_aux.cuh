@@ -215,29 +215,41 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherParams g) {
     }
 }
 
-// layout coordinates -> (record, start, end, k)  (the re-offsetting of prf:81, per record)
-__global__ void __launch_bounds__(256) translate_kernel(const uint64_t *fin_key, const uint16_t *fin_k,
-                                                        const uint32_t *rec_dev_off, uint32_t n_records,
-                                                        const unsigned long long *counters, uint32_t fin_cap,
-                                                        uint32_t *o_rec, uint32_t *o_start, uint32_t *o_end,
-                                                        uint32_t *o_k) {
-    const unsigned long long n = counters[C_TOTAL];
-    if (n > fin_cap) return;
+// layout coordinates -> (record, start, end, k)  (the re-offsetting of prf:81, per record); with an
+// output map (partitioned loads) the unit's record id / offset are applied and open-ended results counted
+struct TranslateParams {
+    const uint64_t *fin_key;
+    const uint16_t *fin_k;
+    const uint32_t *rec_dev_off, *rec_len;
+    const uint32_t *map_rec, *map_shift;   // nullable
+    const uint8_t *map_open;               // nullable
+    uint32_t n_records, fin_cap;
+    unsigned long long *counters;
+    uint32_t *o_rec, *o_start, *o_end, *o_k;
+};
+
+__global__ void __launch_bounds__(256) translate_kernel(const TranslateParams t) {
+    const unsigned long long n = t.counters[C_TOTAL];
+    if (n > t.fin_cap) return;
     const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t n_open = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t key = fin_key[i];
+        const uint64_t key = t.fin_key[i];
         const uint32_t st = (uint32_t)(key >> 32), en = (uint32_t)key;
-        uint32_t lo = 0, hi = n_records - 1;
+        uint32_t lo = 0, hi = t.n_records - 1;
         while (lo < hi) {
             const uint32_t mid = (lo + hi + 1) >> 1;
-            if (rec_dev_off[mid] <= st) lo = mid; else hi = mid - 1;
+            if (t.rec_dev_off[mid] <= st) lo = mid; else hi = mid - 1;
         }
-        const uint32_t d0 = rec_dev_off[lo];
-        o_rec[i] = lo;
-        o_start[i] = st - d0;
-        o_end[i] = en - d0;
-        o_k[i] = fin_k[i];
+        const uint32_t d0 = t.rec_dev_off[lo];
+        const uint32_t shift = t.map_shift ? t.map_shift[lo] : 0u;
+        if (t.map_open && t.map_open[lo] && en - d0 == t.rec_len[lo]) ++n_open;
+        t.o_rec[i] = t.map_rec ? t.map_rec[lo] : lo;
+        t.o_start[i] = st - d0 + shift;
+        t.o_end[i] = en - d0 + shift;
+        t.o_k[i] = t.fin_k[i];
     }
+    if (n_open) atomicAdd(t.counters + C_OPEN, (unsigned long long)n_open);
 }
 
 // ---- fallback ordering: global bitonic network on (key, k); n_pow2 elements, tail padded with

@@ -76,7 +76,7 @@ struct ScanParams {
     unsigned long long *counters;  // see CounterIdx
 };
 
-enum CounterIdx { C_STAGE = 0, C_SPILL = 1, C_LONG = 2, C_CAND = 3, C_TOTAL = 4, C_COUNT = 8 };
+enum CounterIdx { C_STAGE = 0, C_SPILL = 1, C_LONG = 2, C_CAND = 3, C_TOTAL = 4, C_TILE = 5, C_OPEN = 6, C_COUNT = 8 };
 
 __device__ __forceinline__ uint32_t plane_at(const uint32_t *__restrict__ P, uint32_t w, uint32_t q, uint32_t s) {
     return __funnelshift_r(__ldg(P + w + q), __ldg(P + w + q + 1), s);

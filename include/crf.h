@@ -63,6 +63,12 @@ int crf_seq_load_ascii_ranges(crf_ctx *ctx, const uint8_t *bases, const uint64_t
                               const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records,
                               uint32_t max_motif_cap, int bases_on_device, crf_seq **seq);
 int crf_seq_destroy(crf_seq *seq);
+/* Optional, for partitioned loads: report record r of this load as record out_record[r] with start/end
+ * shifted by out_shift[r] (a unit's offset inside its chromosome), and count as "open" every result that
+ * ends exactly at the end of a record flagged in open_ended[r] (the unit's data stops before the
+ * chromosome does, so the run may continue: crf_scan_stats().n_open, see crf_run_end).  NULLs reset. */
+int crf_seq_set_output_map(crf_seq *seq, const uint32_t *out_record, const uint64_t *out_shift,
+                           const uint8_t *open_ended);
 
 typedef struct {
     uint64_t n_records;
@@ -121,6 +127,7 @@ typedef struct {
     uint64_t word_k_pairs; /* 32-base words x motif sizes evaluated                        */
     uint32_t reruns;     /* scans repeated because the result buffer was too small         */
     uint32_t launches;   /* kernels launched by the last crf_scan                          */
+    uint64_t n_open;     /* results that reached the end of an open-ended record (output map) */
 } crf_scan_stats_t;
 int crf_scan_stats(const crf_seq *seq, crf_scan_stats_t *stats);
 

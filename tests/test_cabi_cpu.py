@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     from crf_b200 import _cabi
     assert ctypes.sizeof(_cabi.ScanParams) == 9 * 4
     assert ctypes.sizeof(_cabi.SeqInfo) == 5 * 8 + 2 * 4 + 8
-    assert ctypes.sizeof(_cabi.ScanStats) == 2 * 8 + 6 * 8 + 2 * 4
+    assert ctypes.sizeof(_cabi.ScanStats) == 2 * 8 + 6 * 8 + 2 * 4 + 8
 
 
 def test_sass_is_sm100a_only():
