@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--words-per-thread", type=int, default=0)
+    ap.add_argument("--trace", action="store_true", help="print per-stage host timings of one extra step (stderr)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -209,9 +210,13 @@ def main():
         seq.set_output_map(out_record=[u.record for u in mine], out_shift=[u.d0 for u in mine],
                            open_ended=[int(u.d1 < u.rec_len) for u in mine])
     gstate = {"cap": 0, "buf": None, "out": None}
-    first_t = torch.tensor([plan._first_of_record.get(r, 0) for r in range(len(lengths))], dtype=torch.int64, device=dev)
-    d1_t = torch.tensor([u.d1 for u in plan.units], dtype=torch.int32, device=dev)
-    len_t = torch.tensor(lengths, dtype=torch.int32, device=dev)
+
+    trace = {"on": False, "t": []}
+
+    def mark(name):
+        if trace["on"]:
+            torch.cuda.synchronize()
+            trace["t"].append((name, time.perf_counter()))
 
     def gather_to_rank0(n):
         """N > 1: compacted results -> rank 0 (the only collective of the path: one 16-byte all-gather of
@@ -224,6 +229,7 @@ def main():
         hdrs = torch.empty(2 * world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(hdrs, hdr)
         hdrs = hdrs.cpu().tolist()
+        mark('hdr all-gather')
         counts, any_open = hdrs[0::2], sum(hdrs[1::2])
         if max(counts) > gstate["cap"]:
             cap = int(max(counts) * 1.05) + 1024
@@ -233,22 +239,21 @@ def main():
         cap, buf = gstate["cap"], gstate["buf"]
         rec, st, en, kk = (buf[i * cap:i * cap + n] for i in range(4))
         seq.fetch_device(rec.data_ptr(), st.data_ptr(), en.data_ptr(), kk.data_ptr(), n)
-        if any_open:                                  # rare: a repeat longer than the halo crossed a unit end
-            open_idx, rows = [], None
-            if n_open:                                # this rank's open rows: end == end of the owning unit's data
-                unit_idx = first_t[rec.long()] + torch.div(st, plan.chunk, rounding_mode="floor").long()
-                d1 = d1_t[unit_idx]
-                idx_t = torch.nonzero((en == d1) & (d1 < len_t[rec.long()])).flatten()
-                rows = torch.stack([rec[idx_t], st[idx_t], en[idx_t], kk[idx_t]], 1).cpu().numpy().astype(np.int64)
-                open_idx = idx_t.cpu().tolist()
-            open_mine = [tuple(int(x) for x in row) for row in rows] if open_idx else []
+        mark('fetch_device')
+        if any_open:                                  # a repeat longer than the halo crossed a unit end
+            open_rows = seq.fetch_open() if n_open else np.zeros((0, 5), np.uint32)
+            open_mine = [tuple(int(x) for x in row[1:]) for row in open_rows]
             fixed = partition.stitch_collective(
                 plan, open_mine, lambda unit, lp, k: seq.run_end(unit.index - plan.bounds[rank], lp, k), rank, world,
                 dist, dev)
             mine_fixed = {(r_, s_, k_): e_ for (r_, s_, e_, k_) in fixed}
-            for j, row in zip(open_idx, rows if open_idx else []):
-                en[j] = mine_fixed[(int(row[0]), int(row[1]), int(row[3]))]
+            for row in open_rows:
+                new_end = mine_fixed[(int(row[1]), int(row[2]), int(row[4]))]
+                seq.patch_end(int(row[0]), new_end)
+                en[int(row[0])] = new_end
+        mark('stitch')
         dist.gather(buf, gstate["out"], dst=0)       # rank order == genome order: concatenation is the sorted result
+        mark('gather')
         return int(sum(counts))
 
     # ---- device-resident timing ----
@@ -283,6 +288,15 @@ def main():
         elapsed_ms = float(t.item())
         dist.barrier()
     ms_per_step = elapsed_ms / args.steps
+    if args.trace:
+        trace["on"] = True
+        mark("start")
+        n_t = one_step()
+        mark("scan")
+        gather_to_rank0(n_t)
+        trace["on"] = False
+        t0_ = trace["t"][0][1]
+        log(f"[rank {rank}] trace: " + ", ".join(f"{nm} +{(t - t0_) * 1e3:.3f} ms" for nm, t in trace["t"][1:]))
     value = total_bp / (ms_per_step * 1e-3) / 1e9
     stats = seq.stats()
 

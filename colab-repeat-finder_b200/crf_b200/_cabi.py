@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrf.so")
+LIB_PATH = os.environ.get("CRF_LIB_PATH") or os.path.join(_HERE, "libcrf.so")   # override: A/B builds while tuning
 
 SCAN_NO_PRIMITIVITY = 1
 
@@ -19,7 +19,7 @@ CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_C
 EXPORTS = [
     "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
     "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
-    "crf_scan_stats", "crf_run_end",
+    "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end",
 ]
 
 
@@ -78,6 +78,8 @@ def lib():
         L.crf_fetch.argtypes = [vp, vp, vp, vp, vp, u64, i]
         L.crf_scan_stats.argtypes = [vp, P(ScanStats)]
         L.crf_run_end.argtypes = [vp, u32, u32, u32, P(u32)]
+        L.crf_fetch_open.argtypes = [vp, vp, u32, P(u32)]
+        L.crf_patch_end.argtypes = [vp, u64, u32]
         for name in EXPORTS:
             if name != "crf_last_error":
                 getattr(L, name).restype = i
@@ -217,6 +219,16 @@ class Sequence:
         out = ScanStats()
         _check(lib().crf_scan_stats(self._h, ctypes.byref(out)))
         return out
+
+    def fetch_open(self, cap=256):
+        """(n, 5) uint32 rows (row index, record, start, end, k) of the open-ended results, in result order."""
+        rows = np.zeros((cap, 5), np.uint32)
+        n = ctypes.c_uint32()
+        _check(lib().crf_fetch_open(self._h, rows.ctypes.data, cap, ctypes.byref(n)))
+        return rows[:min(n.value, cap)]
+
+    def patch_end(self, row, new_end):
+        _check(lib().crf_patch_end(self._h, int(row), int(new_end)))
 
     def run_end(self, record, pos, k):
         out = ctypes.c_uint32()

@@ -56,6 +56,7 @@ struct crf_seq {
     uint32_t *d_rec_dev_off = nullptr, *d_own_lo = nullptr, *d_own_hi = nullptr, *d_rec_len = nullptr;
     uint32_t *d_map_rec = nullptr, *d_map_shift = nullptr;
     uint8_t *d_map_open = nullptr;
+    uint32_t *d_open_rows = nullptr;
     std::vector<uint32_t> h_rec_dev_off;
     std::vector<uint64_t> h_rec_len;
     uint64_t *ex_key = nullptr;
@@ -171,7 +172,7 @@ static void free_seq(crf_seq *s) {
     if (s->ctx) cudaSetDevice(s->ctx->device);
     dev_free(s->H); dev_free(s->L); dev_free(s->NM); dev_free(s->X);
     dev_free(s->d_rec_dev_off); dev_free(s->d_own_lo); dev_free(s->d_own_hi); dev_free(s->d_rec_len);
-    dev_free(s->d_map_rec); dev_free(s->d_map_shift); dev_free(s->d_map_open); dev_free(s->ex_key); dev_free(s->d_ktab); dev_free(s->d_segs);
+    dev_free(s->d_map_rec); dev_free(s->d_map_shift); dev_free(s->d_map_open); dev_free(s->d_open_rows); dev_free(s->ex_key); dev_free(s->d_ktab); dev_free(s->d_segs);
     dev_free(s->stage_key); dev_free(s->spill_key); dev_free(s->fin_key);
     dev_free(s->stage_k); dev_free(s->spill_k); dev_free(s->fin_k);
     dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
@@ -197,6 +198,7 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     for (auto &e : s->ev) CU(cudaEventCreate(&e));
     CU(cudaMallocHost((void **)&s->h_counters, C_COUNT * sizeof(unsigned long long)));
     CHECK(dev_alloc(&s->d_counters, C_COUNT));
+    CHECK(dev_alloc(&s->d_open_rows, 5 * OPEN_CAP));
 
     // layout: record r at dev_off[r], followed by a gap of max_motif_cap masked positions
     s->h_rec_dev_off.resize(n_records);
@@ -594,6 +596,7 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         tp.map_rec = s->d_map_rec; tp.map_shift = s->d_map_shift; tp.map_open = s->d_map_open;
         tp.n_records = s->n_records; tp.fin_cap = s->res_cap; tp.counters = s->d_counters;
         tp.o_rec = s->o_rec; tp.o_start = s->o_start; tp.o_end = s->o_end; tp.o_k = s->o_k;
+        tp.open_rows = s->d_open_rows;
         translate_kernel<<<tgrid, 256, 0, st>>>(tp);
         CU(cudaGetLastError());
         launches += 5;
@@ -668,6 +671,36 @@ extern "C" int crf_fetch(crf_seq *s, uint32_t *record, uint32_t *start, uint32_t
 extern "C" int crf_scan_stats(const crf_seq *s, crf_scan_stats_t *stats) {
     if (!s || !stats) { set_err("crf_scan_stats: null argument"); return CRF_ERR_ARG; }
     *stats = s->stats;
+    return CRF_OK;
+}
+
+extern "C" int crf_fetch_open(crf_seq *s, uint32_t *rows, uint32_t cap, uint32_t *n_open) {
+    if (!s || !n_open) { set_err("crf_fetch_open: null argument"); return CRF_ERR_ARG; }
+    if (!s->have_results) { set_err("crf_fetch_open: no scan results"); return CRF_ERR_ARG; }
+    *n_open = (uint32_t)std::min<uint64_t>(s->stats.n_open, 0xFFFFFFFFull);
+    const uint32_t n = std::min<uint32_t>(std::min<uint32_t>(*n_open, cap), OPEN_CAP);
+    if (*n_open > OPEN_CAP) {
+        set_err("crf_fetch_open: %u open-ended results, at most %u are kept per scan (use a longer halo)", *n_open, OPEN_CAP);
+        return CRF_ERR_UNSUPPORTED;
+    }
+    if (!n) return CRF_OK;
+    if (!rows) { set_err("crf_fetch_open: null rows"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(s->ctx->device));
+    std::vector<uint32_t> tmp(5 * (size_t)n);
+    CU(cudaMemcpyAsync(tmp.data(), s->d_open_rows, tmp.size() * 4, cudaMemcpyDeviceToHost, s->ctx->stream));
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return tmp[5 * a] < tmp[5 * b]; });  // result order
+    for (uint32_t i = 0; i < n; ++i) memcpy(rows + 5 * i, &tmp[5 * order[i]], 20);
+    return CRF_OK;
+}
+
+extern "C" int crf_patch_end(crf_seq *s, uint64_t row, uint32_t new_end) {
+    if (!s || !s->have_results || row >= s->n_results) { set_err("crf_patch_end: no such result row"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(s->ctx->device));
+    CU(cudaMemcpyAsync(s->o_end + row, &new_end, 4, cudaMemcpyHostToDevice, s->ctx->stream));
+    CU(cudaStreamSynchronize(s->ctx->stream));
     return CRF_OK;
 }
 

@@ -226,13 +226,15 @@ struct TranslateParams {
     uint32_t n_records, fin_cap;
     unsigned long long *counters;
     uint32_t *o_rec, *o_start, *o_end, *o_k;
+    uint32_t *open_rows;                   // OPEN_CAP x 5: row, record, start, end, k of open-ended results
 };
+
+constexpr uint32_t OPEN_CAP = 256;
 
 __global__ void __launch_bounds__(256) translate_kernel(const TranslateParams t) {
     const unsigned long long n = t.counters[C_TOTAL];
     if (n > t.fin_cap) return;
     const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t n_open = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t key = t.fin_key[i];
         const uint32_t st = (uint32_t)(key >> 32), en = (uint32_t)key;
@@ -243,13 +245,19 @@ __global__ void __launch_bounds__(256) translate_kernel(const TranslateParams t)
         }
         const uint32_t d0 = t.rec_dev_off[lo];
         const uint32_t shift = t.map_shift ? t.map_shift[lo] : 0u;
-        if (t.map_open && t.map_open[lo] && en - d0 == t.rec_len[lo]) ++n_open;
-        t.o_rec[i] = t.map_rec ? t.map_rec[lo] : lo;
+        const uint32_t orec = t.map_rec ? t.map_rec[lo] : lo;
+        t.o_rec[i] = orec;
         t.o_start[i] = st - d0 + shift;
         t.o_end[i] = en - d0 + shift;
         t.o_k[i] = t.fin_k[i];
+        if (t.map_open && t.map_open[lo] && en - d0 == t.rec_len[lo]) {  // reached the end of an open-ended record
+            const unsigned long long slot = atomicAdd(t.counters + C_OPEN, 1ull);
+            if (slot < OPEN_CAP) {
+                uint32_t *row = t.open_rows + 5 * slot;
+                row[0] = i; row[1] = orec; row[2] = st - d0 + shift; row[3] = en - d0 + shift; row[4] = t.fin_k[i];
+            }
+        }
     }
-    if (n_open) atomicAdd(t.counters + C_OPEN, (unsigned long long)n_open);
 }
 
 // ---- fallback ordering: global bitonic network on (key, k); n_pow2 elements, tail padded with

@@ -131,6 +131,13 @@ typedef struct {
 } crf_scan_stats_t;
 int crf_scan_stats(const crf_seq *seq, crf_scan_stats_t *stats);
 
+/* Results of the last scan that reached the end of an open-ended record (see crf_seq_set_output_map): up to
+ * `cap` rows of 5 values (row index in the result list, record, start, end, motif_size) in result order;
+ * *n_open = how many there are in total.  crf_patch_end overwrites the end of one result row in HBM (after
+ * the run has been followed with crf_run_end on whoever holds the next bases). */
+int crf_fetch_open(crf_seq *seq, uint32_t *rows, uint32_t cap, uint32_t *n_open);
+int crf_patch_end(crf_seq *seq, uint64_t row, uint32_t new_end);
+
 /* End of the maximal run of period k through position `pos` of `record` (pos must satisfy
  * M_k[pos] == 1, else *run_end = pos).  *run_end = first position >= pos that does not match.
  * Used to stitch runs that leave a partition (chunk/GPU) -- see DESIGN.md "multi-GPU". */

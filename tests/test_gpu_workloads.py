@@ -82,6 +82,32 @@ def test_partitioned_scan_with_stitching_on_gpu(mods):
     assert np.array_equal(whole[0], o_s) and np.array_equal(whole[1], o_e) and np.array_equal(whole[2], o_m)
 
 
+def test_output_map_open_rows_and_patch(mods):
+    """The library-side variant of the same bookkeeping: chromosome coordinates via crf_seq_set_output_map,
+    open-ended results via crf_fetch_open, ends fixed with crf_run_end + crf_patch_end."""
+    chunk, halo = 65536, 4096
+    bases, offsets, meta = mods.synth.sx(3_000_000, chunk, device=None)
+    ctx = mods.api.get_context()
+    whole = mods.api.scan_arrays(bases, 1, 50, 3, 9)
+    plan = mods.partition.Plan([bases.size], 1, chunk, halo, 50, 3, 9)
+    starts, lens, own_lo, own_hi = plan.load_args(0, [0])
+    units = plan.units
+    with ctx.load_ranges(bases, starts, lens, own_lo, own_hi, max_motif_cap=50) as seq:
+        seq.set_output_map(out_record=[u.record for u in units], out_shift=[u.d0 for u in units],
+                           open_ended=[int(u.d1 < u.rec_len) for u in units])
+        n = seq.scan(1, 50, 3, 9)
+        assert n == len(whole[0])
+        open_rows = seq.fetch_open()
+        assert len(open_rows) == seq.stats().n_open and len(open_rows) >= 3
+        fixed = mods.partition.stitch(plan, [tuple(int(x) for x in r[1:]) for r in open_rows],
+                                      lambda unit, lp, k: seq.run_end(unit.index, lp, k))
+        for row, (_r, _s, e, _k) in zip(open_rows, fixed):
+            seq.patch_end(int(row[0]), e)
+        rec, st, en, k = seq.fetch(n)
+    assert rec.max() == 0
+    assert np.array_equal(st, whole[0]) and np.array_equal(en, whole[1]) and np.array_equal(k, whole[2])
+
+
 def test_chr22_sized_record_bit_exact(mods):
     """Configs C1 / C2 on the chr22-shaped stand-in (benchmark/chr22.fa.gz is not in the reference checkout)."""
     bases, offsets, meta = mods.synth.s22(device="cuda:0")
