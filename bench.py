@@ -365,15 +365,24 @@ def main():
     t_hbm = alg_bytes / (hbm_peak * 1e9)
     t_int = alg_ops / (alu_peak_tops * 1e12)
     bound_int = t_int >= t_hbm
+    traffic = None                 # DRAM bytes of one launch from the committed `ncu --set full` capture (same workload)
+    try:
+        with open(os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")) as f:
+            tj = json.load(f)
+        if world == 1 and args.workload == "s38" and args.scale == 1.0:
+            traffic = tj["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "bound": "int32-alu" if bound_int else "hbm",
         "achieved": int_ach if bound_int else hbm_ach,
         "peak": alu_peak_tops if bound_int else hbm_peak,
         "unit": "Tops/s" if bound_int else "GB/s",
         "frac": (int_ach / alu_peak_tops) if bound_int else (hbm_ach / hbm_peak),
-        "traffic": None,
+        "traffic": traffic,
         "kernel": "crf::scan_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         "algorithmic_ops_per_launch": alg_ops, "algorithmic_bytes_per_launch": alg_bytes,
+        "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/r01_scan_kernel_ncu.txt)",
         "peak_source": "INT32 ALU pipe (LOP3+SHF) measured live by crf_tools_alu_peak" if bound_int else hbm_src,
         "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": hbm_src},
         "stated_roofline_ms": max(t_hbm, t_int) * 1e3,
