@@ -64,7 +64,7 @@ struct crf_seq {
     // scan scratch
     KEntry *d_ktab = nullptr;
     Seg *d_segs = nullptr;
-    uint32_t ktab_cap = 0, segs_cap = 0, n_segs = 0;
+    uint32_t ktab_cap = 0, segs_cap = 0, n_segs = 0, sup_enabled = 0;
     crf_scan_params ktab_for = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t *stage_key = nullptr, *spill_key = nullptr, *fin_key = nullptr;
     uint16_t *stage_k = nullptr, *spill_k = nullptr, *fin_k = nullptr;
@@ -227,7 +227,7 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     if (src_lo > src_hi) src_lo = src_hi = 0;
     s->layout_len = (uint32_t)pos;
     s->n_words = (s->layout_len + 31) / 32;
-    s->n_words_alloc = (s->n_words + TILE_WORDS_MAX - 1) / TILE_WORDS_MAX * TILE_WORDS_MAX + (max_motif_cap >> 5) + 8;
+    s->n_words_alloc = (s->n_words + TILE_WORDS_MAX - 1) / TILE_WORDS_MAX * TILE_WORDS_MAX + (max_motif_cap >> 5) + 16;
 
     CU(cudaEventRecord(s->ev[0], st));
     const uint8_t *d_src = bases;   // device view; record r starts at d_src[starts[r] - src_base]
@@ -404,7 +404,7 @@ extern "C" int crf_seq_info(const crf_seq *s, crf_seq_info_t *info) {
 }
 
 // ---- scan ---------------------------------------------------------------------------------------
-static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab, std::vector<Seg> &segs) {
+static void build_ktab(const crf_scan_params &pr, bool allow_sup, std::vector<KEntry> &tab, std::vector<Seg> &segs) {
     tab.assign((size_t)pr.max_motif_size + 1, KEntry{});
     for (uint32_t k = 1; k <= pr.max_motif_size; ++k) {
         KEntry &e = tab[k];
@@ -447,19 +447,24 @@ static void build_ktab(const crf_scan_params &pr, std::vector<KEntry> &tab, std:
         if (pr.flags & CRF_SCAN_NO_PRIMITIVITY)
             for (int j = 0; j < 6; ++j) e.div[j] = 0;
     }
-    // segments: maximal k ranges with the same k >> 5 and the same fast-phase filter
+    // segments: maximal k ranges with the same k >> 5, the same fast-phase filter and the same homopolymer
+    // suppression level (2 <= k <= 8: stretches of > 8 equal bases; 9 <= k <= 16: > 16; none for the H-plane
+    // filters, for k = 1 itself, and when the load has exotic symbols, whose filler codes may collide)
     segs.clear();
     for (uint32_t k = pr.min_motif_size; k <= pr.max_motif_size; ++k) {
         const KEntry &e = tab[k];
+        uint8_t sup = 0;
+        if (allow_sup && (e.mode == MODE_ERODE || e.mode == MODE_BYTE) && k >= 2 && k <= 16) sup = k <= 8 ? 1 : 2;
+        const uint8_t mode = (uint8_t)(e.mode | (sup << 4));
         if (!segs.empty()) {
             Seg &g = segs.back();
-            if ((uint32_t)(g.k_hi >> 5) == (k >> 5) && g.mode == e.mode && g.sh0 == e.sh[0] && g.sh1 == e.sh[1] &&
+            if ((uint32_t)(g.k_hi >> 5) == (k >> 5) && g.mode == mode && g.sh0 == e.sh[0] && g.sh1 == e.sh[1] &&
                 g.sh2 == e.sh[2]) {
                 g.k_hi = (uint16_t)k;
                 continue;
             }
         }
-        segs.push_back(Seg{(uint16_t)k, (uint16_t)k, e.mode, e.sh[0], e.sh[1], e.sh[2]});
+        segs.push_back(Seg{(uint16_t)k, (uint16_t)k, mode, e.sh[0], e.sh[1], e.sh[2]});
     }
 }
 
@@ -521,7 +526,9 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         s->ktab_for.min_motif_size != pr->min_motif_size) {
         std::vector<KEntry> tab;
         std::vector<Seg> segs;
-        build_ktab(*pr, tab, segs);
+        build_ktab(*pr, s->n_exotic == 0 && !(pr->flags & CRF_SCAN_DEBUG_NO_SUP), tab, segs);
+        s->sup_enabled = 0;
+        for (const Seg &g : segs) s->sup_enabled |= (g.mode >> 4) ? 1u : 0u;
         if (s->segs_cap < segs.size()) {
             dev_free(s->d_segs);
             s->segs_cap = 0;
@@ -564,6 +571,7 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         sp.outcap = outcap;
         sp.walk_limit = pr->walk_limit_words ? pr->walk_limit_words : 64;
         sp.debug_flags = (pr->flags >> 16) & 0xFFFFu;
+        sp.sup_enabled = s->sup_enabled;
         sp.stage_key = s->stage_key; sp.stage_k = s->stage_k; sp.stage_cap = s->res_cap;
         sp.tile_cnt = s->tile_cnt; sp.tile_base = s->tile_base;
         sp.spill_key = s->spill_key; sp.spill_k = s->spill_k; sp.spill_cap = s->res_cap;

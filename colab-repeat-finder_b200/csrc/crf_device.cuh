@@ -47,7 +47,7 @@ static_assert(sizeof(KEntry) == 32, "KEntry layout");
 // A maximal range of motif sizes that share (k >> 5) and the fast-phase filter.
 struct Seg {
     uint16_t k_lo, k_hi;
-    uint8_t mode, sh0, sh1, sh2;
+    uint8_t mode, sh0, sh1, sh2;  // mode: FilterMode | (suppression level << 4)
 };
 static_assert(sizeof(Seg) == 8, "Seg layout");
 
@@ -65,6 +65,7 @@ struct ScanParams {
     uint32_t kmin, kmax;
     uint32_t outcap;         // per-tile sorted-output slots
     uint32_t walk_limit;     // words one thread walks before the block takes over
+    uint32_t sup_enabled;    // some segment carries a homopolymer-suppression level
     uint32_t debug_flags;    // bit 0: skip the exact phase (profiling only, results are then empty)
     uint64_t *stage_key;     // (start << 32 | end), tile-sorted segments
     uint16_t *stage_k;

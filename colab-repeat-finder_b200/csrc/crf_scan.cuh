@@ -227,27 +227,36 @@ __device__ __forceinline__ bool filter_half(const uint32_t (&NH)[T + 1], const u
     }
     return (acc & 0x80008000u) != 0;
 }
-template <int T>
+// SUP: positions that start a stretch of > k equal bases (HD = dilated mismatch word of M'_1, ~HD = such
+// positions) are treated as mismatches.  A primitive motif of size k cannot contain k+1 equal consecutive
+// bases, so no run that will be reported loses a position; runs of k that only exist because of a
+// homopolymer (they are dropped by the primitivity rule anyway) stop producing candidates.
+template <int T, bool SUP>
 __device__ __forceinline__ bool filter_byte(const uint32_t (&NH)[T + 1], const uint32_t (&NL)[T + 1],
-                                            const uint32_t (&FH)[T + 2], const uint32_t (&FL)[T + 2], uint32_t s) {
+                                            const uint32_t (&FH)[T + 2], const uint32_t (&FL)[T + 2], uint32_t s,
+                                            const uint32_t (&HD)[T + 2]) {
     uint32_t acc = 0;
 #pragma unroll
     for (int i = 0; i <= T; ++i) {
-        const uint32_t x = (NH[i] ^ __funnelshift_r(FH[i], FH[i + 1], s)) |
-                           (NL[i] ^ __funnelshift_r(FL[i], FL[i + 1], s));
+        uint32_t x = NH[i] ^ __funnelshift_r(FH[i], FH[i + 1], s);
+        if (SUP) x |= ~HD[i];
+        x |= NL[i] ^ __funnelshift_r(FL[i], FL[i + 1], s);
         acc |= (x - 0x01010101u) & ~x;
     }
     return (acc & 0x80808080u) != 0;
 }
 // NSH = number of dilation steps (compile time), shifts at run time
-template <int T, int NSH>
+template <int T, int NSH, bool SUP>
 __device__ __forceinline__ bool filter_erode(const uint32_t (&NH)[T + 1], const uint32_t (&NL)[T + 1],
                                              const uint32_t (&FH)[T + 2], const uint32_t (&FL)[T + 2], uint32_t s,
-                                             uint32_t sh0, uint32_t sh1, uint32_t sh2) {
+                                             uint32_t sh0, uint32_t sh1, uint32_t sh2, const uint32_t (&HD)[T + 2]) {
     uint32_t x[T + 1];  // mismatch words; dilating mismatches == eroding matches
 #pragma unroll
-    for (int i = 0; i <= T; ++i)
-        x[i] = (NH[i] ^ __funnelshift_r(FH[i], FH[i + 1], s)) | (NL[i] ^ __funnelshift_r(FL[i], FL[i + 1], s));
+    for (int i = 0; i <= T; ++i) {
+        uint32_t v = NH[i] ^ __funnelshift_r(FH[i], FH[i + 1], s);
+        if (SUP) v |= ~HD[i];
+        x[i] = v | (NL[i] ^ __funnelshift_r(FL[i], FL[i + 1], s));
+    }
     if (NSH >= 1) {
 #pragma unroll
         for (int i = 0; i < T; ++i) x[i] |= __funnelshift_r(x[i], x[i + 1], sh0);
@@ -270,7 +279,7 @@ __device__ __forceinline__ bool filter_erode(const uint32_t (&NH)[T + 1], const 
 
 // dynamic shared memory a scan block needs
 __host__ __device__ inline uint32_t scan_tile_words(int T, uint32_t kmax) {
-    return (uint32_t)THREADS * T + (kmax >> 5) + 4;  // 1 word of left context + tile + halo (q+3)
+    return (uint32_t)THREADS * T + (kmax >> 5) + 5;  // 1 word of left context + tile + halo (q+4)
 }
 __host__ __device__ inline size_t scan_smem_bytes(int T, uint32_t kmax, uint32_t outcap) {
     const size_t plane = pad_idx(scan_tile_words(T, kmax)) + 1;
@@ -343,38 +352,91 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
                 FH[i] = sH[pad_idx(1 + tid * T + qb + i)];
                 FL[i] = sL[pad_idx(1 + tid * T + qb + i)];
             }
+            // homopolymer mask for this strip (only k <= 16, i.e. the first group): HD bit j = some mismatch of
+            // M'_1 in [j, j+8): ~HD = nine equal bases from j on; the word after the window is filled with mismatches
+            uint32_t HD[T + 2];
+            uint32_t hd_level = 0;
+            if (qb == 0 && p.sup_enabled) {
+                const uint32_t hx = sH[pad_idx(1 + tid * T + T + 2)], lx = sL[pad_idx(1 + tid * T + T + 2)];
+#pragma unroll
+                for (int i = 0; i <= T; ++i)
+                    HD[i] = (FH[i] ^ __funnelshift_r(FH[i], FH[i + 1], 1)) | (FL[i] ^ __funnelshift_r(FL[i], FL[i + 1], 1));
+                HD[T + 1] = (FH[T + 1] ^ __funnelshift_r(FH[T + 1], hx, 1)) | (FL[T + 1] ^ __funnelshift_r(FL[T + 1], lx, 1));
+#pragma unroll
+                for (int sh = 1; sh <= 4; sh <<= 1) {
+#pragma unroll
+                    for (int i = 0; i <= T; ++i) HD[i] |= __funnelshift_r(HD[i], HD[i + 1], sh);
+                    HD[T + 1] |= __funnelshift_r(HD[T + 1], 0xFFFFFFFFu, sh);
+                }
+                hd_level = 1;
+            } else {
+#pragma unroll
+                for (int i = 0; i <= T + 1; ++i) HD[i] = 0xFFFFFFFFu;
+            }
             uint32_t hitmask = 0;
             for (; si < p.n_segs; ++si) {
                 const Seg sg = p.segs[si];
                 if (((uint32_t)sg.k_lo >> 5) != qb) break;
                 const uint32_t s_lo = sg.k_lo & 31, s_hi = sg.k_hi & 31;
                 const uint32_t sh0 = sg.sh0, sh1 = sg.sh1, sh2 = sg.sh2;
-                if (sg.mode == MODE_WORD) {
+                if ((sg.mode & 15u) == MODE_WORD) {
 #pragma unroll 1
                     for (uint32_t s = s_lo; s <= s_hi; ++s) hitmask |= (filter_word<T>(NH, FH, s) ? 1u : 0u) << s;
-                } else if (sg.mode == MODE_HALF) {
+                } else if ((sg.mode & 15u) == MODE_HALF) {
 #pragma unroll 1
                     for (uint32_t s = s_lo; s <= s_hi; ++s) hitmask |= (filter_half<T>(NH, FH, s) ? 1u : 0u) << s;
-                } else if (sg.mode == MODE_BYTE) {
-#pragma unroll 1
-                    for (uint32_t s = s_lo; s <= s_hi; ++s)
-                        hitmask |= (filter_byte<T>(NH, NL, FH, FL, s) ? 1u : 0u) << s;
-                } else if (sh2) {
-#pragma unroll 1
-                    for (uint32_t s = s_lo; s <= s_hi; ++s)
-                        hitmask |= (filter_erode<T, 3>(NH, NL, FH, FL, s, sh0, sh1, sh2) ? 1u : 0u) << s;
-                } else if (sh1) {
-#pragma unroll 1
-                    for (uint32_t s = s_lo; s <= s_hi; ++s)
-                        hitmask |= (filter_erode<T, 2>(NH, NL, FH, FL, s, sh0, sh1, 0) ? 1u : 0u) << s;
-                } else if (sh0) {
-#pragma unroll 1
-                    for (uint32_t s = s_lo; s <= s_hi; ++s)
-                        hitmask |= (filter_erode<T, 1>(NH, NL, FH, FL, s, sh0, 0, 0) ? 1u : 0u) << s;
                 } else {
+                    const uint32_t sup = sg.mode >> 4;  // 0: none, 1: stretches of > 8 equal bases, 2: > 16
+                    if (sup == 2 && hd_level == 1) {    // widen the homopolymer mask from 8 to 16 matches
+#pragma unroll
+                        for (int i = 0; i <= T; ++i) HD[i] |= __funnelshift_r(HD[i], HD[i + 1], 8);
+                        HD[T + 1] |= __funnelshift_r(HD[T + 1], 0xFFFFFFFFu, 8);
+                        hd_level = 2;
+                    }
+                    const uint32_t mode = sg.mode & 15u;
+                    if (sup) {
+                        if (mode == MODE_BYTE) {
 #pragma unroll 1
-                    for (uint32_t s = s_lo; s <= s_hi; ++s)
-                        hitmask |= (filter_erode<T, 0>(NH, NL, FH, FL, s, 0, 0, 0) ? 1u : 0u) << s;
+                            for (uint32_t s = s_lo; s <= s_hi; ++s)
+                                hitmask |= (filter_byte<T, true>(NH, NL, FH, FL, s, HD) ? 1u : 0u) << s;
+                        } else if (sh2) {
+#pragma unroll 1
+                            for (uint32_t s = s_lo; s <= s_hi; ++s)
+                                hitmask |= (filter_erode<T, 3, true>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD) ? 1u : 0u) << s;
+                        } else if (sh1) {
+#pragma unroll 1
+                            for (uint32_t s = s_lo; s <= s_hi; ++s)
+                                hitmask |= (filter_erode<T, 2, true>(NH, NL, FH, FL, s, sh0, sh1, 0, HD) ? 1u : 0u) << s;
+                        } else if (sh0) {
+#pragma unroll 1
+                            for (uint32_t s = s_lo; s <= s_hi; ++s)
+                                hitmask |= (filter_erode<T, 1, true>(NH, NL, FH, FL, s, sh0, 0, 0, HD) ? 1u : 0u) << s;
+                        } else {
+#pragma unroll 1
+                            for (uint32_t s = s_lo; s <= s_hi; ++s)
+                                hitmask |= (filter_erode<T, 0, true>(NH, NL, FH, FL, s, 0, 0, 0, HD) ? 1u : 0u) << s;
+                        }
+                    } else if (mode == MODE_BYTE) {
+#pragma unroll 1
+                        for (uint32_t s = s_lo; s <= s_hi; ++s)
+                            hitmask |= (filter_byte<T, false>(NH, NL, FH, FL, s, HD) ? 1u : 0u) << s;
+                    } else if (sh2) {
+#pragma unroll 1
+                        for (uint32_t s = s_lo; s <= s_hi; ++s)
+                            hitmask |= (filter_erode<T, 3, false>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD) ? 1u : 0u) << s;
+                    } else if (sh1) {
+#pragma unroll 1
+                        for (uint32_t s = s_lo; s <= s_hi; ++s)
+                            hitmask |= (filter_erode<T, 2, false>(NH, NL, FH, FL, s, sh0, sh1, 0, HD) ? 1u : 0u) << s;
+                    } else if (sh0) {
+#pragma unroll 1
+                        for (uint32_t s = s_lo; s <= s_hi; ++s)
+                            hitmask |= (filter_erode<T, 1, false>(NH, NL, FH, FL, s, sh0, 0, 0, HD) ? 1u : 0u) << s;
+                    } else {
+#pragma unroll 1
+                        for (uint32_t s = s_lo; s <= s_hi; ++s)
+                            hitmask |= (filter_erode<T, 0, false>(NH, NL, FH, FL, s, 0, 0, 0, HD) ? 1u : 0u) << s;
+                    }
                 }
             }
             s_hit[nb * THREADS + tid] = hitmask;

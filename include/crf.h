@@ -94,6 +94,7 @@ int crf_seq_info(const crf_seq *seq, crf_seq_info_t *info);
 #define CRF_SCAN_NO_PRIMITIVITY 1u
 /* bits 16..31: profiling switches (results are NOT valid when set): 1<<16 = fast phase only */
 #define CRF_SCAN_DEBUG_FAST_ONLY (1u << 16)
+#define CRF_SCAN_DEBUG_NO_SUP (1u << 17)   /* tuning: no homopolymer suppression in the filters (results stay valid) */
 
 typedef struct {
     uint32_t min_motif_size;

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=0.25)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--fast-only", action="store_true")
+ap.add_argument("--no-sup", action="store_true")
 ap.add_argument("--wpt", type=int, default=0)
 ap.add_argument("--kmin", type=int, default=1)
 ap.add_argument("--kmax", type=int, default=50)
@@ -23,7 +24,7 @@ bases, offsets, meta = synth.s38(device="cuda:0", scale=args.scale)
 torch.cuda.synchronize()
 ctx = _cabi.Context(0)
 seq = ctx.load(bases.data_ptr(), offsets, max_motif_cap=args.kmax, on_device=True)
-flags = (1 << 16) if args.fast_only else 0
+flags = ((1 << 16) if args.fast_only else 0) | ((1 << 17) if args.no_sup else 0)
 for i in range(args.reps):
     n = seq.scan(args.kmin, args.kmax, 3, 9, flags=flags, words_per_thread=args.wpt)
     st = seq.stats()
