@@ -103,6 +103,8 @@ def make_workload(name, device, scale):
         return synth.s38(device=device, scale=scale)
     if name == "s22":
         return synth.s22(device=device, scale=scale)
+    if name == "sr":                                  # config C5: 10 M reads x 150 bp, motif 1-20
+        return synth.sr(int(10_000_000 * scale), device=device)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -153,13 +155,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="s38", choices=["s38", "s22"])
+    ap.add_argument("--workload", default="s38", choices=["s38", "s22", "sr"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--words-per-thread", type=int, default=0)
     ap.add_argument("--trace", action="store_true", help="print per-stage host timings of one extra step (stderr)")
     args = ap.parse_args()
+    global KMAX
+    if args.workload == "sr":
+        KMAX = 20
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -187,17 +192,27 @@ def main():
     t0 = time.time()
     bases, offsets, meta = make_workload(args.workload, dev, args.scale)
     torch.cuda.synchronize()
-    lengths = [int(offsets[i + 1] - offsets[i]) for i in range(len(offsets) - 1)]
+    lengths = np.diff(offsets.astype(np.int64)).tolist()
     total_bp = int(offsets[-1])
     log(f"[rank {rank}] generated {meta['workload']} in {time.time() - t0:.1f}s")
 
-    # ---- this rank's share: contiguous (record, chunk) units with halo ----
-    plan = partition.Plan(lengths, world, chunk=args_chunk(world), halo=partition.DEFAULT_HALO,
-                          kmax=KMAX, min_repeats=MIN_REPEATS, min_span=MIN_SPAN)
-    mine = plan.units_of(rank)
-    starts, lens, own_lo, own_hi = plan.load_args(rank, offsets)
-    if world == 1:
-        own_lo = own_hi = None                      # whole records: nothing to own or stitch
+    # ---- this rank's share: contiguous (record, chunk) units with halo; reads are split by count ----
+    if args.workload == "sr":
+        n_rec = len(lengths)
+        lo_r, hi_r = n_rec * rank // world, n_rec * (rank + 1) // world
+        plan, mine = None, []
+        starts = offsets[lo_r:hi_r].astype(np.uint64)
+        lens = np.diff(offsets[lo_r:hi_r + 1]).astype(np.uint64)
+        own_lo = own_hi = None
+        n_units, my_bp = n_rec, int(lens.sum())
+    else:
+        plan = partition.Plan(lengths, world, chunk=args_chunk(world), halo=partition.DEFAULT_HALO,
+                              kmax=KMAX, min_repeats=MIN_REPEATS, min_span=MIN_SPAN)
+        mine = plan.units_of(rank)
+        starts, lens, own_lo, own_hi = plan.load_args(rank, offsets)
+        if world == 1:
+            own_lo = own_hi = None                      # whole records: nothing to own or stitch
+        n_units, my_bp = len(plan.units), int(sum(u.d1 - u.d0 for u in mine))
     knobs = {"words_per_thread": args.words_per_thread} if args.words_per_thread else {}
 
     seq = ctx.load_ranges(bases.data_ptr(), starts, lens, own_lo, own_hi, max_motif_cap=KMAX, on_device=True)
@@ -206,7 +221,7 @@ def main():
     def one_step():
         return seq.scan(KMIN, KMAX, MIN_REPEATS, MIN_SPAN, **knobs)
 
-    if world > 1:   # results come out in chromosome coordinates; open-ended results are counted by the library
+    if world > 1 and plan is not None:   # results come out in chromosome coordinates; open-ended results are counted by the library
         seq.set_output_map(out_record=[u.record for u in mine], out_shift=[u.d0 for u in mine],
                            open_ended=[int(u.d1 < u.rec_len) for u in mine])
     gstate = {"cap": 0, "buf": None, "out": None}
@@ -240,7 +255,7 @@ def main():
         rec, st, en, kk = (buf[i * cap:i * cap + n] for i in range(4))
         seq.fetch_device(rec.data_ptr(), st.data_ptr(), en.data_ptr(), kk.data_ptr(), n)
         mark('fetch_device')
-        if any_open:                                  # a repeat longer than the halo crossed a unit end
+        if any_open and plan is not None:             # a repeat longer than the halo crossed a unit end
             open_rows = seq.fetch_open() if n_open else np.zeros((0, 5), np.uint32)
             open_mine = [tuple(int(x) for x in row[1:]) for row in open_rows]
             fixed = partition.stitch_collective(
@@ -356,7 +371,6 @@ def main():
     tools.crf_tools_alu_peak(local_rank, ctypes.byref(ops), None)
     alu_peak_tops = ops.value / 1e12
     k_ms = float(np.mean(kernel_ms))
-    my_bp = int(sum(u.d1 - u.d0 for u in mine))
     n_k = KMAX - KMIN + 1
     alg_bytes = (my_bp + 3) // 4 + (my_bp + 7) // 8 + 12 * int(stats.n_results)
     alg_ops = 6 * ((my_bp + 31) // 32) * n_k
@@ -394,12 +408,19 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         r = 0 if len(lengths) == 1 else 20          # chr21 of S38 (46.7 Mbp x 50 motif sizes)
-        sample = bases[int(offsets[r]):int(offsets[r + 1])].cpu().numpy()
+        if args.workload == "sr":                   # reads: the first 200 000 reads, concatenated with N gaps
+            nr = min(200_000, len(lengths))
+            block = bases[:nr * 150].reshape(nr, 150)
+            gapped = torch.full((nr, 150 + KMAX), ord("N"), dtype=torch.uint8, device=dev)
+            gapped[:, :150] = block
+            sample = gapped.flatten().cpu().numpy()
+        else:
+            sample = bases[int(offsets[r]):int(offsets[r + 1])].cpu().numpy()
         res = cpu_baseline_run(sample)
         rec, st, en, kk = seq.fetch(int(stats.n_results))
         unit_of_r = [i for i, u in enumerate(mine) if u.record == r]
         parity = None
-        if len(unit_of_r) == 1:                      # record scanned as one unit: compare row by row
+        if len(unit_of_r) == 1 and args.workload != "sr":  # record scanned as one unit: compare row by row
             sel = rec == unit_of_r[0]
             o_s, o_e, o_m = res["rows"]
             parity = bool(np.array_equal(st[sel], o_s) and np.array_equal(en[sel], o_e) and
@@ -418,7 +439,7 @@ def main():
         "config": {"workload": meta["workload"], "motif_sizes": [KMIN, KMAX], "min_repeats": MIN_REPEATS,
                    "min_span": MIN_SPAN, "total_bp": total_bp, "results_per_step": int(total_results),
                    "l2": "inputs larger than L2 (packed planes %.0f MB per GPU)" % (info.packed_bytes / 1e6),
-                   "partition": f"{len(plan.units)} (record, chunk) units over {world} rank(s)"},
+                   "partition": f"{n_units} (record, chunk) units over {world} rank(s)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "scan_stats": {"scan_ms": float(np.mean(scan_ms)), "kernel_ms": k_ms, "candidates": int(stats.n_candidates),

@@ -547,7 +547,7 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
     if (s->tiles_cap < n_tiles + 1) {
         dev_free(s->tile_cnt); dev_free(s->tile_base); dev_free(s->tile_off);
         s->tiles_cap = 0;
-        CHECK(dev_alloc(&s->tile_cnt, (size_t)n_tiles + 1));
+        CHECK(dev_alloc(&s->tile_cnt, (size_t)n_tiles + 8));   // slack: tile_offsets_kernel reads uint4
         CHECK(dev_alloc(&s->tile_base, (size_t)n_tiles + 1));
         CHECK(dev_alloc(&s->tile_off, (size_t)n_tiles + 1));
         s->tiles_cap = n_tiles + 1;

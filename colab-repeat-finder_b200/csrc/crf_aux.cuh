@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
 }
 
 // ---- assembly: tile segments -> one (start, end)-sorted list --------------------------------
-// exclusive prefix sum of tile_cnt (single block; n_tiles is tens of thousands at most)
+// exclusive prefix sum of tile_cnt (single block, four tiles per thread and step; n_tiles is tens of
+// thousands at most, the arrays are allocated with slack for the vector loads)
 __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t *tile_cnt, uint32_t *tile_off,
                                                             uint32_t n_tiles, unsigned long long *counters) {
     __shared__ uint32_t warp_sum[32];
@@ -87,10 +88,16 @@ __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t *tile
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < n_tiles; base += 1024) {
-        const uint32_t i = base + tid;
-        const uint32_t v = (i < n_tiles) ? tile_cnt[i] : 0;
-        uint32_t incl = v;
+    for (uint32_t base = 0; base < n_tiles; base += 4096) {
+        const uint32_t i = base + 4 * tid;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < n_tiles) v = *reinterpret_cast<const uint4 *>(tile_cnt + i);
+        if (i + 1 >= n_tiles) v.y = 0;
+        if (i + 2 >= n_tiles) v.z = 0;
+        if (i + 3 >= n_tiles) v.w = 0;
+        if (i >= n_tiles) v.x = 0;
+        const uint32_t mine = v.x + v.y + v.z + v.w;
+        uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -105,7 +112,11 @@ __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t *tile
             total += t;
         }
         const uint32_t carry = carry_s;
-        if (i < n_tiles) tile_off[i] = carry + woff + incl - v;
+        const uint32_t e0 = carry + woff + incl - mine;
+        if (i < n_tiles) tile_off[i] = e0;
+        if (i + 1 < n_tiles) tile_off[i + 1] = e0 + v.x;
+        if (i + 2 < n_tiles) tile_off[i + 2] = e0 + v.x + v.y;
+        if (i + 3 < n_tiles) tile_off[i + 3] = e0 + v.x + v.y + v.z;
         __syncthreads();
         if (tid == 0) carry_s = carry + total;
         __syncthreads();

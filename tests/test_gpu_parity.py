@@ -141,3 +141,19 @@ def test_megabase_default_settings(prf, oracle):
     assert len(want) > 1000
     for knobs in ({}, {"words_per_thread": 16}):
         assert prf.detect_repeats(seq, fs, **knobs) == want
+
+
+def test_large_motif_range_like_the_hail_pipeline(prf, oracle):
+    """run_hail_batch_pipeline.py:33 defaults to motif sizes up to 1000: k >> 5 up to 31, halo of 1000 bases."""
+    rng = random.Random(77)
+    parts = []
+    for _ in range(60):
+        parts.append("".join(rng.choice("ACGT") for _ in range(rng.randint(50, 4000))))
+        unit = "".join(rng.choice("ACGT") for _ in range(rng.choice([1, 3, 33, 64, 97, 255, 256, 500, 999, 1000])))
+        parts.append(unit * rng.randint(3, 6) + unit[:rng.randint(0, len(unit) - 1)] if len(unit) > 1 else unit * 40)
+    seq = "".join(parts)
+    fs = ns(min_motif_size=1, max_motif_size=1000, min_repeats=3, min_span=9)
+    want = oracle.detect_repeats_by_k(seq, fs)
+    assert any(len(m) >= 500 for _, _, m in want)
+    for knobs in ({}, {"words_per_thread": 1}):
+        assert prf.detect_repeats(seq, fs, **knobs) == want
