@@ -19,7 +19,7 @@ CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_C
 EXPORTS = [
     "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
     "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
-    "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end",
+    "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end", "crf_write_rows",
 ]
 
 
@@ -80,6 +80,7 @@ def lib():
         L.crf_run_end.argtypes = [vp, u32, u32, u32, P(u32)]
         L.crf_fetch_open.argtypes = [vp, vp, u32, P(u32)]
         L.crf_patch_end.argtypes = [vp, u64, u32]
+        L.crf_write_rows.argtypes = [ctypes.c_char_p, i, i, vp, vp, vp, vp, vp, vp, vp, u64, P(u64)]
         for name in EXPORTS:
             if name != "crf_last_error":
                 getattr(L, name).restype = i
@@ -215,6 +216,10 @@ class Sequence:
     def fetch_device(self, rec_ptr, start_ptr, end_ptr, k_ptr, capacity):
         _check(lib().crf_fetch(self._h, rec_ptr, start_ptr, end_ptr, k_ptr, capacity, 1))
 
+    def fetch_host(self, rec_ptr, start_ptr, end_ptr, k_ptr, capacity):
+        """Fetch into caller-owned host buffers given by address (e.g. pinned memory)."""
+        _check(lib().crf_fetch(self._h, rec_ptr, start_ptr, end_ptr, k_ptr, capacity, 0))
+
     def stats(self):
         out = ScanStats()
         _check(lib().crf_scan_stats(self._h, ctypes.byref(out)))
@@ -251,3 +256,20 @@ class Sequence:
             self.close()
         except Exception:
             pass
+
+
+def write_rows(path, names, bases, offsets, record, start, end, k, tsv=False, append=False):
+    """Native BED / TSV writer (crf_write_rows).  bases: bytes or uint8 array with all records back to back."""
+    blob = b"".join(n.encode("utf-8") + b"\0" for n in names) if names is not None else None
+    arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (record, start, end, k)]
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    if isinstance(bases, np.ndarray):
+        bptr = bases.ctypes.data
+    else:
+        bptr = ctypes.cast(ctypes.c_char_p(bases), ctypes.c_void_p).value or 0
+    nbytes = ctypes.c_uint64()
+    _check(lib().crf_write_rows(os.fsencode(path), int(append), int(tsv),
+                                ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p) if blob is not None else None,
+                                ctypes.c_void_p(bptr), ctypes.c_void_p(offsets.ctypes.data),
+                                *(ctypes.c_void_p(a.ctypes.data) for a in arrs), len(arrs[0]), ctypes.byref(nbytes)))
+    return nbytes.value

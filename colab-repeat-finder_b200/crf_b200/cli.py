@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-from . import api, fasta
+from . import _cabi, api, fasta
 
 
 def build_parser():
@@ -33,21 +33,22 @@ def build_parser():
     return parser
 
 
-def _scan_records(records, args):
-    """All records in one load / one scan -> per-record lists of (start, end, motif)."""
+def _scan_records_to_bed(records, args, bed_path):
+    """All records in one load / one scan; rows written by the native writer.  Returns rows per record."""
     ctx = api.get_context()
     lengths = np.array([len(r.seq) for r in records], dtype=np.uint64)
     offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
     blob = b"".join(r.seq for r in records)
-    out = [[] for _ in records]
+    counts = np.zeros(len(records), dtype=np.int64)
     if not len(blob):
-        return out
+        open(bed_path, "wb").close()
+        return counts
     with ctx.load(blob, offsets, max_motif_cap=args.max_motif_size) as seq:
         n = seq.scan(args.min_motif_size, args.max_motif_size, args.min_repeats, args.min_span)
         rec, start, end, k = seq.fetch(n)
-    for r, s, e, kk in zip(rec.tolist(), start.tolist(), end.tolist(), k.tolist()):
-        out[r].append((s, e, records[r].seq[s:s + kk].decode("latin-1").upper()))
-    return out
+    _cabi.write_rows(bed_path, [r.name for r in records], blob, offsets, rec, start, end, k)
+    np.add.at(counts, rec.astype(np.int64), 1)
+    return counts
 
 
 def main(argv=None):
@@ -82,23 +83,22 @@ def main(argv=None):
                 parser.error(f"Chromosome {args.interval_chrom} not found in the input FASTA file")
             fasta_entries = [matches[0]]
 
-        with open(output_bed_path, "wt") as bed_file:
-            if args.interval:
+        if args.interval:
+            with open(output_bed_path, "wt") as bed_file:
                 entry = fasta_entries[0]
                 seq_len = len(entry.seq)
                 if args.interval_end > seq_len:
                     args.interval_end = seq_len
                 seq_len = args.interval_end - args.interval_start_0based
                 print(f"Processing {entry.name} ({seq_len:,d} bp)")
-                per_record = [api.detect_repeats(entry.seq, args)]
-            else:
-                per_record = _scan_records(fasta_entries, args)
-            for entry, output_intervals in zip(fasta_entries, per_record):
-                if not args.interval:
-                    print(f"Processing {entry.name} ({len(entry.seq):,d} bp)")
+                output_intervals = api.detect_repeats(entry.seq, args)
                 print(f"Found {len(output_intervals):,d} repeats")
-                chrom = entry.name
-                bed_file.write("".join(f"{chrom}\t{s}\t{e}\t{m}\n" for s, e, m in output_intervals))
+                bed_file.write("".join(f"{entry.name}\t{s}\t{e}\t{m}\n" for s, e, m in output_intervals))
+        else:
+            counts = _scan_records_to_bed(fasta_entries, args, output_bed_path)
+            for entry, n_found in zip(fasta_entries, counts.tolist()):
+                print(f"Processing {entry.name} ({len(entry.seq):,d} bp)")
+                print(f"Found {n_found:,d} repeats")
 
         print(f"Wrote results to {output_bed_path}")
 

@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <unordered_map>
+#include <utility>
 #include <new>
 #include <vector>
 
@@ -42,11 +44,65 @@ static void set_err(const char *fmt, ...) {
         if (rc_) return rc_;   \
     } while (0)
 
+// Device buffers freed by a sequence are kept by its context and handed out again to later loads / scans of
+// similar size: cudaMalloc / cudaFree of multi-GB buffers cost tens of milliseconds and made the end-to-end
+// path (load -> scan -> fetch -> destroy, every step) erratic.
 struct crf_ctx {
     int device;
     cudaStream_t own_stream;
     cudaStream_t stream;
+    std::vector<std::pair<void *, size_t>> cache;       // free blocks
+    std::unordered_map<void *, size_t> live;            // blocks handed out -> size
+    size_t cached_bytes = 0;
 };
+static const size_t CACHE_LIMIT_BYTES = 24ull << 30;
+static thread_local crf_ctx *g_ctx = nullptr;          // context of the API call in progress
+
+static cudaError_t ctx_malloc(void **p, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    crf_ctx *c = g_ctx;
+    if (c) {
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < c->cache.size(); ++i) {
+            const size_t sz = c->cache[i].second;
+            if (sz >= bytes && sz <= bytes + bytes / 4 + (1u << 20) && (best == (size_t)-1 || sz < c->cache[best].second)) best = i;
+        }
+        if (best != (size_t)-1) {
+            *p = c->cache[best].first;
+            c->live[*p] = c->cache[best].second;
+            c->cached_bytes -= c->cache[best].second;
+            c->cache.erase(c->cache.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && c && !c->cache.empty()) {   // out of memory: give the cached blocks back and retry
+        cudaGetLastError();
+        for (auto &b : c->cache) cudaFree(b.first);
+        c->cache.clear();
+        c->cached_bytes = 0;
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess && c) c->live[*p] = bytes;
+    return e;
+}
+static void ctx_free(void *p) {
+    if (!p) return;
+    crf_ctx *c = g_ctx;
+    if (c) {
+        auto it = c->live.find(p);
+        if (it != c->live.end()) {
+            const size_t sz = it->second;
+            c->live.erase(it);
+            if (c->cached_bytes + sz <= CACHE_LIMIT_BYTES && c->cache.size() < 256) {
+                c->cache.emplace_back(p, sz);
+                c->cached_bytes += sz;
+                return;
+            }
+        }
+    }
+    cudaFree(p);
+}
 
 struct crf_seq {
     crf_ctx *ctx = nullptr;
@@ -83,12 +139,12 @@ struct crf_seq {
 template <typename T>
 static int dev_alloc(T **p, size_t n) {
     *p = nullptr;
-    CU(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    CU(ctx_malloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
     return CRF_OK;
 }
 template <typename T>
 static void dev_free(T *&p) {
-    if (p) cudaFree(p);
+    if (p) ctx_free(p);
     p = nullptr;
 }
 
@@ -123,6 +179,8 @@ extern "C" int crf_ctx_destroy(crf_ctx *c) {
     if (!c) return CRF_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (auto &b : c->cache) cudaFree(b.first);
+    if (g_ctx == c) g_ctx = nullptr;
     cudaStreamDestroy(c->own_stream);
     delete c;
     return CRF_OK;
@@ -169,7 +227,7 @@ static int bitonic_sort(cudaStream_t st, uint64_t *key, uint16_t *val, uint32_t 
 // ---- sequence upload ------------------------------------------------------------------------
 static void free_seq(crf_seq *s) {
     if (!s) return;
-    if (s->ctx) cudaSetDevice(s->ctx->device);
+    if (s->ctx) { cudaSetDevice(s->ctx->device); g_ctx = s->ctx; }
     dev_free(s->H); dev_free(s->L); dev_free(s->NM); dev_free(s->X);
     dev_free(s->d_rec_dev_off); dev_free(s->d_own_lo); dev_free(s->d_own_hi); dev_free(s->d_rec_len);
     dev_free(s->d_map_rec); dev_free(s->d_map_shift); dev_free(s->d_map_open); dev_free(s->d_open_rows); dev_free(s->ex_key); dev_free(s->d_ktab); dev_free(s->d_segs);
@@ -249,7 +307,7 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
         for (uint32_t r = 0; r < n_records; ++r) {
             if (own_lo[r] > own_hi[r] || own_hi[r] > lengths[r]) {
                 set_err("crf_seq_load_ascii_ranges: own range of record %u is not inside the record", r);
-                if (d_src_own) cudaFree(d_src_own);
+                if (d_src_own) ctx_free(d_src_own);
                 return CRF_ERR_ARG;
             }
             olo[r] = s->h_rec_dev_off[r] + (uint32_t)own_lo[r];
@@ -288,8 +346,8 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // also keeps rel/len32/olo alive long enough
     }
-    if (d_src_own) cudaFree(d_src_own);
-    if (d_src_start) cudaFree(d_src_start);
+    if (d_src_own) ctx_free(d_src_own);
+    if (d_src_start) ctx_free(d_src_start);
     if (rc) return rc;
     if (e != cudaSuccess) { set_err("crf_seq_load_ascii: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
 
@@ -331,6 +389,7 @@ extern "C" int crf_seq_load_ascii_ranges(crf_ctx *c, const uint8_t *bases, const
             if (lengths[r]) { set_err("crf_seq_load_ascii: null bases"); return CRF_ERR_ARG; }
     }
     CU(cudaSetDevice(c->device));
+    g_ctx = c;
     crf_seq *s = new (std::nothrow) crf_seq;
     if (!s) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
     int rc;
@@ -363,6 +422,7 @@ extern "C" int crf_seq_load_ascii(crf_ctx *c, const uint8_t *bases, const uint64
 
 extern "C" int crf_seq_destroy(crf_seq *s) {
     if (!s) return CRF_OK;
+    g_ctx = s->ctx;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     free_seq(s);
@@ -372,6 +432,7 @@ extern "C" int crf_seq_destroy(crf_seq *s) {
 extern "C" int crf_seq_set_output_map(crf_seq *s, const uint32_t *out_record, const uint64_t *out_shift,
                                       const uint8_t *open_ended) {
     if (!s) { set_err("crf_seq_set_output_map: null sequence"); return CRF_ERR_ARG; }
+    g_ctx = s->ctx;
     CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
     CU(cudaStreamSynchronize(st));
@@ -511,6 +572,7 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
     crf_ctx *c = s->ctx;
     cudaStream_t st = c->stream;
     CU(cudaSetDevice(c->device));
+    g_ctx = c;
     s->have_results = false;
 
     // per-k table
@@ -728,5 +790,67 @@ extern "C" int crf_run_end(crf_seq *s, uint32_t record, uint32_t pos, uint32_t k
     CU(cudaMemcpyAsync(s->h_counters, d_out, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *run_end = *reinterpret_cast<uint32_t *>(s->h_counters) - d0;
+    return CRF_OK;
+}
+
+// ---- text output (host only) ----------------------------------------------------------------------
+static inline char *put_u32(char *p, uint32_t v) {
+    char tmp[10];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+extern "C" int crf_write_rows(const char *path, int append, int tsv, const char *names, const uint8_t *bases,
+                              const uint64_t *offsets, const uint32_t *record, const uint32_t *start,
+                              const uint32_t *end, const uint32_t *motif_size, uint64_t n_rows, uint64_t *bytes) {
+    if (!path || (n_rows && (!bases || !offsets || !record || !start || !end || !motif_size)) || (!tsv && !names)) {
+        set_err("crf_write_rows: null argument");
+        return CRF_ERR_ARG;
+    }
+    FILE *f = fopen(path, append ? "ab" : "wb");
+    if (!f) { set_err("crf_write_rows: cannot open %s", path); return CRF_ERR_ARG; }
+    std::vector<const char *> name_ptr;
+    std::vector<size_t> name_len;
+    if (!tsv) {
+        uint32_t max_rec = 0;
+        for (uint64_t i = 0; i < n_rows; ++i) max_rec = std::max(max_rec, record[i]);
+        const char *q = names;
+        for (uint32_t r = 0; r <= max_rec && n_rows; ++r) {
+            name_ptr.push_back(q);
+            name_len.push_back(strlen(q));
+            q += name_len.back() + 1;
+        }
+    }
+    uint64_t total = 0;
+    if (tsv && !append) total += fwrite("start_0based\tend\tmotif\n", 1, 23, f);
+    std::vector<char> buf(1 << 22);
+    size_t used = 0;
+    for (uint64_t i = 0; i < n_rows; ++i) {
+        const uint32_t r = record[i], k = motif_size[i];
+        const size_t need = (tsv ? 0 : name_len[r] + 1) + 24 + k + 1;
+        if (used + need > buf.size()) {
+            total += fwrite(buf.data(), 1, used, f);
+            used = 0;
+            if (need > buf.size()) buf.resize(need * 2);
+        }
+        char *p = buf.data() + used;
+        if (!tsv) { memcpy(p, name_ptr[r], name_len[r]); p += name_len[r]; *p++ = '\t'; }
+        p = put_u32(p, start[i]); *p++ = '\t';
+        p = put_u32(p, end[i]); *p++ = '\t';
+        const uint8_t *m = bases + offsets[r] + start[i];
+        for (uint32_t j = 0; j < k; ++j) {
+            uint8_t c = m[j];
+            if (c >= 'a' && c <= 'z') c -= 32;
+            *p++ = (char)c;
+        }
+        *p++ = '\n';
+        used = (size_t)(p - buf.data());
+    }
+    total += fwrite(buf.data(), 1, used, f);
+    const bool ok = fclose(f) == 0;
+    if (bytes) *bytes = total;
+    if (!ok) { set_err("crf_write_rows: write to %s failed", path); return CRF_ERR_ARG; }
     return CRF_OK;
 }

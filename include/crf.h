@@ -144,6 +144,15 @@ int crf_patch_end(crf_seq *seq, uint64_t row, uint32_t new_end);
  * Used to stitch runs that leave a partition (chunk/GPU) -- see DESIGN.md "multi-GPU". */
 int crf_run_end(crf_seq *seq, uint32_t record, uint32_t pos, uint32_t k, uint32_t *run_end);
 
+/* ---- output (host only, no GPU) -------------------------------------------------------------
+ * Writes result rows as text, replacing the per-row Python of prf:148-149 (BED: chrom, start, end, motif) and
+ * prf:166-170 (TSV: start_0based, end, motif, with header).  names = NUL-separated record names in record
+ * order; bases/offsets = the host copy of the records (the motif is bases[offsets[r] + start .. + k),
+ * upper-cased).  append != 0 appends to an existing file.  Returns the number of bytes written in *bytes. */
+int crf_write_rows(const char *path, int append, int tsv, const char *names, const uint8_t *bases,
+                   const uint64_t *offsets, const uint32_t *record, const uint32_t *start, const uint32_t *end,
+                   const uint32_t *motif_size, uint64_t n_rows, uint64_t *bytes);
+
 #ifdef __cplusplus
 }
 #endif

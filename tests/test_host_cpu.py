@@ -57,3 +57,21 @@ def test_synth_numpy_and_torch_agree_and_are_deterministic():
 def test_synth_read_set_shape():
     bases, offsets, _ = synth.sr(500)
     assert bases.size == 500 * 150 and offsets[1] == 150 and offsets[-1] == 75000
+
+
+def test_native_row_writer_bed_and_tsv(tmp_path):
+    """crf_write_rows is host-only code in libcrf.so: BED (prf:148-149) and TSV (prf:166-170) formats."""
+    from crf_b200 import _cabi, build
+    build.build()
+    bases, offsets = b"ACGTacgtNNacgtttttt", [0, 10, 19]
+    bed = tmp_path / "o.bed"
+    n = _cabi.write_rows(str(bed), ["chr1", "chrZ"], bases, offsets, [0, 1, 1], [0, 0, 3], [8, 4, 9], [4, 4, 1])
+    assert bed.read_text() == "chr1\t0\t8\tACGT\nchrZ\t0\t4\tACGT\nchrZ\t3\t9\tT\n" and n == 39
+    tsv = tmp_path / "o.tsv"
+    _cabi.write_rows(str(tsv), None, bases, offsets, [0], [4], [8], [2], tsv=True)
+    assert tsv.read_text() == "start_0based\tend\tmotif\n4\t8\tAC\n"
+    # many rows: buffer flushes
+    k = 5000
+    _cabi.write_rows(str(bed), ["a"], b"ACGT" * 2000, [0, 8000], [0] * k, list(range(k)), list(range(1, k + 1)), [1] * k)
+    lines = bed.read_text().splitlines()
+    assert len(lines) == k and lines[-1].startswith("a\t4999\t5000\t")
