@@ -225,6 +225,7 @@ def main():
         seq.set_output_map(out_record=[u.record for u in mine], out_shift=[u.d0 for u in mine],
                            open_ended=[int(u.d1 < u.rec_len) for u in mine])
     gstate = {"cap": 0, "buf": None, "out": None}
+    MAX_OPEN = 32
 
     trace = {"on": False, "t": []}
 
@@ -240,12 +241,18 @@ def main():
         if world == 1:
             return n
         n_open = int(seq.stats().n_open)
-        hdr = torch.tensor([n, n_open], dtype=torch.int64, device=dev)
-        hdrs = torch.empty(2 * world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(hdrs, hdr)
-        hdrs = hdrs.cpu().tolist()
+        open_rows = seq.fetch_open() if (n_open and plan is not None) else np.zeros((0, 5), np.uint32)
+        # one small all-gather carries every rank's row count and its open-ended rows (record, start, end, k)
+        hdr = torch.full((2 + 4 * MAX_OPEN,), -1, dtype=torch.int64)
+        hdr[0], hdr[1] = n, len(open_rows)
+        if 0 < len(open_rows) <= MAX_OPEN:
+            hdr[2:2 + 4 * len(open_rows)] = torch.from_numpy(open_rows[:, 1:].astype(np.int64).reshape(-1))
+        hdrs = torch.empty(world * hdr.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(hdrs, hdr.to(dev))
+        hdrs = hdrs.cpu().view(world, -1)
         mark('hdr all-gather')
-        counts, any_open = hdrs[0::2], sum(hdrs[1::2])
+        counts = hdrs[:, 0].tolist()
+        n_open_all = hdrs[:, 1].tolist()
         if max(counts) > gstate["cap"]:
             cap = int(max(counts) * 1.05) + 1024
             gstate["cap"] = cap
@@ -255,12 +262,22 @@ def main():
         rec, st, en, kk = (buf[i * cap:i * cap + n] for i in range(4))
         seq.fetch_device(rec.data_ptr(), st.data_ptr(), en.data_ptr(), kk.data_ptr(), n)
         mark('fetch_device')
-        if any_open and plan is not None:             # a repeat longer than the halo crossed a unit end
-            open_rows = seq.fetch_open() if n_open else np.zeros((0, 5), np.uint32)
-            open_mine = [tuple(int(x) for x in row[1:]) for row in open_rows]
-            fixed = partition.stitch_collective(
-                plan, open_mine, lambda unit, lp, k: seq.run_end(unit.index - plan.bounds[rank], lp, k), rank, world,
-                dist, dev)
+        if sum(n_open_all) and plan is not None:      # a repeat longer than the halo crossed a unit end
+            run_end = lambda unit, lp, k: seq.run_end(unit.index - plan.bounds[rank], lp, k)   # noqa: E731
+            if max(n_open_all) <= MAX_OPEN:
+                open_all = [tuple(hdrs[r, 2 + 4 * i:6 + 4 * i].tolist()) for r in range(world) for i in range(n_open_all[r])]
+
+                def exchange(ans):                    # one all-reduce per hop
+                    t = torch.full((len(open_all),), -1, dtype=torch.int64)
+                    for i, v in ans.items():
+                        t[i] = v
+                    t = t.to(dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    return {i: v for i, v in enumerate(t.cpu().tolist()) if v >= 0}
+                fixed = partition.stitch(plan, open_all, run_end, exchange, rank)
+            else:
+                fixed = partition.stitch_collective(plan, [tuple(int(x) for x in row[1:]) for row in open_rows],
+                                                    run_end, rank, world, dist, dev)
             mine_fixed = {(r_, s_, k_): e_ for (r_, s_, e_, k_) in fixed}
             for row in open_rows:
                 new_end = mine_fixed[(int(row[1]), int(row[2]), int(row[4]))]
@@ -279,7 +296,8 @@ def main():
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:                                   # one poller only: nvidia-smi queries perturb running kernels
+        sampler.start()
     time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, scan_ms, launches = [], [], 0
@@ -296,7 +314,7 @@ def main():
     torch.cuda.synchronize()
     elapsed_ms = ev0.elapsed_time(ev1)
     time.sleep(0.3)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
