@@ -179,6 +179,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    if os.environ.get("CRF_BENCH_BLOCKING_SYNC", "0") == "1":     # measured slower at 8 ranks on a 32-core host; off
+        # let synchronisation calls sleep instead of spin.  Must precede the creation of the CUDA context.
+        import ctypes as _ct
+        _rc = _ct.CDLL("libcudart.so.12").cudaInitDevice(local_rank, 4, 1)   # cudaDeviceScheduleBlockingSync, flags valid
+        log(f"[rank {rank}] blocking-sync scheduling requested (cudaInitDevice rc={_rc})")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -285,7 +290,8 @@ def main():
                 en[int(row[0])] = new_end
         mark('stitch')
         dist.gather(buf, gstate["out"], dst=0)       # rank order == genome order: concatenation is the sorted result
-        mark('gather')
+        torch.cuda.synchronize()                     # keep the NCCL copy kernels out of the next step's scan kernel:
+        mark('gather')                               # overlapped, they wait for free SMs and the steps queue up
         return int(sum(counts))
 
     # ---- device-resident timing ----
@@ -296,13 +302,16 @@ def main():
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:                                   # one poller only: nvidia-smi queries perturb running kernels
+    if rank == 0 and not os.environ.get("CRF_BENCH_NO_SAMPLER"):   # one poller only: nvidia-smi queries perturb running kernels
         sampler.start()
     time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, scan_ms, launches = [], [], 0
+    if world > 1:
+        dist.barrier()                               # all ranks enter the timed region together
     torch.cuda.synchronize()
     ev0.record(stream)
+    step_t = [time.perf_counter()]
     for _ in range(args.steps):
         n_res = one_step()
         st_ = seq.stats()
@@ -310,6 +319,9 @@ def main():
         scan_ms.append(st_.scan_ms)
         launches += st_.launches
         total_results = gather_to_rank0(n_res)
+        step_t.append(time.perf_counter())
+    if world > 1:
+        dist.barrier()
     ev1.record(stream)
     torch.cuda.synchronize()
     elapsed_ms = ev0.elapsed_time(ev1)
@@ -322,6 +334,7 @@ def main():
         dist.barrier()
     ms_per_step = elapsed_ms / args.steps
     if args.trace:
+        log(f"[rank {rank}] host time per timed step (ms): " + " ".join(f"{(b - a) * 1e3:.2f}" for a, b in zip(step_t, step_t[1:])))
         trace["on"] = True
         mark("start")
         n_t = one_step()
