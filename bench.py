@@ -190,7 +190,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = _cabi.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # one stream for torch, NCCL waits and the library: the CUDA
+    torch.cuda.set_stream(stream)                   # events below see every kernel of the step
     ctx.set_stream(stream.cuda_stream)
 
     # ---- workload: generated in HBM, deterministic, identical on every rank ----

@@ -1,7 +1,14 @@
-"""Command line of the drop-in: same flags, defaults, messages and output files as the reference's
-main() (perfect_repeat_finder.py:83-179).  Deliberate deviations:
-  * a FASTA file WITHOUT --interval works (the reference raises AttributeError at :139): every record is
-    scanned as detect_repeats(record.seq, filters) -- all records in one GPU load;
+"""Command line of the drop-in.
+
+Same flags, defaults, stdout lines and output files as the reference's main()
+(/root/reference/perfect_repeat_finder.py:83-179), re-organised around two code paths:
+
+  FASTA file  -> <basename(prefix)>.bed in the working directory (chrom, start_0based, end, motif)
+  raw string  -> <prefix>.tsv with a header line (start_0based, end, motif)
+
+Deliberate deviations:
+  * a FASTA file WITHOUT --interval works (the reference raises AttributeError at :139): all records go to the GPU
+    in one load and one scan, rows are written by the native writer (crf_write_rows);
   * --plot is accepted but plotting is out of scope here (matplotlib is not a dependency).
 """
 import argparse
@@ -13,28 +20,52 @@ import numpy as np
 
 from . import _cabi, api, fasta
 
+# (flags, keyword arguments) -- the reference's options, prf:86-98
+_FILTER_OPTIONS = [
+    (("-min", "--min-motif-size"), dict(default=1, type=int, help="Smallest motif size (bp) to look for.")),
+    (("-max", "--max-motif-size"), dict(default=50, type=int, help="Largest motif size (bp) to look for.")),
+    (("--min-repeats",), dict(default=3, type=int, help="Report a locus only if the motif occurs at least this many "
+                                                         "times in a row.")),
+    (("--min-span",), dict(default=9, type=int, help="Report a locus only if it covers at least this many bases.")),
+]
+_OTHER_OPTIONS = [
+    (("-i", "--interval"), dict(help="Restrict the scan to chrom:start_0based-end (FASTA input only).")),
+    (("-p", "--plot"), dict(help="Plot file name (accepted for compatibility; plotting is not part of this build).")),
+    (("-o", "--output-prefix"), dict(help="Prefix of the output file: <prefix>.tsv for a sequence given on the command "
+                                          "line, <basename(prefix)>.bed for a FASTA file.")),
+    (("--verbose",), dict(action="store_true", help="Accepted for compatibility.")),
+    (("--debug",), dict(action="store_true", help="Accepted for compatibility.")),
+    (("--show-progress-bar",), dict(action="store_true", help="Accepted for compatibility.")),
+]
+
 
 def build_parser():
-    parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    group = parser.add_argument_group("Repeat Filters")
-    group.add_argument("-min", "--min-motif-size", default=1, type=int, help="Minimum motif size in base pairs.")
-    group.add_argument("-max", "--max-motif-size", default=50, type=int, help="Maximum motif size in base pairs.")
-    group.add_argument("--min-repeats", default=3, type=int, help="The minimum number of repeats to look for.")
-    group.add_argument("--min-span", default=9, type=int, help="The repeats should span at least this many consecutive "
-                                                               "bases in the input sequence.")
-    parser.add_argument("-i", "--interval", help="Only consider sequence from this interval (chrom:start_0based-end).")
-    parser.add_argument("-p", "--plot", help="Write out a plot with this filename.")
-    parser.add_argument("-o", "--output-prefix", help="The output filename prefix for the output TSV file. If the input "
-                                                      "is a FASTA file, a BED file will also be generated.")
-    parser.add_argument("--verbose", action="store_true", help="Print verbose output.")
-    parser.add_argument("--debug", action="store_true", help="Print debugging output.")
-    parser.add_argument("--show-progress-bar", action="store_true", help="Show progress bar.")
-    parser.add_argument("input_sequence", help="The nucleotide sequence, or a FASTA file path")
+    parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter,
+                                     description="Find perfect tandem repeats (B200 build).")
+    filters = parser.add_argument_group("Repeat Filters")
+    for flags, kw in _FILTER_OPTIONS:
+        filters.add_argument(*flags, **kw)
+    for flags, kw in _OTHER_OPTIONS:
+        parser.add_argument(*flags, **kw)
+    parser.add_argument("input_sequence", help="A nucleotide string, or the path of a FASTA file (plain or .gz)")
     return parser
 
 
-def _scan_records_to_bed(records, args, bed_path):
-    """All records in one load / one scan; rows written by the native writer.  Returns rows per record."""
+def _check_filters(parser, args):
+    """prf:102-109 -- same messages, exit status 2."""
+    for value, flag, floor in ((args.min_motif_size, "--min-motif-size", "1"),):
+        if value < 1:
+            parser.error(f"{flag} is set to {value}. It must be at least {floor}.")
+    if args.max_motif_size < args.min_motif_size:
+        parser.error(f"--max-motif-size is set to {args.max_motif_size}. It must be at least --min-motif-size.")
+    if args.min_repeats < 1:
+        parser.error(f"--min-repeats is set to {args.min_repeats}. It must be at least 1.")
+    if args.min_span < 1:
+        parser.error(f"--min-span is set to {args.min_span}. It must be at least 1.")
+
+
+def _whole_fasta_to_bed(records, args, bed_path):
+    """Every record of the file: one load, one scan, native row writer.  Returns the row count per record."""
     ctx = api.get_context()
     lengths = np.array([len(r.seq) for r in records], dtype=np.uint64)
     offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
@@ -51,82 +82,64 @@ def _scan_records_to_bed(records, args, bed_path):
     return counts
 
 
+def _run_fasta(parser, args):
+    if not args.output_prefix:
+        args.output_prefix = re.sub(".fa(sta)?(.gz)?", "", args.input_sequence)   # the (unanchored) regex of prf:114
+    bed_path = f"{os.path.basename(args.output_prefix)}.bed"                       # always in the working directory
+    records = fasta.read_fasta(args.input_sequence)
+
+    if args.interval:
+        fields = re.split("[:-]", args.interval)
+        if len(fields) != 3:
+            parser.error("Invalid --interval format. Must be chrom:start_0based-end")
+        args.interval_chrom = fields[0]
+        args.interval_start_0based, args.interval_end = int(fields[1]), int(fields[2])
+        chosen = next((r for r in records if r.name == args.interval_chrom), None)
+        if chosen is None:
+            parser.error(f"Chromosome {args.interval_chrom} not found in the input FASTA file")
+        args.interval_end = min(args.interval_end, len(chosen.seq))               # prf:139-140
+        print(f"Processing {chosen.name} ({args.interval_end - args.interval_start_0based:,d} bp)")
+        rows = api.detect_repeats(chosen.seq, args)
+        print(f"Found {len(rows):,d} repeats")
+        with open(bed_path, "wt") as bed_file:
+            bed_file.write("".join(f"{chosen.name}\t{s}\t{e}\t{m}\n" for s, e, m in rows))
+    else:
+        counts = _whole_fasta_to_bed(records, args, bed_path)
+        for record, n_found in zip(records, counts.tolist()):
+            print(f"Processing {record.name} ({len(record.seq):,d} bp)")
+            print(f"Found {n_found:,d} repeats")
+    print(f"Wrote results to {bed_path}")
+
+
+def _run_raw(parser, args):
+    if args.interval:
+        parser.error("The --interval option is only supported for FASTA files.")
+    if not args.output_prefix:
+        args.output_prefix = "repeats"
+    tsv_path = f"{args.output_prefix}.tsv"
+    rows = api.detect_repeats(args.input_sequence, args)
+    print(f"Found {len(rows):,d} repeats")
+    with open(tsv_path, "wt") as tsv_file:
+        tsv_file.write("start_0based\tend\tmotif\n")
+        tsv_file.writelines(f"{s}\t{e}\t{m}\n" for s, e, m in rows)
+    print(f"Wrote results to {tsv_path}")
+    if args.plot:
+        if len(args.input_sequence) > 5_000:
+            print(f"Warning: The input sequence is too long ({len(args.input_sequence):,d} bp). Skipping plot...")
+        else:
+            print("Warning: plotting is not part of this build (matplotlib is not a dependency). Skipping plot...")
+
+
 def main(argv=None):
     parser = build_parser()
     args = parser.parse_args(argv)
-
-    if args.min_motif_size < 1:
-        parser.error(f"--min-motif-size is set to {args.min_motif_size}. It must be at least 1.")
-    if args.max_motif_size < args.min_motif_size:
-        parser.error(f"--max-motif-size is set to {args.max_motif_size}. It must be at least --min-motif-size.")
-    if args.min_repeats < 1:
-        parser.error(f"--min-repeats is set to {args.min_repeats}. It must be at least 1.")
-    if args.min_span < 1:
-        parser.error(f"--min-span is set to {args.min_span}. It must be at least 1.")
-
-    interval_sequence = None
+    _check_filters(parser, args)
     if os.path.isfile(args.input_sequence):
-        if not args.output_prefix:
-            args.output_prefix = re.sub(".fa(sta)?(.gz)?", "", args.input_sequence)   # same (unanchored) regex as prf:114
-
-        output_bed_path = f"{os.path.basename(args.output_prefix)}.bed"
-        fasta_entries = fasta.read_fasta(args.input_sequence)
-        if args.interval:
-            interval = re.split("[:-]", args.interval)
-            if len(interval) != 3:
-                parser.error("Invalid --interval format. Must be chrom:start_0based-end")
-            args.interval_chrom, args.interval_start_0based, args.interval_end = interval
-            args.interval_start_0based = int(args.interval_start_0based)
-            args.interval_end = int(args.interval_end)
-            matches = [e for e in fasta_entries if e.name == args.interval_chrom]
-            if not matches:
-                parser.error(f"Chromosome {args.interval_chrom} not found in the input FASTA file")
-            fasta_entries = [matches[0]]
-
-        if args.interval:
-            with open(output_bed_path, "wt") as bed_file:
-                entry = fasta_entries[0]
-                seq_len = len(entry.seq)
-                if args.interval_end > seq_len:
-                    args.interval_end = seq_len
-                seq_len = args.interval_end - args.interval_start_0based
-                print(f"Processing {entry.name} ({seq_len:,d} bp)")
-                output_intervals = api.detect_repeats(entry.seq, args)
-                print(f"Found {len(output_intervals):,d} repeats")
-                bed_file.write("".join(f"{entry.name}\t{s}\t{e}\t{m}\n" for s, e, m in output_intervals))
-        else:
-            counts = _scan_records_to_bed(fasta_entries, args, output_bed_path)
-            for entry, n_found in zip(fasta_entries, counts.tolist()):
-                print(f"Processing {entry.name} ({len(entry.seq):,d} bp)")
-                print(f"Found {n_found:,d} repeats")
-
-        print(f"Wrote results to {output_bed_path}")
-
+        _run_fasta(parser, args)
     elif set(args.input_sequence.upper()) <= set("ACGTN"):
-        if args.interval:
-            parser.error("The --interval option is only supported for FASTA files.")
-
-        interval_sequence = args.input_sequence
-        if not args.output_prefix:
-            args.output_prefix = "repeats"
-        output_tsv_path = f"{args.output_prefix}.tsv"
-
-        output_intervals = api.detect_repeats(args.input_sequence, args)
-        print(f"Found {len(output_intervals):,d} repeats")
-
-        with open(output_tsv_path, "wt") as tsv_file:
-            tsv_file.write("\t".join(["start_0based", "end", "motif"]) + "\n")
-            for start_0based, end, motif in output_intervals:
-                tsv_file.write("\t".join([str(start_0based), str(end), motif]) + "\n")
-        print(f"Wrote results to {output_tsv_path}")
+        _run_raw(parser, args)
     else:
         parser.error(f"Invalid input: {args.input_sequence}. This should be a FASTA file path or a string of nucleotides.")
-
-    if args.plot and interval_sequence:
-        if len(interval_sequence) > 5_000:
-            print(f"Warning: The input sequence is too long ({len(interval_sequence):,d} bp). Skipping plot...")
-        else:
-            print("Warning: plotting is not part of this build (matplotlib is not a dependency). Skipping plot...")
     return 0
 
 

@@ -157,3 +157,65 @@ def test_large_motif_range_like_the_hail_pipeline(prf, oracle):
     assert any(len(m) >= 500 for _, _, m in want)
     for knobs in ({}, {"words_per_thread": 1}):
         assert prf.detect_repeats(seq, fs, **knobs) == want
+
+
+def test_knob_settings_agree_and_stream_binding(prf):
+    """Every tile shape gives the same rows; the library runs on a caller-provided CUDA stream."""
+    import torch
+    from crf_b200 import _cabi
+    rng = random.Random(123)
+    seq = random_seq(rng, 300_000).encode()
+    ctx = _cabi.Context(0)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    ref = None
+    with ctx.load(seq, max_motif_cap=64) as s:
+        for wpt in (1, 2, 4, 8, 16):
+            n = s.scan(1, 64, 3, 9, words_per_thread=wpt)
+            rows = [a.tolist() for a in s.fetch(n)]
+            ref = ref or rows
+            assert rows == ref and n > 100
+        st = s.stats()
+        assert st.kernel_ms > 0 and st.scan_ms >= st.kernel_ms and st.launches >= 5
+        info = s.info()
+        assert info.total_bases == len(seq) and info.n_records == 1 and info.max_motif_cap == 64
+    ctx.set_stream(0)
+    ctx.close()
+
+
+def test_c_abi_error_paths(prf):
+    import ctypes
+    import numpy as np
+    from crf_b200 import _cabi
+    lib = _cabi.lib()
+    ctx = _cabi.Context(0)
+    with pytest.raises(ValueError):
+        ctx.load(b"ACGT", max_motif_cap=0)
+    with pytest.raises(NotImplementedError):
+        ctx.load(b"ACGT", max_motif_cap=70000)
+    with pytest.raises(ValueError):
+        _cabi.Context(1234)
+    with ctx.load(b"ACGTACGTACGTACGT", max_motif_cap=8) as s:
+        with pytest.raises(ValueError, match="exceeds the max_motif_cap"):
+            s.scan(1, 9, 3, 9)
+        with pytest.raises(ValueError, match="no scan results"):
+            s.fetch(1)
+        n = s.scan(1, 8, 3, 9)
+        assert n == 1
+        small = np.zeros(0, np.uint32)
+        rc = lib.crf_fetch(s._h, small.ctypes.data, small.ctypes.data, small.ctypes.data, small.ctypes.data, 0, 0)
+        assert rc == _cabi.CRF_ERR_CAPACITY and b"capacity" in lib.crf_last_error()
+        with pytest.raises(ValueError):
+            s.run_end(0, 99, 2)
+        assert s.run_end(0, 0, 4) == 12       # M_4 is one for positions 0..11 of ACGTx4
+        with pytest.raises(ValueError):
+            s.scan(1, 8, 3, 9, words_per_thread=3)
+    ctx.close()
+
+
+def test_non_ascii_text(prf, oracle):
+    fs = ns(min_motif_size=1, max_motif_size=5, min_repeats=3, min_span=6)
+    seq = "ACGT" + "é" * 7 + "acacacacac"          # latin-1 symbol: an ordinary letter for the reference
+    assert prf.detect_repeats(seq, fs) == [(4, 11, "É"), (11, 21, "AC")]
+    with pytest.raises(NotImplementedError):
+        prf.detect_repeats("ACGT\u0394\u0394\u0394\u0394\u0394\u0394\u0394", fs)
