@@ -123,7 +123,7 @@ def _interval_stop_position(ctx, s, end_position, kmin, kmax, knobs):
         keep = hi_c > lo_c
         np.add.at(diff, lo_c[keep], 1)
         np.add.at(diff, hi_c[keep], -1)
-        covered = np.cumsum(diff[:-1]) > 0
+        covered = np.cumsum(diff)[:hi_t - E] > 0        # one entry per t in [E+1, hi_t]
         free = np.flatnonzero(~covered)
         if free.size:
             return E + 1 + int(free[0])

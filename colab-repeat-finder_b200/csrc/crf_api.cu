@@ -588,7 +588,8 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         s->ktab_for.min_motif_size != pr->min_motif_size) {
         std::vector<KEntry> tab;
         std::vector<Seg> segs;
-        build_ktab(*pr, s->n_exotic == 0 && !(pr->flags & CRF_SCAN_DEBUG_NO_SUP), tab, segs);
+        // the suppression relies on the primitivity rule dropping what it hides: not with CRF_SCAN_NO_PRIMITIVITY
+        build_ktab(*pr, s->n_exotic == 0 && !(pr->flags & (CRF_SCAN_DEBUG_NO_SUP | CRF_SCAN_NO_PRIMITIVITY)), tab, segs);
         s->sup_enabled = 0;
         for (const Seg &g : segs) s->sup_enabled |= (g.mode >> 4) ? 1u : 0u;
         if (s->segs_cap < segs.size()) {

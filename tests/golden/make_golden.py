@@ -121,6 +121,25 @@ def fuzz(ref, seed, count, mode):
     return out
 
 
+def fuzz_interval_long(ref, seed, count):
+    """Interval mode with repeats that run far past interval_end (the lock-step loop keeps going while a
+    tracker is mid-repeat, prf:70-74) and with motif size 1 not always tracked."""
+    rng = random.Random(seed)
+    out = []
+    for _ in range(count):
+        seq = random_seq(rng, 1500)
+        unit = "".join(rng.choice("ACGT") for _ in range(rng.choice([1, 1, 2, 3, 7])))
+        pos = rng.randint(0, len(seq))
+        seq = seq[:pos] + unit * rng.randint(150, 900) + seq[pos:]
+        a = rng.randint(max(0, pos - 200), pos + 100)
+        b = rng.randint(a, min(len(seq), pos + 300))
+        kmin = rng.choice([1, 2, 3])
+        kw = dict(min_motif_size=kmin, max_motif_size=kmin + rng.choice([3, 10, 30]), min_repeats=rng.choice([2, 3]),
+                  min_span=rng.choice([9, 40]), interval_start_0based=a, interval_end=b)
+        out.append(run_case(ref, seq, kw))
+    return out
+
+
 def main():
     ref = import_reference()
     # sanity: the reference's own test-suite passes under the stubs
@@ -138,6 +157,7 @@ def main():
     dump("fuzz_full.json", fuzz(ref, 1001, 700, "full"))
     dump("fuzz_interval.json", fuzz(ref, 2002, 400, "interval"))
     dump("fuzz_minrep1.json", fuzz(ref, 3003, 300, "minrep1"))
+    dump("fuzz_interval_long.json", fuzz_interval_long(ref, 4004, 40))
 
 
 if __name__ == "__main__":

@@ -31,7 +31,7 @@ KNOB_SETS = [
 
 
 @pytest.mark.parametrize("knobs", KNOB_SETS)
-@pytest.mark.parametrize("name", ["kat.json", "fuzz_full.json", "fuzz_interval.json"])
+@pytest.mark.parametrize("name", ["kat.json", "fuzz_full.json", "fuzz_interval.json", "fuzz_interval_long.json"])
 def test_golden_vectors(prf, name, knobs):
     for i, case in enumerate(load_golden(name)):
         fs = ns(**case["settings"])
@@ -219,3 +219,27 @@ def test_non_ascii_text(prf, oracle):
     assert prf.detect_repeats(seq, fs) == [(4, 11, "É"), (11, 21, "AC")]
     with pytest.raises(NotImplementedError):
         prf.detect_repeats("ACGT\u0394\u0394\u0394\u0394\u0394\u0394\u0394", fs)
+
+
+def test_interval_mode_with_long_runs_past_the_interval_end(prf, oracle):
+    """Found by tests/fuzz_gpu.py: the stop position of the reference's loop (prf:73-74) when a repeat runs far
+    beyond interval_end (several probe windows), with and without motif size 1 being tracked."""
+    rng = random.Random(99)
+    for case in range(40):
+        seq = random_seq(rng, rng.randint(3000, 30000))
+        unit = "".join(rng.choice("ACGT") for _ in range(rng.choice([1, 1, 2, 3, 16])))
+        pos = rng.randint(0, len(seq))
+        seq = seq[:pos] + unit * rng.randint(100, 3000) + seq[pos:]
+        a = rng.randint(max(0, pos - 500), pos + 200)
+        b = rng.randint(a, min(len(seq), pos + 600))
+        fs = ns(min_motif_size=rng.choice([1, 2, 3]), max_motif_size=rng.choice([6, 20, 64]), min_repeats=rng.choice([2, 3]),
+                min_span=rng.choice([9, 100]), interval_start_0based=a, interval_end=b)
+        try:
+            want, exc = oracle.detect_repeats(seq, fs), None
+        except AssertionError:
+            want, exc = None, AssertionError
+        if exc:
+            with pytest.raises(exc):
+                prf.detect_repeats(seq, fs)
+        else:
+            assert prf.detect_repeats(seq, fs) == want, f"case {case}: {fs}"

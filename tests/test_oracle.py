@@ -14,7 +14,7 @@ def _run(case, fn=oracle.detect_repeats):
     return fn(case["seq"], ns(**case["settings"]))
 
 
-@pytest.mark.parametrize("name", ["kat.json", "fuzz_full.json", "fuzz_interval.json", "fuzz_minrep1.json"])
+@pytest.mark.parametrize("name", ["kat.json", "fuzz_full.json", "fuzz_interval.json", "fuzz_minrep1.json", "fuzz_interval_long.json"])
 def test_oracle_matches_reference_golden(name):
     cases = load_golden(name)
     assert cases
