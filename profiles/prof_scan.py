@@ -16,6 +16,7 @@ ap.add_argument("--scale", type=float, default=0.25)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--fast-only", action="store_true")
 ap.add_argument("--no-sup", action="store_true")
+ap.add_argument("--outcap", type=int, default=0)
 ap.add_argument("--wpt", type=int, default=0)
 ap.add_argument("--kmin", type=int, default=1)
 ap.add_argument("--kmax", type=int, default=50)
@@ -26,7 +27,7 @@ ctx = _cabi.Context(0)
 seq = ctx.load(bases.data_ptr(), offsets, max_motif_cap=args.kmax, on_device=True)
 flags = ((1 << 16) if args.fast_only else 0) | ((1 << 17) if args.no_sup else 0)
 for i in range(args.reps):
-    n = seq.scan(args.kmin, args.kmax, 3, 9, flags=flags, words_per_thread=args.wpt)
+    n = seq.scan(args.kmin, args.kmax, 3, 9, flags=flags, words_per_thread=args.wpt, tile_out_cap=args.outcap)
     st = seq.stats()
     print(f"rep {i}: kernel {st.kernel_ms:.3f} ms scan {st.scan_ms:.3f} ms results {n} cand {st.n_candidates} "
           f"bp {int(offsets[-1])} -> {int(offsets[-1]) / st.kernel_ms / 1e6:.1f} Gbp/s (kernel)")

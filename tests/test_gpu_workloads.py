@@ -108,6 +108,41 @@ def test_output_map_open_rows_and_patch(mods):
     assert np.array_equal(st, whole[0]) and np.array_equal(en, whole[1]) and np.array_equal(k, whole[2])
 
 
+def test_c4_chunk_crossing_repeats_256mbp(mods):
+    """Config C4 at full size: one 256 Mbp record with perfect repeats of 0.5 / 1 / 2.5 chunks (2-10 Mbp) whose
+    ends sit within +-(k+1) of chunk boundaries, a run to the last base and runs abutting N.  Whole-record scan
+    vs the oracle, then the same record cut into 62 units with a 64 kbp halo, every long repeat stitched."""
+    chunk, halo = 1 << 22, 1 << 16
+    bases, offsets, meta = mods.synth.sx(256_000_000, chunk, device="cuda:0")
+    assert len(meta["planted"]) >= 20
+    host = bases.cpu().numpy()
+    ctx = mods.api.get_context()
+    with ctx.load(bases.data_ptr(), offsets, max_motif_cap=50, on_device=True) as seq:
+        n = seq.scan(1, 50, 3, 9)
+        _, st, en, k = seq.fetch(n)
+        assert seq.stats().n_long >= 20
+    o_s, o_e, o_m, _ = mods.oracle.detect_repeats_by_k(host, ns(**DEFAULTS), arrays=True)
+    assert np.array_equal(st, o_s) and np.array_equal(en, o_e) and np.array_equal(k, o_m)
+    spans = en.astype(np.int64) - st
+    assert (spans > 2 * chunk).sum() >= 5
+    # partitioned: units of 4 Mbp + halo, results in record coordinates, open-ended rows fixed in place
+    plan = mods.partition.Plan([host.size], 1, chunk, halo, 50, 3, 9)
+    starts, lens, own_lo, own_hi = plan.load_args(0, [0])
+    with ctx.load_ranges(bases.data_ptr(), starts, lens, own_lo, own_hi, max_motif_cap=50, on_device=True) as seq:
+        seq.set_output_map(out_record=[u.record for u in plan.units], out_shift=[u.d0 for u in plan.units],
+                           open_ended=[int(u.d1 < u.rec_len) for u in plan.units])
+        n2 = seq.scan(1, 50, 3, 9)
+        assert n2 == n
+        open_rows = seq.fetch_open()
+        assert len(open_rows) >= 20
+        fixed = mods.partition.stitch(plan, [tuple(int(x) for x in r[1:]) for r in open_rows],
+                                      lambda unit, lp, kk: seq.run_end(unit.index, lp, kk))
+        for row, (_r, _s, e, _k) in zip(open_rows, fixed):
+            seq.patch_end(int(row[0]), e)
+        _, st2, en2, k2 = seq.fetch(n2)
+    assert np.array_equal(st2, st) and np.array_equal(en2, en) and np.array_equal(k2, k)
+
+
 def test_chr22_sized_record_bit_exact(mods):
     """Configs C1 / C2 on the chr22-shaped stand-in (benchmark/chr22.fa.gz is not in the reference checkout)."""
     bases, offsets, meta = mods.synth.s22(device="cuda:0")
