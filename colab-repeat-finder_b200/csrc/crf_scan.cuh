@@ -14,12 +14,16 @@
 //      and, for every k, forms the shifted-compare words with funnel shifts and tests a
 //      *necessary* condition for "a qualifying run starts in my strip" (FilterMode); the motif
 //      sizes come as segments of constant filter, so the inner loop has no table look-ups and no
-//      branches; the result is one bit per (strip, k) in a register;
+//      branches; for 2 <= k <= 16 positions that start a stretch of more than 8 / 16 equal bases count
+//      as mismatches (no primitive motif of that size can contain them), which removes the
+//      candidates that homopolymers would otherwise raise for every multiple of 1; the result is
+//      one bit per (strip, k) in a register;
 //   3. exact phase -- the block compacts the (strip, k) hits (prefix sum, no atomics); one
 //      thread per hit re-evaluates the exact mask from shared memory (N mask; exotic symbols via
-//      global memory), locates run starts as "first fully matching aligned unit of a run", walks
-//      right to the run end, applies the thresholds and the primitivity rule and appends
-//      (start, end, k) to the tile's shared-memory result list;
+//      global memory), erodes it by min(r_min, 32) across word boundaries -- the rising edges of the
+//      eroded mask are the starts of runs of at least that many matches --, walks right to the run
+//      end, applies the thresholds and the primitivity rule and appends (start, end, k) to the
+//      tile's shared-memory result list;
 //   4. runs longer than walk_limit words are finished by the whole block (256 words per step);
 //   5. the tile's results are ordered by (start, end) with a counting sort over strips and
 //      written as one segment; a later pass concatenates the segments in tile order, which is
