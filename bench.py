@@ -28,7 +28,7 @@ for p in (ROOT, os.path.join(ROOT, "colab-repeat-finder_b200")):
 import numpy as np  # noqa: E402
 
 KMIN, KMAX, MIN_REPEATS, MIN_SPAN = 1, 50, 3, 9       # the reference CLI defaults (prf:86-89)
-METRIC = "Gbp/s scanned (motif 1-50)"
+METRIC = "Gbp/s scanned (motif 1-50)"     # BASELINE.json metric; the reads workload (--workload sr) scans motif 1-20
 
 
 def log(*a):

@@ -64,21 +64,32 @@ def _check_filters(parser, args):
         parser.error(f"--min-span is set to {args.min_span}. It must be at least 1.")
 
 
+MAX_LOAD_BASES = 3_500_000_000   # one device load holds < 2^32 layout positions (records + gaps); larger files go in groups
+
+
 def _whole_fasta_to_bed(records, args, bed_path):
-    """Every record of the file: one load, one scan, native row writer.  Returns the row count per record."""
+    """Every record of the file: as few loads as the 2^32-position limit allows (one for a human genome), one scan
+    per load, native row writer.  Returns the row count per record."""
     ctx = api.get_context()
-    lengths = np.array([len(r.seq) for r in records], dtype=np.uint64)
-    offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
-    blob = b"".join(r.seq for r in records)
     counts = np.zeros(len(records), dtype=np.int64)
-    if not len(blob):
-        open(bed_path, "wb").close()
-        return counts
-    with ctx.load(blob, offsets, max_motif_cap=args.max_motif_size) as seq:
-        n = seq.scan(args.min_motif_size, args.max_motif_size, args.min_repeats, args.min_span)
-        rec, start, end, k = seq.fetch(n)
-    _cabi.write_rows(bed_path, [r.name for r in records], blob, offsets, rec, start, end, k)
-    np.add.at(counts, rec.astype(np.int64), 1)
+    open(bed_path, "wb").close()
+    first = 0
+    while first < len(records):
+        last, total = first, 0
+        while last < len(records) and (last == first or total + len(records[last].seq) <= MAX_LOAD_BASES):
+            total += len(records[last].seq)
+            last += 1
+        group = records[first:last]
+        lengths = np.array([len(r.seq) for r in group], dtype=np.uint64)
+        offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+        blob = b"".join(r.seq for r in group)
+        if len(blob):
+            with ctx.load(blob, offsets, max_motif_cap=args.max_motif_size) as seq:
+                n = seq.scan(args.min_motif_size, args.max_motif_size, args.min_repeats, args.min_span)
+                rec, start, end, k = seq.fetch(n)
+            _cabi.write_rows(bed_path, [r.name for r in group], blob, offsets, rec, start, end, k, append=True)
+            np.add.at(counts, rec.astype(np.int64) + first, 1)
+        first = last
     return counts
 
 
