@@ -164,12 +164,13 @@ def stitch_collective(plan, open_mine, run_end_fn, rank, world, dist, device):
 
 
 def scan_partitioned(ctx, bases, record_starts, lengths, kmin, kmax, min_repeats, min_span, rank=0, world=1,
-                     chunk=DEFAULT_CHUNK, halo=DEFAULT_HALO, on_device=False, dist=None, **knobs):
+                     chunk=DEFAULT_CHUNK, halo=DEFAULT_HALO, on_device=False, dist=None, tensor_device=None, **knobs):
     """Scan `lengths` records split over `world` ranks; every rank returns the full, stitched,
     (record, start, end)-sorted result as numpy arrays (record, start, end, k).
 
     dist: torch.distributed (initialised) when world > 1; results travel with all_gather_object
-    (bench.py uses a device-side gather instead)."""
+    (bench.py uses a device-side gather instead).  tensor_device: stitch with fixed-size tensor collectives
+    on that device (stitch_collective) instead of pickled objects."""
     plan = Plan(lengths, world, chunk, halo, kmax, min_repeats, min_span)
     starts, lens, own_lo, own_hi = plan.load_args(rank, record_starts)
     mine = plan.units_of(rank)
@@ -204,7 +205,10 @@ def scan_partitioned(ctx, bases, record_starts, lengths, kmin, kmax, min_repeats
             merged.update(part)
         return merged
 
-    stitched = stitch(plan, open_all, run_end_fn, exchange if world > 1 else None, rank)
+    if world > 1 and tensor_device is not None:
+        stitched = stitch_collective(plan, open_mine, run_end_fn, rank, world, dist, tensor_device)
+    else:
+        stitched = stitch(plan, open_all, run_end_fn, exchange if world > 1 else None, rank)
     parts = gather_obj(closed)
     rows = np.concatenate(parts, axis=1) if parts else closed
     if stitched:

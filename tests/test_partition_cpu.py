@@ -83,7 +83,13 @@ def _worker(rank, world, port, q):
     starts = np.concatenate([[0], np.cumsum(lengths)])[:-1]
     rec, st, en, k = partition.scan_partitioned(FakeContext(), b"".join(records), starts, lengths, KMIN, KMAX, MR, MS,
                                                 rank=rank, world=world, chunk=300, halo=64, dist=dist)
-    q.put((rank, list(zip(rec.tolist(), st.tolist(), en.tolist(), k.tolist()))))
+    first = list(zip(rec.tolist(), st.tolist(), en.tolist(), k.tolist()))
+    # the same with the fixed-size tensor collectives bench.py uses for the stitch (CPU tensors over gloo)
+    rec, st, en, k = partition.scan_partitioned(FakeContext(), b"".join(records), starts, lengths, KMIN, KMAX, MR, MS,
+                                                rank=rank, world=world, chunk=300, halo=64, dist=dist,
+                                                tensor_device="cpu")
+    assert list(zip(rec.tolist(), st.tolist(), en.tolist(), k.tolist())) == first
+    q.put((rank, first))
     dist.barrier()
     dist.destroy_process_group()
 
