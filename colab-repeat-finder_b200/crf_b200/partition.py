@@ -146,9 +146,9 @@ def stitch_collective(plan, open_mine, run_end_fn, rank, world, dist, device):
     if open_mine:
         mine[1:1 + len(open_mine)] = torch.tensor(open_mine, dtype=torch.int64)
     mine = mine.to(device)
-    allrows = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=device)
+    allrows = torch.empty((world * mine.shape[0], 4), dtype=torch.int64, device=device)   # concatenated along dim 0
     dist.all_gather_into_tensor(allrows, mine)
-    allrows = allrows.cpu().numpy()
+    allrows = allrows.cpu().numpy().reshape(world, mine.shape[0], 4)
     open_all = [tuple(int(x) for x in allrows[r, 1 + i]) for r in range(world) for i in range(int(allrows[r, 0, 0]))]
 
     def exchange(answers):
