@@ -20,6 +20,7 @@ EXPORTS = [
     "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
     "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
     "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end", "crf_write_rows",
+    "crf_fasta_open", "crf_fasta_info", "crf_fasta_data", "crf_fasta_close",
 ]
 
 
@@ -81,6 +82,10 @@ def lib():
         L.crf_fetch_open.argtypes = [vp, vp, u32, P(u32)]
         L.crf_patch_end.argtypes = [vp, u64, u32]
         L.crf_write_rows.argtypes = [ctypes.c_char_p, i, i, vp, vp, vp, vp, vp, vp, vp, u64, P(u64)]
+        L.crf_fasta_open.argtypes = [ctypes.c_char_p, u32, i, P(vp)]
+        L.crf_fasta_info.argtypes = [vp, P(u64), P(u64), P(i)]
+        L.crf_fasta_data.argtypes = [vp, P(vp), P(vp), P(vp), P(u64)]
+        L.crf_fasta_close.argtypes = [vp]
         for name in EXPORTS:
             if name != "crf_last_error":
                 getattr(L, name).restype = i
@@ -258,9 +263,57 @@ class Sequence:
             pass
 
 
+class Fasta:
+    """A FASTA file read by the native reader (crf_fasta_open): `bases` (uint8 view of all records back to
+    back, owned by the library until close()), `offsets` (n_records+1, uint64), `names` (list of str) and
+    `names_blob` (NUL-separated, as crf_write_rows takes them)."""
+
+    def __init__(self, path, n_threads=0, pinned=False):
+        self._h = ctypes.c_void_p()
+        _check(lib().crf_fasta_open(os.fsencode(path), n_threads, int(pinned), ctypes.byref(self._h)))
+        n_rec, total, pin = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
+        _check(lib().crf_fasta_info(self._h, ctypes.byref(n_rec), ctypes.byref(total), ctypes.byref(pin)))
+        bases, offsets, names, nbytes = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64()
+        _check(lib().crf_fasta_data(self._h, ctypes.byref(bases), ctypes.byref(offsets), ctypes.byref(names),
+                                    ctypes.byref(nbytes)))
+        self.n_records, self.total_bases, self.pinned = n_rec.value, total.value, bool(pin.value)
+        self.bases = np.ctypeslib.as_array(ctypes.cast(bases, ctypes.POINTER(ctypes.c_uint8)),
+                                           shape=(max(self.total_bases, 1),))[:self.total_bases]
+        self.offsets = np.ctypeslib.as_array(ctypes.cast(offsets, ctypes.POINTER(ctypes.c_uint64)),
+                                             shape=(self.n_records + 1,)).copy()
+        self.names_blob = ctypes.string_at(names, nbytes.value) if nbytes.value else b""
+        self.names = [x.decode("utf-8", "replace") for x in self.names_blob.split(b"\0")[:self.n_records]]
+
+    def record(self, i):
+        """uint8 view of record i."""
+        return self.bases[int(self.offsets[i]):int(self.offsets[i + 1])]
+
+    def close(self):
+        if self._h:
+            self.bases = None
+            lib().crf_fasta_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def write_rows(path, names, bases, offsets, record, start, end, k, tsv=False, append=False):
-    """Native BED / TSV writer (crf_write_rows).  bases: bytes or uint8 array with all records back to back."""
-    blob = b"".join(n.encode("utf-8") + b"\0" for n in names) if names is not None else None
+    """Native BED / TSV writer (crf_write_rows).  bases: bytes or uint8 array with all records back to back;
+    names: list of str, or the NUL-separated blob."""
+    if isinstance(names, (bytes, bytearray)):
+        blob = bytes(names)
+    else:
+        blob = b"".join(n.encode("utf-8") + b"\0" for n in names) if names is not None else None
     arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (record, start, end, k)]
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     if isinstance(bases, np.ndarray):

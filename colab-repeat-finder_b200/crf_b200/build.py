@@ -6,9 +6,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 OUT = os.path.join(_HERE, "libcrf.so")
 SOURCES = ["crf_api.cu"]
-HEADERS = ["crf_device.cuh", "crf_scan.cuh", "crf_aux.cuh"]
+HEADERS = ["crf_device.cuh", "crf_scan.cuh", "crf_aux.cuh", "crf_fasta.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC,-pthread"]
+LINK_FLAGS = ["-lz"]
 
 
 TOOLS_OUT = os.path.join(_HERE, "libcrf_tools.so")   # bench-only helpers (INT32 peak micro-benchmark)
@@ -25,7 +26,7 @@ def _stale(out, deps):
 def _nvcc(out, sources, verbose):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
-          [os.path.join(CSRC, f) for f in sources]
+          [os.path.join(CSRC, f) for f in sources] + LINK_FLAGS
     subprocess.check_call(cmd)
 
 

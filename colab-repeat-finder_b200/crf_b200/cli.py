@@ -67,27 +67,28 @@ def _check_filters(parser, args):
 MAX_LOAD_BASES = 3_500_000_000   # one device load holds < 2^32 layout positions (records + gaps); larger files go in groups
 
 
-def _whole_fasta_to_bed(records, args, bed_path):
+def _whole_fasta_to_bed(fa, args, bed_path):
     """Every record of the file: as few loads as the 2^32-position limit allows (one for a human genome), one scan
-    per load, native row writer.  Returns the row count per record."""
+    per load, native row writer.  The groups are slices of the reader's buffer (no copies on the Python side).
+    Returns the row count per record."""
     ctx = api.get_context()
-    counts = np.zeros(len(records), dtype=np.int64)
+    lengths = np.diff(fa.offsets.astype(np.int64))
+    counts = np.zeros(fa.n_records, dtype=np.int64)
     open(bed_path, "wb").close()
     first = 0
-    while first < len(records):
+    while first < fa.n_records:
         last, total = first, 0
-        while last < len(records) and (last == first or total + len(records[last].seq) <= MAX_LOAD_BASES):
-            total += len(records[last].seq)
+        while last < fa.n_records and (last == first or total + int(lengths[last]) <= MAX_LOAD_BASES):
+            total += int(lengths[last])
             last += 1
-        group = records[first:last]
-        lengths = np.array([len(r.seq) for r in group], dtype=np.uint64)
-        offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
-        blob = b"".join(r.seq for r in group)
-        if len(blob):
+        base0 = int(fa.offsets[first])
+        blob = fa.bases[base0:base0 + total]
+        offsets = fa.offsets[first:last + 1] - np.uint64(base0)
+        if total:
             with ctx.load(blob, offsets, max_motif_cap=args.max_motif_size) as seq:
                 n = seq.scan(args.min_motif_size, args.max_motif_size, args.min_repeats, args.min_span)
                 rec, start, end, k = seq.fetch(n)
-            _cabi.write_rows(bed_path, [r.name for r in group], blob, offsets, rec, start, end, k, append=True)
+            _cabi.write_rows(bed_path, fa.names[first:last], blob, offsets, rec, start, end, k, append=True)
             np.add.at(counts, rec.astype(np.int64) + first, 1)
         first = last
     return counts
@@ -97,28 +98,28 @@ def _run_fasta(parser, args):
     if not args.output_prefix:
         args.output_prefix = re.sub(".fa(sta)?(.gz)?", "", args.input_sequence)   # the (unanchored) regex of prf:114
     bed_path = f"{os.path.basename(args.output_prefix)}.bed"                       # always in the working directory
-    records = fasta.read_fasta(args.input_sequence)
-
-    if args.interval:
-        fields = re.split("[:-]", args.interval)
-        if len(fields) != 3:
-            parser.error("Invalid --interval format. Must be chrom:start_0based-end")
-        args.interval_chrom = fields[0]
-        args.interval_start_0based, args.interval_end = int(fields[1]), int(fields[2])
-        chosen = next((r for r in records if r.name == args.interval_chrom), None)
-        if chosen is None:
-            parser.error(f"Chromosome {args.interval_chrom} not found in the input FASTA file")
-        args.interval_end = min(args.interval_end, len(chosen.seq))               # prf:139-140
-        print(f"Processing {chosen.name} ({args.interval_end - args.interval_start_0based:,d} bp)")
-        rows = api.detect_repeats(chosen.seq, args)
-        print(f"Found {len(rows):,d} repeats")
-        with open(bed_path, "wt") as bed_file:
-            bed_file.write("".join(f"{chosen.name}\t{s}\t{e}\t{m}\n" for s, e, m in rows))
-    else:
-        counts = _whole_fasta_to_bed(records, args, bed_path)
-        for record, n_found in zip(records, counts.tolist()):
-            print(f"Processing {record.name} ({len(record.seq):,d} bp)")
-            print(f"Found {n_found:,d} repeats")
+    with fasta.open_fasta(args.input_sequence, pinned=True) as fa:
+        if args.interval:
+            fields = re.split("[:-]", args.interval)
+            if len(fields) != 3:
+                parser.error("Invalid --interval format. Must be chrom:start_0based-end")
+            args.interval_chrom = fields[0]
+            args.interval_start_0based, args.interval_end = int(fields[1]), int(fields[2])
+            if args.interval_chrom not in fa.names:
+                parser.error(f"Chromosome {args.interval_chrom} not found in the input FASTA file")
+            chosen = fa.record(fa.names.index(args.interval_chrom))
+            args.interval_end = min(args.interval_end, len(chosen))                    # prf:139-140
+            print(f"Processing {args.interval_chrom} ({args.interval_end - args.interval_start_0based:,d} bp)")
+            rows = api.detect_repeats(chosen.tobytes(), args)
+            print(f"Found {len(rows):,d} repeats")
+            with open(bed_path, "wt") as bed_file:
+                bed_file.write("".join(f"{args.interval_chrom}\t{s}\t{e}\t{m}\n" for s, e, m in rows))
+        else:
+            counts = _whole_fasta_to_bed(fa, args, bed_path)
+            lengths = np.diff(fa.offsets.astype(np.int64))
+            for name, length, n_found in zip(fa.names, lengths.tolist(), counts.tolist()):
+                print(f"Processing {name} ({length:,d} bp)")
+                print(f"Found {n_found:,d} repeats")
     print(f"Wrote results to {bed_path}")
 
 

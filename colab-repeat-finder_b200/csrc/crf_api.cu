@@ -855,3 +855,5 @@ extern "C" int crf_write_rows(const char *path, int append, int tsv, const char 
     if (!ok) { set_err("crf_write_rows: write to %s failed", path); return CRF_ERR_ARG; }
     return CRF_OK;
 }
+
+#include "crf_fasta.h"

@@ -153,6 +153,20 @@ int crf_write_rows(const char *path, int append, int tsv, const char *names, con
                    const uint64_t *offsets, const uint32_t *record, const uint32_t *start, const uint32_t *end,
                    const uint32_t *motif_size, uint64_t n_rows, uint64_t *bytes);
 
+/* ---- input (host only, no GPU) ---------------------------------------------------------------
+ * Native FASTA ingest, replacing what the reference takes from pyfastx (prf:117-137: the records in file
+ * order, .name = first whitespace-delimited header token, .seq = the lines joined, case preserved).  Plain or
+ * gzip (concatenated members / bgzip too).  The result is laid out as crf_seq_load_ascii and crf_write_rows
+ * take it: all records back to back, n_records+1 offsets, NUL-separated names.  n_threads = 0: up to 16.
+ * pinned != 0: page-locked buffer (cudaHostAlloc) when a device is present, for a faster upload.
+ * The pointers of crf_fasta_data stay valid until crf_fasta_close. */
+typedef struct crf_fasta crf_fasta;
+int crf_fasta_open(const char *path, uint32_t n_threads, int pinned, crf_fasta **fasta);
+int crf_fasta_info(const crf_fasta *fasta, uint64_t *n_records, uint64_t *total_bases, int *pinned);
+int crf_fasta_data(const crf_fasta *fasta, const uint8_t **bases, const uint64_t **offsets, const char **names,
+                   uint64_t *names_bytes);
+int crf_fasta_close(crf_fasta *fasta);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,66 @@ def test_fasta_reader_plain_and_gzip(tmp_path):
     assert [(r.name, r.seq) for r in fasta.read_fasta(str(gz))] == want
 
 
+def _simple_fasta(raw):
+    """Checker: the obvious line-by-line reading of FASTA text (bytes) -> [(name, seq)]."""
+    out = []
+    for line in raw.split(b"\n"):
+        if line.startswith(b">"):
+            fields = line[1:].split()
+            out.append([fields[0].decode() if fields else "", []])
+        elif out:
+            out[-1][1].append(line.replace(b"\r", b""))
+    return [(n, b"".join(parts)) for n, parts in out]
+
+
+@pytest.mark.parametrize("eol", [b"\n", b"\r\n"])
+def test_fasta_reader_large_multi_piece(tmp_path, eol):
+    """Records larger than one 8 MiB reader piece, ragged line widths, several threads, multi-member gzip."""
+    from crf_b200 import _cabi
+    rng = np.random.default_rng(5)
+    chunks = []
+    for r, size in enumerate([0, 1, 59, 60, 61, 20_000_000, 3, 9_000_000]):
+        seq = rng.choice(np.frombuffer(b"ACGTacgtNn", dtype=np.uint8), size=size).tobytes()
+        width = [60, 61, 1, 70, 80, 60, 7, 10_000_000][r]
+        chunks.append(b">rec%d description %d" % (r, r) + eol)
+        chunks.extend(seq[i:i + width] + eol for i in range(0, size, width))
+    raw = b"".join(chunks)[:-len(eol)]                  # no line end after the last line
+    want = _simple_fasta(raw)
+    assert sum(len(s) for _, s in want) == 29_000_184
+    plain = tmp_path / "big.fa"
+    plain.write_bytes(raw)
+    cut = len(raw) // 3
+    gz = tmp_path / "big.fa.gz"
+    gz.write_bytes(gzip.compress(raw[:cut], 1) + gzip.compress(raw[cut:], 1))      # two members, like bgzip
+    for path in (plain, gz):
+        for threads in (1, 5):
+            with _cabi.Fasta(str(path), n_threads=threads) as fa:
+                assert fa.names == [n for n, _ in want]
+                assert fa.total_bases == int(fa.offsets[-1]) == len(fa.bases)
+                for i, (_, seq) in enumerate(want):
+                    assert fa.record(i).tobytes() == seq, (path, threads, i)
+
+
+def test_fasta_reader_edge_cases(tmp_path):
+    from crf_b200 import _cabi
+    cases = {
+        "empty.fa": (b"", []),
+        "nohdr.fa": (b"ACGT\nACGT\n", []),
+        "hdronly.fa": (b">x", [("x", b"")]),
+        "leading.fa": (b"junk\n>  a b\nAC>GT\n>\nTT\n", [("a", b"AC>GT"), ("", b"TT")]),
+    }
+    for name, (raw, want) in cases.items():
+        (tmp_path / name).write_bytes(raw)
+        with _cabi.Fasta(str(tmp_path / name)) as fa:
+            assert [(n, fa.record(i).tobytes()) for i, n in enumerate(fa.names)] == want, name
+    with pytest.raises(ValueError):
+        _cabi.Fasta(str(tmp_path / "missing.fa"))
+    bad = tmp_path / "bad.fa.gz"
+    bad.write_bytes(gzip.compress(b">a\nACGT\n" * 1000)[:-20])
+    with pytest.raises(ValueError):
+        _cabi.Fasta(str(bad))
+
+
 @pytest.mark.parametrize("argv", [
     ["--min-motif-size", "0", "ACGT"],
     ["--min-motif-size", "5", "--max-motif-size", "4", "ACGT"],
