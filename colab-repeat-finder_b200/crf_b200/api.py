@@ -132,6 +132,79 @@ def _interval_stop_position(ctx, s, end_position, kmin, kmax, knobs):
         window *= 4
 
 
+def _is_primitive(motif):
+    """not consists_of_perfect_repeats(motif) (trk:108-142): no proper divisor of len(motif) is a period."""
+    n = len(motif)
+    return not any(n % d == 0 and motif == motif[:d] * (n // d) for d in range(1, n // 2 + 1))
+
+
+def _position0_candidates(s, kmin, kmax, min_span, stop):
+    """min_repeats == 1: what the trackers emit for the run that starts at position 0 when it has fewer than k-1
+    matches -- the one place where trk:87 (`seq[i+1] == seq[i+1-period]`) reads negative indices, i.e. the END of
+    the sequence.  At most one candidate per motif size, each a walk of < 2k symbol compares; everything else
+    the reference reports comes from the GPU scan (a run with st > 0 and r < k-1 can never pass trk:91, see
+    DESIGN.md section 6).  Yields (end, motif_length); raises IndexError where trk:87 does."""
+    L = len(s)
+    N = ord("N")
+    for k in range(kmin, kmax + 1):
+        reach = max(L - k, 0)                            # where tracker k stands when the loop ends (trk:50) ...
+        if stop is not None:
+            reach = min(reach, stop + 1)                 # ... or where the early break left it (prf:73-74)
+        r = 0
+        while r < min(reach, k - 1) and s[r] == s[r + k] and s[r] != N:
+            r += 1
+        if r >= k - 1:
+            continue                                     # an ordinary run: reported by the scan
+        motif = s[0:k]
+        if N in motif:                                   # trk:83
+            continue
+        run, i = r + 1, r
+        if run + k - 1 >= min_span:                      # trk:86 (min_repeats * period == k always holds)
+            while i < L - 1:
+                j = i + 1 - k
+                if j < -L:
+                    raise IndexError("string index out of range")
+                if s[i + 1] != s[j]:
+                    break
+                i += 1
+                run += 1
+        if run >= min_span and run >= k and _is_primitive(motif):      # trk:91,98
+            yield i + 1, len(motif)
+
+
+def _detect_single_copy(input_sequence, raw, filter_settings, kmin, kmax, min_span, ctx, device, knobs):
+    """detect_repeats for min_repeats == 1 (derivation in DESIGN.md section 6)."""
+    if kmin == 1 and min_span <= 1:
+        raise NotImplementedError(
+            "min_repeats == 1 with min_motif_size == 1 and min_span == 1 reports every single base as a repeat "
+            "(perfect_repeat_tracker.py:86-91); this degenerate setting is not implemented on the GPU path")
+    n = len(raw)
+    a = int(getattr(filter_settings, "interval_start_0based", 0))
+    b = int(getattr(filter_settings, "interval_end", n))
+    if a < 0 or b < 0:
+        raise NotImplementedError("negative interval coordinates are not supported")
+    a, b, ltrunc = _n_trim(raw, a, b)                    # the wrap-around reads the trimmed string's end: trim for real
+    s = raw[a:ltrunc].upper()                            # the symbol compares below are on the upper-cased string (prf:33)
+    L = len(s)
+    stop = _interval_stop_position(ctx, s, b - a, kmin, kmax, knobs)
+    if stop is not None and b == L and stop + 1 < L - kmin:
+        raise AssertionError(f"{kmin}bp motif RepeatTracker did not reach end of the sequence")      # prf:77-78
+    rows = {}
+    if L:
+        start, end, k = scan_arrays(s, kmin, kmax, 1, min_span, device=device, **knobs)
+        start, end, k = start.astype(np.int64), end.astype(np.int64), k.astype(np.int64)
+        if stop is not None:
+            # processed mismatch positions, plus what done() (prf:79) makes of a tracker the break left with exactly
+            # k-1 matches behind it: its pre-filter (trk:86) sees 2k-1 bases, then trk:87 follows the run to its end
+            keep = (end - k <= stop) | ((start == stop + 2 - k) & (2 * k - 1 >= min_span))
+            start, end, k = start[keep], end[keep], k[keep]
+        rows = {(s0, e0): k0 for s0, e0, k0 in zip(start.tolist(), end.tolist(), k.tolist())}
+    for e0, k0 in _position0_candidates(s, kmin, kmax, min_span, stop):
+        if k0 < rows.get((0, e0), k0 + 1):               # same interval: the shorter motif stays (trk:94-96)
+            rows[(0, e0)] = k0
+    return [(s0 + a, e0 + a, _upper_slice(input_sequence, s0 + a, k0)) for (s0, e0), k0 in sorted(rows.items())]
+
+
 def detect_repeats(input_sequence, filter_settings, verbose=False, show_progress_bar=False, debug=False,
                    device=None, **knobs):
     """Detect perfect tandem repeats.  Drop-in for the reference's detect_repeats (prf:10-81).
@@ -141,12 +214,11 @@ def detect_repeats(input_sequence, filter_settings, verbose=False, show_progress
     validate_filter_settings(filter_settings)
     kmin, kmax = int(filter_settings.min_motif_size), int(filter_settings.max_motif_size)
     min_repeats, min_span = int(filter_settings.min_repeats), int(filter_settings.min_span)
-    if min_repeats == 1:
-        raise NotImplementedError(
-            "min_repeats == 1 (the reference's wrap-around quirk path, perfect_repeat_tracker.py:86-91) is not "
-            "implemented on the GPU path")
     raw = _encode(input_sequence)
     n = len(raw)
+    if min_repeats == 1:
+        return _detect_single_copy(input_sequence, raw, filter_settings, kmin, kmax, min_span, get_context(device),
+                                   device, knobs)
     has_interval = hasattr(filter_settings, "interval_start_0based") or hasattr(filter_settings, "interval_end")
     ctx = get_context(device)
 

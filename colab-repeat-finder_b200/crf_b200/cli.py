@@ -114,6 +114,14 @@ def _run_fasta(parser, args):
             print(f"Found {len(rows):,d} repeats")
             with open(bed_path, "wt") as bed_file:
                 bed_file.write("".join(f"{args.interval_chrom}\t{s}\t{e}\t{m}\n" for s, e, m in rows))
+        elif args.min_repeats == 1:
+            # the reference's single-copy quirks are per record (wrap-around at each record's position 0): one call each
+            with open(bed_path, "wt") as bed_file:
+                for i, name in enumerate(fa.names):
+                    print(f"Processing {name} ({len(fa.record(i)):,d} bp)")
+                    rows = api.detect_repeats(fa.record(i).tobytes(), args)
+                    print(f"Found {len(rows):,d} repeats")
+                    bed_file.write("".join(f"{name}\t{s}\t{e}\t{m}\n" for s, e, m in rows))
         else:
             counts = _whole_fasta_to_bed(fa, args, bed_path)
             lengths = np.diff(fa.offsets.astype(np.int64))

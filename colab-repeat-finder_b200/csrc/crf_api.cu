@@ -471,7 +471,8 @@ static void build_ktab(const crf_scan_params &pr, bool allow_sup, std::vector<KE
         KEntry &e = tab[k];
         // r_min: trk:86 and trk:91 in closed form
         const uint64_t a = pr.min_span > k ? (uint64_t)pr.min_span - k : 0;
-        const uint64_t b = (uint64_t)(pr.min_repeats - 1) * k;
+        // min_repeats == 1: a shorter run cannot fill its own motif (Appendix A.4 reduces to r >= k-1 away from position 0)
+        const uint64_t b = pr.min_repeats > 1 ? (uint64_t)(pr.min_repeats - 1) * k : k - 1;
         const uint64_t rmin = std::max<uint64_t>(std::max(a, b), 1);
         e.rmin = (uint32_t)std::min<uint64_t>(rmin, 0xFFFFFF00u);
         e.re = (uint8_t)std::min<uint32_t>(e.rmin, 32);
@@ -559,8 +560,9 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
     if (pr->max_motif_size < pr->min_motif_size) { set_err("max_motif_size is set to %u. It must be at least min_motif_size.", pr->max_motif_size); return CRF_ERR_ARG; }
     if (pr->min_repeats < 1) { set_err("min_repeats is set to %u. It must be at least 1.", pr->min_repeats); return CRF_ERR_ARG; }
     if (pr->min_span < 1) { set_err("min_span is set to %u. It must be at least 1.", pr->min_span); return CRF_ERR_ARG; }
-    if (pr->min_repeats == 1) {
-        set_err("min_repeats == 1 (the reference's wrap-around quirk path, perfect_repeat_tracker.py:86-91) is not implemented on the GPU path");
+    if (pr->min_repeats == 1 && pr->min_motif_size == 1 && pr->min_span <= 1) {
+        set_err("min_repeats == 1 with min_motif_size == 1 and min_span == 1 reports every single base as a repeat "
+                "(perfect_repeat_tracker.py:86-91); this degenerate setting is not implemented on the GPU path");
         return CRF_ERR_UNSUPPORTED;
     }
     if (pr->max_motif_size > s->cap) {
@@ -589,7 +591,8 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         std::vector<KEntry> tab;
         std::vector<Seg> segs;
         // the suppression relies on the primitivity rule dropping what it hides: not with CRF_SCAN_NO_PRIMITIVITY
-        build_ktab(*pr, s->n_exotic == 0 && !(pr->flags & (CRF_SCAN_DEBUG_NO_SUP | CRF_SCAN_NO_PRIMITIVITY)), tab, segs);
+        build_ktab(*pr, s->n_exotic == 0 && pr->min_repeats > 1 && !(pr->flags & (CRF_SCAN_DEBUG_NO_SUP | CRF_SCAN_NO_PRIMITIVITY)),
+                   tab, segs);
         s->sup_enabled = 0;
         for (const Seg &g : segs) s->sup_enabled |= (g.mode >> 4) ? 1u : 0u;
         if (s->segs_cap < segs.size()) {
@@ -635,6 +638,7 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         sp.walk_limit = pr->walk_limit_words ? pr->walk_limit_words : 64;
         sp.debug_flags = (pr->flags >> 16) & 0xFFFFu;
         sp.sup_enabled = s->sup_enabled;
+        sp.single_copy = pr->min_repeats == 1;
         sp.stage_key = s->stage_key; sp.stage_k = s->stage_k; sp.stage_cap = s->res_cap;
         sp.tile_cnt = s->tile_cnt; sp.tile_base = s->tile_base;
         sp.spill_key = s->spill_key; sp.spill_k = s->spill_k; sp.spill_cap = s->res_cap;

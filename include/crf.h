@@ -87,7 +87,12 @@ int crf_seq_info(const crf_seq *seq, crf_seq_info_t *info);
  * [min_motif_size, max_motif_size], filters min_repeats / min_span (trk:86,91), primitivity
  * (trk:98, 108-142), ordering by (record, start, end) (prf:81).  Results stay in HBM until
  * fetched.  The argument checks and messages of prf:23-30 map to CRF_ERR_ARG.
- * min_repeats == 1 (the reference's wrap-around quirk, trk:86-91) is CRF_ERR_UNSUPPORTED.
+ * min_repeats == 1 (trk:86-91 then lets a mismatch position with fewer than k-1 matches before it emit only
+ * through Python's negative-index wrap-around at position 0): the scan returns every maximal run of at least
+ * max(min_span - k, k - 1) matches whose motif is N-free and primitive -- all the reference reports except the
+ * (at most one per motif size) wrap-around candidates of position 0 and the early-break selection of interval
+ * mode, which the caller adds from the sequence ends (crf_b200/api.py, O(max_motif_size^2) symbol compares).
+ * min_repeats == 1 with min_motif_size == 1 and min_span == 1 (every base is a "repeat") is CRF_ERR_UNSUPPORTED.
  */
 /* keep runs whose motif is not primitive too (used to find where the reference's interval-mode
  * loop stops, prf:70-74: is_in_middle_of_repeat() does not look at the motif) */

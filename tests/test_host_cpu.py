@@ -135,3 +135,64 @@ def test_native_row_writer_bed_and_tsv(tmp_path):
     _cabi.write_rows(str(bed), ["a"], b"ACGT" * 2000, [0, 8000], [0] * k, list(range(k)), list(range(1, k + 1)), [1] * k)
     lines = bed.read_text().splitlines()
     assert len(lines) == k and lines[-1].startswith("a\t4999\t5000\t")
+
+
+# ---- min_repeats == 1: the host half (position-0 wrap-around, early-break selection) with the GPU scan replaced by
+# ---- a numpy statement of what crf_scan documents for that setting
+
+def _runs_single_copy(s, kmin, kmax, min_span):
+    """include/crf.h, crf_scan with min_repeats == 1: maximal runs of >= max(min_span-k, k-1) matches, motif N-free
+    and primitive."""
+    from crf_b200 import api
+    L, arr = len(s), np.frombuffer(s, dtype=np.uint8)
+    rows = []
+    for k in range(kmin, min(kmax, L - 1) + 1):
+        m = (arr[:L - k] == arr[k:]) & (arr[:L - k] != ord("N"))
+        edge = np.diff(np.concatenate([[0], m.astype(np.int8), [0]]))
+        for st, i0 in zip(np.flatnonzero(edge == 1).tolist(), np.flatnonzero(edge == -1).tolist()):
+            if i0 - st >= max(min_span - k, k - 1, 1) and s[st + k - 1] != ord("N") and api._is_primitive(s[st:st + k]):
+                rows.append((st, i0 + k, k))
+    rows.sort()
+    cols = np.array(rows, dtype=np.uint32).reshape(-1, 3)
+    return cols[:, 0], cols[:, 1], cols[:, 2]
+
+
+def _stop_literal(s, end_position, kmin, kmax):
+    """prf:66-74 word for word, trackers reduced to their run length."""
+    L = len(s)
+    run = {k: 1 for k in range(kmin, kmax + 1)}
+    for t in range(L):
+        for k in run:
+            if t < L - k:
+                run[k] = run[k] + 1 if (s[t] == s[t + k] and s[t] != ord("N")) else 1
+        if t > end_position and not any(v >= k + 1 for k, v in run.items()):
+            return t
+    return None
+
+
+def test_single_copy_host_logic_against_reference_vectors(monkeypatch):
+    from crf_b200 import api
+    from tests.helpers import load_golden, ns
+    monkeypatch.setattr(api, "get_context", lambda device=None: None)
+    monkeypatch.setattr(api, "scan_arrays",
+                        lambda s, kmin, kmax, mr, span, device=None, **kw: _runs_single_copy(bytes(s), kmin, kmax, span))
+    monkeypatch.setattr(api, "_interval_stop_position",
+                        lambda ctx, s, e, kmin, kmax, knobs: _stop_literal(bytes(s), e, kmin, kmax))
+    checked = refused = raising = 0
+    for case in load_golden("fuzz_minrep1.json"):
+        fs = ns(**case["settings"])
+        if fs.min_motif_size == 1 and fs.min_span <= 1:
+            with pytest.raises(NotImplementedError):
+                api.detect_repeats(case["seq"], fs)
+            refused += 1
+            continue
+        try:
+            got, exc = api.detect_repeats(case["seq"], fs), None
+        except (AssertionError, IndexError) as e:
+            got, exc = None, type(e).__name__
+        assert exc == case.get("raises"), case["settings"]
+        if exc is None:
+            assert got == [tuple(r) for r in case["result"]], case["settings"]
+        raising += exc is not None
+        checked += 1
+    assert checked >= 280 and raising >= 10 and refused <= 15
