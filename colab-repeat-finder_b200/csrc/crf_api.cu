@@ -638,7 +638,6 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         sp.walk_limit = pr->walk_limit_words ? pr->walk_limit_words : 64;
         sp.debug_flags = (pr->flags >> 16) & 0xFFFFu;
         sp.sup_enabled = s->sup_enabled;
-        sp.single_copy = pr->min_repeats == 1;
         sp.stage_key = s->stage_key; sp.stage_k = s->stage_k; sp.stage_cap = s->res_cap;
         sp.tile_cnt = s->tile_cnt; sp.tile_base = s->tile_base;
         sp.spill_key = s->spill_key; sp.spill_k = s->spill_k; sp.spill_cap = s->res_cap;
@@ -665,6 +664,12 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         g.counters = s->d_counters;
         const uint32_t ggrid = (n_tiles * 32 + 255) / 256;
         gather_kernel<<<ggrid, 256, 0, st>>>(g);
+        const bool single_copy = pr->min_repeats == 1;    // see single_copy_filter_kernel
+        if (single_copy) {
+            single_copy_filter_kernel<<<1, 1024, 0, st>>>(s->fin_key, s->fin_k, s->NM, s->X, s->n_words_alloc, s->res_cap,
+                                                          s->d_counters);
+            ++launches;
+        }
         const uint32_t tgrid = std::min<uint32_t>(148 * 8, (s->res_cap + 255) / 256);
         TranslateParams tp;
         tp.fin_key = s->fin_key; tp.fin_k = s->fin_k; tp.rec_dev_off = s->d_rec_dev_off; tp.rec_len = s->d_rec_len;
@@ -691,6 +696,11 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
             CHECK(bitonic_sort(st, s->spill_key, s->spill_k, (uint32_t)n_spill, &launches));
             g.spill_sorted = 1;
             gather_kernel<<<ggrid, 256, 0, st>>>(g);
+            if (single_copy) {
+                single_copy_filter_kernel<<<1, 1024, 0, st>>>(s->fin_key, s->fin_k, s->NM, s->X, s->n_words_alloc,
+                                                              s->res_cap, s->d_counters);
+                ++launches;
+            }
             CU(cudaMemsetAsync(s->d_counters + C_OPEN, 0, sizeof(unsigned long long), st));
             translate_kernel<<<tgrid, 256, 0, st>>>(tp);
             CU(cudaGetLastError());
@@ -702,11 +712,12 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         float ms_all = 0, ms_k = 0;
         CU(cudaEventElapsedTime(&ms_all, s->ev[0], s->ev[3]));
         CU(cudaEventElapsedTime(&ms_k, s->ev[1], s->ev[2]));
-        s->n_results = n_total;
+        const unsigned long long n_kept = single_copy ? s->h_counters[C_TOTAL] : n_total;
+        s->n_results = n_kept;
         s->have_results = true;
         s->stats.scan_ms = ms_all;
         s->stats.kernel_ms = ms_k;
-        s->stats.n_results = n_total;
+        s->stats.n_results = n_kept;
         s->stats.n_tiles = n_tiles;
         s->stats.n_spilled = n_spill;
         s->stats.n_long = s->h_counters[C_LONG];

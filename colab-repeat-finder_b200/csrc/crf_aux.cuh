@@ -271,6 +271,53 @@ __global__ void __launch_bounds__(256) translate_kernel(const TranslateParams t)
     }
 }
 
+// ---- min_repeats == 1 only: r_min may be k-1, and a run of exactly k-1 matches leaves the motif's last base
+// S[st+k-1] (the mismatch position itself) untested; an 'N' there drops the row (trk:83).  The scan kernel never
+// sees this case in ordinary scans (r_min >= k), so it is settled here, on the sorted list, by one block that
+// compacts in place chunk by chunk (a row only ever moves to a lower index).  Rare mode, not tuned. ---------------
+__global__ void __launch_bounds__(1024) single_copy_filter_kernel(uint64_t *key, uint16_t *kk, const uint32_t *NM,
+                                                                  const uint32_t *X, uint32_t n_words, uint32_t fin_cap,
+                                                                  unsigned long long *counters) {
+    __shared__ uint32_t warp_total[32];
+    const unsigned long long n64 = counters[C_STAGE] + counters[C_SPILL];
+    if (counters[C_STAGE] > fin_cap || counters[C_SPILL] > fin_cap || n64 > fin_cap) return;   // host re-runs
+    const uint32_t n = (uint32_t)n64, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t out = 0;
+    for (uint32_t chunk = 0; chunk < n; chunk += 1024) {
+        const uint32_t i = chunk + threadIdx.x;
+        uint64_t key_i = 0;
+        uint16_t k_i = 0;
+        bool keep = false;
+        if (i < n) {
+            key_i = key[i];
+            k_i = kk[i];
+            const uint32_t st = (uint32_t)(key_i >> 32), en = (uint32_t)key_i;
+            keep = true;
+            if (en - st == 2u * k_i - 1u) {
+                const uint32_t q = st + k_i - 1u, w = q >> 5;
+                if (w < n_words && (((NM[w] & ~X[w]) >> (q & 31)) & 1u)) keep = false;
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) warp_total[warp] = __popc(bal);
+        __syncthreads();                                  // every row of the chunk is in registers now
+        uint32_t before = 0, total = 0;
+        for (uint32_t w = 0; w < 32; ++w) {
+            const uint32_t c = warp_total[w];
+            before += w < warp ? c : 0u;
+            total += c;
+        }
+        if (keep) {
+            const uint32_t pos = out + before + __popc(bal & ((1u << lane) - 1u));
+            key[pos] = key_i;
+            kk[pos] = k_i;
+        }
+        out += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counters[C_TOTAL] = out;
+}
+
 // ---- fallback ordering: global bitonic network on (key, k); n_pow2 elements, tail padded with
 // all-ones keys.  Only used when a tile overflowed its sorted-output slots, and for the (tiny)
 // list of exotic symbols. -------------------------------------------------------------------

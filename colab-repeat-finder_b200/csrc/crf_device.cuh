@@ -67,7 +67,6 @@ struct ScanParams {
     uint32_t walk_limit;     // words one thread walks before the block takes over
     uint32_t sup_enabled;    // some segment carries a homopolymer-suppression level
     uint32_t debug_flags;    // bit 0: skip the exact phase (profiling only, results are then empty)
-    uint32_t single_copy;    // min_repeats == 1: r_min may be k-1, so the motif's last base needs its own N test
     uint64_t *stage_key;     // (start << 32 | end), tile-sorted segments
     uint16_t *stage_k;
     uint32_t stage_cap;

@@ -119,10 +119,6 @@ __device__ inline void handle_start(const ScanParams &p, const TileCtx &t, const
     bool found = tile_walk(p, t, k, st + known, p.walk_limit, &i0);
     while (!found && i0 - st < ke.rmin) found = tile_walk(p, t, k, i0, p.walk_limit, &i0);
     if (found && i0 - st < ke.rmin) return;                       // trk:86/91 thresholds
-    if (p.single_copy) {  // a run of exactly k-1 matches leaves the motif's last base untested: 'N' there drops it (trk:83)
-        const uint32_t q = st + k - 1;
-        if ((__ldg(p.NM + (q >> 5)) & ~__ldg(p.X + (q >> 5))) >> (q & 31) & 1u) return;
-    }
 #pragma unroll 1
     for (int j = 0; j < 6; ++j) {                                 // primitivity, trk:98,108-142
         const uint32_t d = ke.div[j];
