@@ -51,6 +51,8 @@ struct crf_ctx {
     int device;
     cudaStream_t own_stream;
     cudaStream_t stream;
+    cudaStream_t copy_stream = nullptr;                 // host -> device chunks of a pipelined upload (load_impl)
+    cudaEvent_t copy_done = nullptr;
     std::vector<std::pair<void *, size_t>> cache;       // free blocks
     std::unordered_map<void *, size_t> live;            // blocks handed out -> size
     size_t cached_bytes = 0;
@@ -169,6 +171,8 @@ extern "C" int crf_ctx_create(int device, crf_ctx **out) {
     if (!c) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
     c->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete c; set_err("cudaStreamCreate failed: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
     c->stream = c->own_stream;
     *out = c;
@@ -182,6 +186,8 @@ extern "C" int crf_ctx_destroy(crf_ctx *c) {
     for (auto &b : c->cache) cudaFree(b.first);
     if (g_ctx == c) g_ctx = nullptr;
     cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->copy_done);
     delete c;
     return CRF_OK;
 }
@@ -292,9 +298,14 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     uint64_t src_base = 0;
     uint8_t *d_src_own = nullptr;
     uint64_t *d_src_start = nullptr;
-    if (!on_device) {               // one H2D copy of the span the records cover (units may overlap)
-        CHECK(dev_alloc(&d_src_own, (size_t)(src_hi - src_lo)));
-        if (src_hi > src_lo) CU(cudaMemcpyAsync(d_src_own, bases + src_lo, src_hi - src_lo, cudaMemcpyHostToDevice, st));
+    // A long host buffer goes up in chunks on a second stream while the pack kernel works on the layout words whose
+    // bytes have already arrived (the PCIe copy is ~10x longer than the packing, which then hides behind it).
+    const uint64_t UPLOAD_CHUNK = 64ull << 20;
+    const uint64_t src_bytes = src_hi - src_lo;
+    const bool pipelined = !on_device && src_bytes > 2 * UPLOAD_CHUNK;
+    if (!on_device) {               // the span the records cover (units may overlap)
+        CHECK(dev_alloc(&d_src_own, (size_t)src_bytes));
+        if (src_bytes && !pipelined) CU(cudaMemcpyAsync(d_src_own, bases + src_lo, src_bytes, cudaMemcpyHostToDevice, st));
         d_src = d_src_own;
         src_base = src_lo;
     }
@@ -339,10 +350,47 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
         PackParams pp;
         pp.src = d_src; pp.rec_src_start = d_src_start; pp.rec_len = s->d_rec_len; pp.rec_dev_off = s->d_rec_dev_off;
         pp.n_records = n_records;
-        pp.n_words_alloc = s->n_words_alloc; pp.H = s->H; pp.L = s->L; pp.NM = s->NM; pp.X = s->X;
+        pp.H = s->H; pp.L = s->L; pp.NM = s->NM; pp.X = s->X;
         pp.ex_key = s->ex_key; pp.ex_cap = s->ex_cap; pp.ex_count = s->d_counters;
-        pack_kernel<<<(s->n_words_alloc + 255) / 256, 256, 0, st>>>(pp);
-        e = cudaGetLastError();
+        if (!pipelined) {
+            pp.w_lo = 0; pp.w_hi = s->n_words_alloc;
+            pack_kernel<<<(s->n_words_alloc + 255) / 256, 256, 0, st>>>(pp);
+            e = cudaGetLastError();
+        } else {
+            // src_end[r]: running maximum of where records 0..r end in the source, so "the first record whose bytes
+            // are not all there" bounds the layout words that can be packed, whatever order the records come in
+            std::vector<uint64_t> src_end(n_records);
+            uint64_t run = 0;
+            for (uint32_t r = 0; r < n_records; ++r) {
+                if (s->h_rec_len[r]) run = std::max(run, rel[r] + s->h_rec_len[r]);
+                src_end[r] = run;
+            }
+            e = cudaEventRecord(c->copy_done, st);                       // the copies start after what is queued on st
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0);
+            uint32_t w_done = 0;
+            for (uint64_t b = 0; b < src_bytes && e == cudaSuccess; b += UPLOAD_CHUNK) {
+                const uint64_t nb = std::min(UPLOAD_CHUNK, src_bytes - b), avail = b + nb;
+                e = cudaMemcpyAsync(d_src_own + b, bases + src_lo + b, nb, cudaMemcpyHostToDevice, c->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(c->copy_done, c->copy_stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->copy_done, 0);
+                if (e != cudaSuccess) break;
+                uint32_t w_hi = s->n_words_alloc;
+                if (avail < src_bytes) {
+                    const uint32_t r = (uint32_t)(std::upper_bound(src_end.begin(), src_end.end(), avail) - src_end.begin());
+                    if (r < n_records) {
+                        const uint64_t have = avail > rel[r] ? std::min<uint64_t>(avail - rel[r], s->h_rec_len[r]) : 0;
+                        w_hi = (uint32_t)((s->h_rec_dev_off[r] + have) >> 5);
+                    }
+                }
+                if (w_hi > w_done) {
+                    pp.w_lo = w_done; pp.w_hi = w_hi;
+                    pack_kernel<<<(w_hi - w_done + 255) / 256, 256, 0, st>>>(pp);
+                    e = cudaGetLastError();
+                    w_done = w_hi;
+                }
+            }
+            if (e != cudaSuccess) cudaStreamSynchronize(c->copy_stream);   // nothing may still write the buffer freed below
+        }
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // also keeps rel/len32/olo alive long enough
     }

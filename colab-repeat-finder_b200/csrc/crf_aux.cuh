@@ -12,7 +12,7 @@ struct PackParams {
     const uint32_t *rec_len;
     const uint32_t *rec_dev_off;  // n_records (layout position of each record's first base)
     uint32_t n_records;
-    uint32_t n_words_alloc;
+    uint32_t w_lo, w_hi;          // layout words this launch packs (the upload is pipelined chunk by chunk)
     uint32_t *H, *L, *NM, *X;
     uint64_t *ex_key;
     uint32_t ex_cap;
@@ -20,8 +20,8 @@ struct PackParams {
 };
 
 __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= p.n_words_alloc) return;
+    const uint32_t w = p.w_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= p.w_hi) return;
     const uint32_t p0 = w << 5;
     // record containing (or preceding) p0: last r with rec_dev_off[r] <= p0
     uint32_t lo = 0, hi = p.n_records ? p.n_records - 1 : 0;

@@ -208,8 +208,8 @@ __device__ inline void exact_item(const ScanParams &p, const TileCtx &t, uint32_
     }
     if (st0 != NOPOS) {
         const KEntry ke = p.ktab[k];
-        handle_start(p, t, ke, k, st0, re);
-        if (st1 != NOPOS) handle_start(p, t, ke, k, st1, re);
+#pragma unroll 1
+        for (uint32_t st = st0; st != NOPOS; st = st1, st1 = NOPOS) handle_start(p, t, ke, k, st, re);
     }
 }
 

@@ -212,3 +212,41 @@ def test_many_reads_path(mods):
         want = mods.oracle.detect_repeats_by_k(np.ascontiguousarray(host[r]), fs, arrays=True)
         sel = rec == r
         assert np.array_equal(st[sel], want[0]) and np.array_equal(en[sel], want[1])
+
+
+def test_pipelined_host_upload_equals_device_load(mods):
+    """Host buffers above 128 MB go up in 64 MB chunks with the pack kernel running behind the copy; the packed
+    planes must not depend on how the bytes arrived: same rows as a load of the same bytes already in HBM, for
+    records in source order, for overlapping out-of-order ranges with empty records in between, and for reads."""
+    torch = mods.torch
+    bases, offsets, _ = mods.synth.s38(device="cuda:0", scale=0.1)          # ~309 Mbp, 24 records
+    host = bases.cpu().numpy()
+    ctx = mods.api.get_context()
+
+    def rows(seq, kmax=50):
+        n = seq.scan(1, kmax, 3, 9)
+        out = seq.fetch(n)
+        seq.close()
+        return out
+
+    want = rows(ctx.load(bases.data_ptr(), offsets, max_motif_cap=50, on_device=True))
+    got = rows(ctx.load(host, offsets, max_motif_cap=50))
+    assert len(want[0]) > 500000
+    assert all(np.array_equal(a, b) for a, b in zip(want, got))
+
+    rng = np.random.default_rng(3)
+    n = len(host)
+    starts = rng.integers(0, n - 40_000_000, size=12).astype(np.uint64)     # out of order, overlapping
+    lens = rng.integers(1, 40_000_000, size=12).astype(np.uint64)
+    lens[[2, 7]] = 0
+    want = rows(ctx.load_ranges(bases.data_ptr(), starts, lens, max_motif_cap=50, on_device=True))
+    got = rows(ctx.load_ranges(host, starts, lens, max_motif_cap=50))
+    assert len(want[0]) > 100000
+    assert all(np.array_equal(a, b) for a, b in zip(want, got))
+
+    n_reads = 2_000_000                                                     # 300 MB of 150-base records
+    r_off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(150))
+    want = rows(ctx.load(bases.data_ptr(), r_off, max_motif_cap=20, on_device=True), 20)
+    got = rows(ctx.load(host[:n_reads * 150], r_off, max_motif_cap=20), 20)
+    assert len(want[0]) > 10000 and all(np.array_equal(a, b) for a, b in zip(want, got))
+    del torch
