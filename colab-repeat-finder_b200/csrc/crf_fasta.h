@@ -14,6 +14,7 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <exception>
 #include <chrono>
 #include <functional>
 #include <thread>
@@ -132,17 +133,38 @@ static void run_parallel(unsigned n_threads, size_t n_items, const std::function
         for (size_t i; (i = next.fetch_add(1)) < n_items;) fn(i);
     };
     std::vector<std::thread> pool;
-    for (unsigned t = 1; t < n_threads && t < n_items; ++t) pool.emplace_back(worker);
+    for (unsigned t = 1; t < n_threads && t < n_items; ++t) {
+        try {
+            pool.emplace_back(worker);
+        } catch (const std::exception &) {              // no more threads to be had: go on with those we have
+            break;
+        }
+    }
     worker();
     for (auto &th : pool) th.join();
 }
 
 }  // namespace fasta_detail
 
+static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf_fasta **out);
+extern "C" int crf_fasta_close(crf_fasta *fa);
+
 extern "C" int crf_fasta_open(const char *path, uint32_t n_threads, int pinned, crf_fasta **out) {
-    using namespace fasta_detail;
     if (!path || !out) { set_err("crf_fasta_open: null argument"); return CRF_ERR_ARG; }
     *out = nullptr;
+    try {                                               // no exception crosses the C boundary
+        return fasta_open_impl(path, n_threads, pinned, out);
+    } catch (const std::bad_alloc &) {
+        set_err("crf_fasta_open: out of host memory reading %s", path);
+        return CRF_ERR_NOMEM;
+    } catch (const std::exception &ex) {
+        set_err("crf_fasta_open: %s", ex.what());
+        return CRF_ERR_ARG;
+    }
+}
+
+static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf_fasta **out) {
+    using namespace fasta_detail;
     const bool trace = getenv("CRF_FASTA_TRACE") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
@@ -164,8 +186,11 @@ extern "C" int crf_fasta_open(const char *path, uint32_t n_threads, int pinned, 
     lap("read");
     if (n_threads == 0) n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
 
-    crf_fasta *fa = new (std::nothrow) crf_fasta;
-    if (!fa) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    struct Guard {                                      // frees the handle unless it is handed to the caller
+        crf_fasta *p;
+        ~Guard() { if (p) crf_fasta_close(p); }
+    } guard{new crf_fasta};
+    crf_fasta *fa = guard.p;
 
     // headers: a '>' at the start of a line
     const uint64_t PIECE = 8u << 20;
@@ -239,7 +264,7 @@ extern "C" int crf_fasta_open(const char *path, uint32_t n_threads, int pinned, 
         }
     }
     if (!fa->bases) fa->bases = (uint8_t *)malloc(alloc);
-    if (!fa->bases) { delete fa; set_err("crf_fasta_open: out of host memory (%llu bases)", (unsigned long long)total); return CRF_ERR_NOMEM; }
+    if (!fa->bases) { set_err("crf_fasta_open: out of host memory (%llu bases)", (unsigned long long)total); return CRF_ERR_NOMEM; }
 
     lap("alloc");
     uint8_t *dst = fa->bases;
@@ -269,6 +294,7 @@ extern "C" int crf_fasta_open(const char *path, uint32_t n_threads, int pinned, 
         }
     });
     lap("compact");
+    guard.p = nullptr;
     *out = fa;
     return CRF_OK;
 }
