@@ -35,6 +35,19 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line, the JSON result: anything libraries write to fd 1 on the way (NCCL prints its
+# version banner there) is sent to stderr, and emit() puts the real stdout back for the one line.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
+
+
 # ---- clocks ----------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
@@ -146,7 +159,7 @@ def reference_arm(args):
                                    f"host has {oracle.max_threads()} cores"},
         "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -480,7 +493,7 @@ def main():
         "scan_stats": {"scan_ms": float(np.mean(scan_ms)), "kernel_ms": k_ms, "candidates": int(stats.n_candidates),
                        "long_runs": int(stats.n_long), "spilled": int(stats.n_spilled), "tiles": int(stats.n_tiles)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

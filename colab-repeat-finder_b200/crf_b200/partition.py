@@ -23,7 +23,8 @@ import numpy as np
 Unit = namedtuple("Unit", "index record u0 u1 d0 d1 rec_len")
 
 DEFAULT_CHUNK = 1 << 25     # 33.5 Mbp owned per unit
-DEFAULT_HALO = 1 << 16      # 64 kbp: repeats shorter than this never need stitching
+DEFAULT_HALO = 1 << 20      # 1 Mbp (3 % of a unit): only a perfect repeat longer than this needs the stitch exchange;
+                            # the halo is never scanned for starts, it is only read when a run is followed into it
 
 
 class Plan:
