@@ -261,6 +261,13 @@ def main():
             return n
         n_open = int(seq.stats().n_open)
         open_rows = seq.fetch_open() if (n_open and plan is not None) else np.zeros((0, 5), np.uint32)
+
+        def fetch_rows():                             # this rank's rows -> its slot of the gather buffer (device to device)
+            cap_, buf_ = gstate["cap"], gstate["buf"]
+            cols = [buf_[i * cap_:i * cap_ + n] for i in range(4)]
+            seq.fetch_device(*(c.data_ptr() for c in cols), n)
+            return cols
+        cols = fetch_rows() if gstate["cap"] >= n else None   # queued before the header exchange blocks the host
         # one small all-gather carries every rank's row count and its open-ended rows (record, start, end, k)
         hdr = torch.full((2 + 4 * MAX_OPEN,), -1, dtype=torch.int64)
         hdr[0], hdr[1] = n, len(open_rows)
@@ -277,9 +284,10 @@ def main():
             gstate["cap"] = cap
             gstate["buf"] = torch.zeros(4 * cap, dtype=torch.int32, device=dev)
             gstate["out"] = [torch.empty_like(gstate["buf"]) for _ in range(world)] if rank == 0 else None
-        cap, buf = gstate["cap"], gstate["buf"]
-        rec, st, en, kk = (buf[i * cap:i * cap + n] for i in range(4))
-        seq.fetch_device(rec.data_ptr(), st.data_ptr(), en.data_ptr(), kk.data_ptr(), n)
+            cols = None
+        if cols is None:
+            cols = fetch_rows()
+        buf, en = gstate["buf"], cols[2]
         mark('fetch_device')
         if sum(n_open_all) and plan is not None:      # a repeat longer than the halo crossed a unit end
             run_end = lambda unit, lp, k: seq.run_end(unit.index - plan.bounds[rank], lp, k)   # noqa: E731
