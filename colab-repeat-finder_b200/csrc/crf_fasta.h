@@ -144,6 +144,68 @@ static void run_parallel(unsigned n_threads, size_t n_items, const std::function
     for (auto &th : pool) th.join();
 }
 
+// BGZF (bgzip, what `samtools faidx` wants and the reference's Hail pipeline ships: run_hail_batch_pipeline.py:112 takes
+// the .gzi next to the FASTA): every gzip member is a self-contained block of <= 64 KiB that says its own compressed size
+// in a 'BC' extra field, so the blocks are found by hopping over the headers and inflated on all threads.
+// Returns false if the file is not BGZF from the first to the last byte (the caller then inflates it serially);
+// *bad is set if it is BGZF but a block is corrupt.
+static bool inflate_bgzf(const FileBytes &in, unsigned n_threads, std::vector<uint8_t> &out, bool *bad) {
+    struct Block { uint64_t cdata, clen, out; uint32_t isize, crc; };
+    std::vector<Block> blocks;
+    const uint8_t *d = in.data;
+    const uint64_t n = in.size;
+    uint64_t pos = 0, total = 0;
+    while (pos < n) {
+        if (n - pos < 18 || d[pos] != 0x1f || d[pos + 1] != 0x8b || d[pos + 2] != 8 || !(d[pos + 3] & 4)) return false;
+        const uint32_t xlen = d[pos + 10] | (d[pos + 11] << 8);
+        if (n - pos < 12ull + xlen + 8) return false;
+        uint32_t bsize = 0;
+        for (uint32_t x = 0; x + 4 <= xlen;) {           // extra subfields: SI1 SI2 SLEN(2) data
+            const uint8_t *f = d + pos + 12 + x;
+            const uint32_t slen = f[2] | (f[3] << 8);
+            if (f[0] == 'B' && f[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (f[4] | (f[5] << 8)) + 1u;
+            x += 4 + slen;
+        }
+        if (bsize < 12 + xlen + 8 || pos + bsize > n) return false;
+        if (d[pos + 3] & ~4) return false;                // other header fields (name, comment, crc): not what bgzip writes
+        Block b;
+        b.cdata = pos + 12 + xlen;
+        b.clen = bsize - 12 - xlen - 8;
+        const uint8_t *tail = d + pos + bsize - 8;
+        b.crc = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
+        b.isize = tail[4] | (tail[5] << 8) | (tail[6] << 16) | ((uint32_t)tail[7] << 24);
+        if (b.isize > 65536) return false;
+        b.out = total;
+        total += b.isize;
+        blocks.push_back(b);
+        pos += bsize;
+    }
+    out.resize(total);
+    std::atomic<bool> failed{false};
+    const size_t GROUP = 128;                             // blocks per work item (<= 8 MiB of text)
+    run_parallel(n_threads, (blocks.size() + GROUP - 1) / GROUP, [&](size_t g) {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) { failed = true; return; }
+        for (size_t i = g * GROUP; i < std::min(blocks.size(), (g + 1) * GROUP) && !failed; ++i) {
+            const Block &b = blocks[i];
+            if (b.isize == 0) continue;                   // the empty end-of-file block
+            zs.next_in = const_cast<Bytef *>(d + b.cdata);
+            zs.avail_in = (uInt)b.clen;
+            zs.next_out = out.data() + b.out;
+            zs.avail_out = b.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data() + b.out, b.isize) != b.crc)
+                failed = true;
+            inflateReset(&zs);
+        }
+        inflateEnd(&zs);
+    });
+    *bad = failed;
+    return true;
+}
+
 }  // namespace fasta_detail
 
 static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf_fasta **out);
@@ -178,13 +240,17 @@ static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf
     if (!open_bytes(path, file)) { set_err("crf_fasta_open: cannot read %s", path); return CRF_ERR_ARG; }
     const uint8_t *t = file.data;
     uint64_t n = file.size;
+    if (n_threads == 0) n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
     if (n >= 2 && t[0] == 0x1f && t[1] == 0x8b) {
-        if (!inflate_all(file, plain)) { set_err("crf_fasta_open: %s is not a valid gzip stream", path); return CRF_ERR_ARG; }
+        bool bad = false;
+        const bool bgzf = inflate_bgzf(file, n_threads, plain, &bad);
+        if (bgzf && bad) { set_err("crf_fasta_open: %s has a corrupt BGZF block", path); return CRF_ERR_ARG; }
+        if (!bgzf && !inflate_all(file, plain)) { set_err("crf_fasta_open: %s is not a valid gzip stream", path); return CRF_ERR_ARG; }
         t = plain.data();
         n = plain.size();
+        lap(bgzf ? "bgzf" : "gzip");
     }
     lap("read");
-    if (n_threads == 0) n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
 
     struct Guard {                                      // frees the handle unless it is handed to the caller
         crf_fasta *p;

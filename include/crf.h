@@ -161,7 +161,7 @@ int crf_write_rows(const char *path, int append, int tsv, const char *names, con
 /* ---- input (host only, no GPU) ---------------------------------------------------------------
  * Native FASTA ingest, replacing what the reference takes from pyfastx (prf:117-137: the records in file
  * order, .name = first whitespace-delimited header token, .seq = the lines joined, case preserved).  Plain or
- * gzip (concatenated members / bgzip too).  The result is laid out as crf_seq_load_ascii and crf_write_rows
+ * gzip (concatenated members too; BGZF/bgzip blocks are inflated in parallel).  The result is laid out as crf_seq_load_ascii and crf_write_rows
  * take it: all records back to back, n_records+1 offsets, NUL-separated names.  n_threads = 0: up to 16.
  * pinned != 0: page-locked buffer (cudaHostAlloc) when a device is present, for a faster upload.
  * The pointers of crf_fasta_data stay valid until crf_fasta_close. */

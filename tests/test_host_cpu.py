@@ -64,6 +64,52 @@ def test_fasta_reader_large_multi_piece(tmp_path, eol):
                     assert fa.record(i).tobytes() == seq, (path, threads, i)
 
 
+def _bgzf(raw, block=30000):
+    """bgzip's container: gzip members of <= 64 KiB with a 'BC' extra field holding the member's size, then the empty
+    end-of-file block."""
+    import struct
+    import zlib
+    out = []
+    for i in list(range(0, len(raw), block)) + [None]:
+        chunk = b"" if i is None else raw[i:i + block]
+        comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+        data = comp.compress(chunk) + comp.flush()
+        bsize = 12 + 6 + len(data) + 8
+        out.append(b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) +
+                   data + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    return b"".join(out)
+
+
+def test_fasta_reader_bgzf_parallel_blocks(tmp_path):
+    from crf_b200 import _cabi
+    rng = np.random.default_rng(11)
+    chunks = []
+    for r, size in enumerate([5_000_000, 0, 123, 9_000_000]):
+        seq = rng.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8), size=size).tobytes()
+        chunks.append(b">c%d x\n" % r + b"".join(seq[i:i + 60] + b"\n" for i in range(0, size, 60)))
+    raw = b"".join(chunks)
+    want = _simple_fasta(raw)
+    blob = _bgzf(raw)
+    assert gzip.decompress(blob) == raw                      # the container is valid gzip
+    path = tmp_path / "ref.fa.bgz"
+    path.write_bytes(blob)
+    for threads in (1, 6):
+        with _cabi.Fasta(str(path), n_threads=threads) as fa:
+            assert [(n, fa.record(i).tobytes()) for i, n in enumerate(fa.names)] == want
+    # BGZF blocks followed by an ordinary gzip member: not BGZF throughout, read by the serial path
+    mixed = tmp_path / "mixed.fa.gz"
+    mixed.write_bytes(_bgzf(raw[:1_000_000])[:-28] + gzip.compress(raw[1_000_000:2_000_000], 1))
+    with _cabi.Fasta(str(mixed)) as fa:
+        assert [(n, fa.record(i).tobytes()) for i, n in enumerate(fa.names)] == _simple_fasta(raw[:2_000_000])
+    # a flipped payload byte is caught by the block's CRC
+    broken = bytearray(blob)
+    broken[len(blob) // 2] ^= 0x55
+    bad = tmp_path / "bad.fa.bgz"
+    bad.write_bytes(bytes(broken))
+    with pytest.raises(ValueError, match="BGZF|gzip"):
+        _cabi.Fasta(str(bad))
+
+
 def test_fasta_reader_edge_cases(tmp_path):
     from crf_b200 import _cabi
     cases = {
