@@ -282,7 +282,14 @@ class Fasta:
         self.offsets = np.ctypeslib.as_array(ctypes.cast(offsets, ctypes.POINTER(ctypes.c_uint64)),
                                              shape=(self.n_records + 1,)).copy()
         self.names_blob = ctypes.string_at(names, nbytes.value) if nbytes.value else b""
-        self.names = [x.decode("utf-8", "replace") for x in self.names_blob.split(b"\0")[:self.n_records]]
+        self._names = None
+
+    @property
+    def names(self):
+        """Record names as str (decoded on first use: a reads file has millions)."""
+        if self._names is None:
+            self._names = [x.decode("utf-8", "replace") for x in self.names_blob.split(b"\0")[:self.n_records]]
+        return self._names
 
     def record(self, i):
         """uint8 view of record i."""

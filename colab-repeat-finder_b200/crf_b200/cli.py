@@ -88,7 +88,9 @@ def _whole_fasta_to_bed(fa, args, bed_path):
             with ctx.load(blob, offsets, max_motif_cap=args.max_motif_size) as seq:
                 n = seq.scan(args.min_motif_size, args.max_motif_size, args.min_repeats, args.min_span)
                 rec, start, end, k = seq.fetch(n)
-            _cabi.write_rows(bed_path, fa.names[first:last], blob, offsets, rec, start, end, k, append=True)
+            whole_file = first == 0 and last == fa.n_records          # the usual case: hand the name table over as it is
+            _cabi.write_rows(bed_path, fa.names_blob if whole_file else fa.names[first:last], blob, offsets, rec, start,
+                             end, k, append=True)
             np.add.at(counts, rec.astype(np.int64) + first, 1)
         first = last
     return counts

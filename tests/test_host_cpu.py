@@ -181,6 +181,13 @@ def test_native_row_writer_bed_and_tsv(tmp_path):
     _cabi.write_rows(str(bed), ["a"], b"ACGT" * 2000, [0, 8000], [0] * k, list(range(k)), list(range(1, k + 1)), [1] * k)
     lines = bed.read_text().splitlines()
     assert len(lines) == k and lines[-1].startswith("a\t4999\t5000\t")
+    # file -> reader -> writer without Python strings in between: the reader's NUL-separated name table and base buffer
+    fa_path = tmp_path / "w.fa"
+    fa_path.write_bytes(b">chr1 first\nACGTacgt\nNN\n>chrZ\nacgtttttt\n")
+    with _cabi.Fasta(str(fa_path)) as fa:
+        assert fa.names_blob == b"chr1\0chrZ\0"
+        _cabi.write_rows(str(bed), fa.names_blob, fa.bases, fa.offsets, [0, 1, 1], [0, 0, 3], [8, 4, 9], [4, 4, 1])
+    assert bed.read_text() == "chr1\t0\t8\tACGT\nchrZ\t0\t4\tACGT\nchrZ\t3\t9\tT\n"
 
 
 # ---- min_repeats == 1: the host half (position-0 wrap-around, early-break selection) with the GPU scan replaced by
@@ -242,3 +249,35 @@ def test_single_copy_host_logic_against_reference_vectors(monkeypatch):
         raising += exc is not None
         checked += 1
     assert checked >= 280 and raising >= 10 and refused <= 15
+
+
+def test_fasta_reader_random_files(tmp_path):
+    """Seeded fuzz of the native reader against the line-by-line checker: ragged widths, LF / CRLF mixed, blank lines,
+    '>' inside sequence lines, empty records, text before the first header; plain, gzip and BGZF containers."""
+    import random
+    from crf_b200 import _cabi
+    rng = random.Random(2026)
+    for case in range(120):
+        parts = []
+        if rng.random() < 0.2:
+            parts.append(b"stray text\n")
+        for r in range(rng.randint(0, 6)):
+            eol = rng.choice([b"\n", b"\r\n"])
+            parts.append(b">" + rng.choice([b"", b" ", b"\t"]) + b"r%d" % r + rng.choice([b"", b" desc here", b"\tx"]) + eol)
+            for _ in range(rng.randint(0, 8)):
+                width = rng.choice([0, 1, 7, 60, 61, 200])
+                line = bytes(rng.choice(b"ACGTacgtNnRY>") for _ in range(width))
+                if line.startswith(b">"):
+                    line = b"A" + line[1:]
+                parts.append(line + rng.choice([eol, b"\n"]))
+        raw = b"".join(parts)
+        if raw and rng.random() < 0.5:
+            raw = raw.rstrip(b"\r\n")                     # no line end after the last line
+        want = _simple_fasta(raw)
+        container = rng.choice(["plain", "gzip", "bgzf"])
+        blob = raw if container == "plain" else gzip.compress(raw) if container == "gzip" else _bgzf(raw, rng.choice([50, 4000]))
+        path = tmp_path / f"f{case}.fa"
+        path.write_bytes(blob)
+        with _cabi.Fasta(str(path), n_threads=rng.choice([1, 3])) as fa:
+            got = [(n, fa.record(i).tobytes()) for i, n in enumerate(fa.names)]
+        assert got == want, (case, container, raw[:200])
