@@ -40,7 +40,18 @@ class FakeSeq:
     def close(self):
         pass
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
 
 class FakeContext:
+    def load(self, bases, offsets=None, max_motif_cap=50, on_device=False):
+        n = len(bases)
+        offsets = np.array([0, n], dtype=np.uint64) if offsets is None else np.asarray(offsets, dtype=np.uint64)
+        return FakeSeq(bases, offsets[:-1], np.diff(offsets.astype(np.int64)), None, None)
+
     def load_ranges(self, bases, starts, lengths, own_lo=None, own_hi=None, max_motif_cap=50, on_device=False):
         return FakeSeq(bases, starts, lengths, own_lo, own_hi)

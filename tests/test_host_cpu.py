@@ -281,3 +281,32 @@ def test_fasta_reader_random_files(tmp_path):
         with _cabi.Fasta(str(path), n_threads=rng.choice([1, 3])) as fa:
             got = [(n, fa.record(i).tobytes()) for i, n in enumerate(fa.names)]
         assert got == want, (case, container, raw[:200])
+
+
+def test_cli_whole_fasta_glue_with_a_stand_in_scan(tmp_path, monkeypatch, capsys):
+    """The CLI's FASTA -> BED plumbing (native reader, grouping of records into loads, native writer, stdout lines) with
+    the GPU scan replaced by tests/fake_ctx.py (the oracle).  The real scan is covered by the -m gpu CLI test."""
+    import random
+    from crf_b200 import api
+    from tests.fake_ctx import FakeContext
+    from tests.helpers import ns, random_seq
+    from oracle import oracle
+    rng = random.Random(4)
+    recs = [("chrA", random_seq(rng, 3000)), ("chrB extra words", random_seq(rng, 50)), ("empty", ""),
+            ("chrC", random_seq(rng, 7000)), ("chrD", random_seq(rng, 900))]
+    fa = tmp_path / "glue.fasta"
+    fa.write_text("".join(f">{n}\n" + "".join(s[i:i + 50] + "\n" for i in range(0, len(s), 50)) for n, s in recs))
+    want = []
+    for name, seq in recs:
+        fs = ns(min_motif_size=1, max_motif_size=12, min_repeats=3, min_span=9)
+        want += [f"{name.split()[0]}\t{s}\t{e}\t{m}\n" for s, e, m in oracle.detect_repeats(seq, fs)]
+    monkeypatch.setattr(api, "get_context", lambda device=None: FakeContext())
+    monkeypatch.chdir(tmp_path)
+    for limit in (cli.MAX_LOAD_BASES, 3500, 1):           # one load / several groups / one record per load
+        monkeypatch.setattr(cli, "MAX_LOAD_BASES", limit)
+        assert cli.main([str(fa), "-max", "12", "-o", str(tmp_path / "sub" / "glue_out")]) == 0
+        assert (tmp_path / "glue_out.bed").read_text() == "".join(want)          # basename(prefix), in the CWD (prf:116)
+        out = capsys.readouterr().out
+        assert "Processing chrB (50 bp)" in out and "Processing empty (0 bp)" in out and "Found 0 repeats" in out
+        assert out.rstrip().endswith("Wrote results to glue_out.bed")
+    assert len(want) > 30
