@@ -7,7 +7,8 @@ tests as a sanity check, then records detect_repeats() outputs for
 
   * kat.json   -- the 32 known-answer calls of perfect_repeat_finder_tests.py:31-143, restated
                   as data (inputs + the reference's outputs),
-  * fuzz_full.json, fuzz_interval.json, fuzz_minrep1.json -- seeded random cases.
+  * fuzz_full.json, fuzz_interval.json, fuzz_minrep1.json, fuzz_interval_long.json -- seeded random cases,
+  * primitivity.json -- consists_of_perfect_repeats() on seeded strings.
 
 The reference cannot travel to the GPU box, so these files are what pins the oracle
 (oracle/crf_oracle.c) and, through it, the CUDA path.  Re-run:  python tests/golden/make_golden.py
@@ -140,6 +141,23 @@ def fuzz_interval_long(ref, seed, count):
     return out
 
 
+def primitivity_cases(seed, count):
+    """Inputs / outputs of the reference's consists_of_perfect_repeats (utils/perfect_repeat_tracker.py:108-142)."""
+    sys.path.insert(0, REF)
+    from utils.perfect_repeat_tracker import consists_of_perfect_repeats
+    rng = random.Random(seed)
+    out = []
+    for _ in range(count):
+        alpha = rng.choice(["A", "AC", "ACG", "ACGT", "ACGTN"])
+        if rng.random() < 0.6:
+            unit = "".join(rng.choice(alpha) for _ in range(rng.randint(1, 12)))
+            seq = unit * rng.randint(1, 8)
+        else:
+            seq = "".join(rng.choice(alpha) for _ in range(rng.randint(0, 40)))
+        out.append({"seq": seq, "unit": consists_of_perfect_repeats(seq)})
+    return out
+
+
 def main():
     ref = import_reference()
     # sanity: the reference's own test-suite passes under the stubs
@@ -158,6 +176,7 @@ def main():
     dump("fuzz_interval.json", fuzz(ref, 2002, 400, "interval"))
     dump("fuzz_minrep1.json", fuzz(ref, 3003, 300, "minrep1"))
     dump("fuzz_interval_long.json", fuzz_interval_long(ref, 4004, 40))
+    dump("primitivity.json", primitivity_cases(5005, 600))
 
 
 if __name__ == "__main__":

@@ -310,3 +310,18 @@ def test_cli_whole_fasta_glue_with_a_stand_in_scan(tmp_path, monkeypatch, capsys
         assert "Processing chrB (50 bp)" in out and "Processing empty (0 bp)" in out and "Found 0 repeats" in out
         assert out.rstrip().endswith("Wrote results to glue_out.bed")
     assert len(want) > 30
+
+
+def test_tracker_module_compat():
+    """utils.perfect_repeat_tracker stays importable: the string helper answers like the reference's (vectors generated
+    from trk:108-142 by tests/golden/make_golden.py, also used by api._is_primitive), the CPU tracker class refuses."""
+    from crf_b200 import api
+    from tests.helpers import load_golden
+    from utils.perfect_repeat_tracker import PerfectRepeatTracker, consists_of_perfect_repeats
+    cases = load_golden("primitivity.json")
+    assert len(cases) == 600 and sum(c["unit"] is not None for c in cases) > 200
+    for c in cases:
+        assert consists_of_perfect_repeats(c["seq"]) == c["unit"], c
+        assert api._is_primitive(c["seq"].encode()) == (c["unit"] is None), c
+    with pytest.raises(NotImplementedError, match="detect_repeats"):
+        PerfectRepeatTracker(3, 3, 9, "ACGT", {})
