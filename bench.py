@@ -37,15 +37,24 @@ def log(*a):
 
 # stdout carries exactly ONE line, the JSON result: anything libraries write to fd 1 on the way (NCCL prints its
 # version banner there) is sent to stderr, and emit() puts the real stdout back for the one line.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line):
     sys.stdout.flush()
-    os.dup2(_REAL_STDOUT, 1)
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
     print(json.dumps(line), flush=True)
-    os.dup2(2, 1)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
 
 
 # ---- clocks ----------------------------------------------------------------------------------------
@@ -175,6 +184,7 @@ def main():
     ap.add_argument("--words-per-thread", type=int, default=0)
     ap.add_argument("--trace", action="store_true", help="print per-stage host timings of one extra step (stderr)")
     args = ap.parse_args()
+    claim_stdout()
     global KMAX
     if args.workload == "sr":
         KMAX = 20
