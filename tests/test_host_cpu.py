@@ -325,3 +325,61 @@ def test_tracker_module_compat():
         assert api._is_primitive(c["seq"].encode()) == (c["unit"] is None), c
     with pytest.raises(NotImplementedError, match="detect_repeats"):
         PerfectRepeatTracker(3, 3, 9, "ACGT", {})
+
+
+# ---- interval mode: the host half (N-trim, probe scan -> stop position, cut, selection, AssertionError / IndexError) with
+# ---- the scan replaced by a numpy statement of the closed form crf_scan documents
+
+class _ClosedFormSeq:
+    def __init__(self, raw):
+        self.s = bytes(raw).upper()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        pass
+
+    def scan(self, kmin, kmax, min_repeats, min_span, flags=0, **knobs):
+        from crf_b200 import _cabi, api
+        s, L = self.s, len(self.s)
+        arr = np.frombuffer(s, dtype=np.uint8)
+        rows = []
+        for k in range(kmin, min(kmax, L - 1) + 1):
+            m = (arr[:L - k] == arr[k:]) & (arr[:L - k] != ord("N"))
+            edge = np.diff(np.concatenate([[0], m.astype(np.int8), [0]]))
+            rmin = max(min_span - k, (min_repeats - 1) * k, 1)
+            for st, i0 in zip(np.flatnonzero(edge == 1).tolist(), np.flatnonzero(edge == -1).tolist()):
+                if i0 - st >= rmin and ((flags & _cabi.SCAN_NO_PRIMITIVITY) or api._is_primitive(s[st:st + k])):
+                    rows.append((st, i0 + k, k))
+        rows.sort()
+        self.rows = np.array(rows, dtype=np.uint32).reshape(-1, 3)
+        return len(rows)
+
+    def fetch(self, n):
+        return np.zeros(n, np.uint32), self.rows[:, 0], self.rows[:, 1], self.rows[:, 2]
+
+
+class _ClosedFormCtx:
+    def load(self, raw, offsets=None, max_motif_cap=50, on_device=False):
+        return _ClosedFormSeq(raw)
+
+
+@pytest.mark.parametrize("name", ["kat.json", "fuzz_full.json", "fuzz_interval.json", "fuzz_interval_long.json"])
+def test_detect_repeats_host_logic_against_reference_vectors(monkeypatch, name):
+    from crf_b200 import api
+    from tests.helpers import load_golden, ns
+    monkeypatch.setattr(api, "get_context", lambda device=None: _ClosedFormCtx())
+    n_rows = n_exc = 0
+    for i, case in enumerate(load_golden(name)):
+        fs = ns(**case["settings"])
+        try:
+            got, exc = api.detect_repeats(case["seq"], fs), None
+        except (AssertionError, IndexError, ValueError, AttributeError) as e:
+            got, exc = None, type(e).__name__
+        assert exc == case.get("raises"), (name, i, case["settings"])
+        if exc is None:
+            assert got == [tuple(r) for r in case["result"]], (name, i, case["settings"])
+            n_rows += len(got)
+        n_exc += exc is not None
+    assert n_rows > 30
