@@ -15,3 +15,16 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def native_artefacts():
+    """libcrf.so / libcrf_tools.so (nvcc, sm_100a -- cross-compiles without a GPU) and the C oracle are built once per session
+    if missing or older than their sources, so the suite does not depend on a prior build step."""
+    pkg = os.path.join(ROOT, "colab-repeat-finder_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from crf_b200 import build as crf_build
+    from oracle import oracle
+    crf_build.build()
+    oracle.build()
