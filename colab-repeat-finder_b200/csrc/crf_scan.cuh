@@ -5,7 +5,8 @@
 // checked against the CPU restatement by tests/): for each k, every maximal run [st, i0) of ones of
 //   M_k[j] = (S[j] == S[j+k]) and S[j] != 'N'
 // with i0 - st >= r_min(k) = max(min_span - k, (min_repeats-1)*k) and a primitive motif S[st:st+k]
-// is reported as (st, i0 + k, k).
+// is reported as (st, i0 + k, k).  (min_repeats == 1: r_min = max(min_span - k, k-1); the host table carries it, and
+// single_copy_filter_kernel settles the one base such a run leaves untested -- DESIGN.md section 6.)
 //
 // One CTA owns one tile of 256*T words (T*8192 bases) and emits the runs that START in it:
 //   1. stage the tile (one word of left context, a halo of kmax bases) of the H, L and NM planes in
