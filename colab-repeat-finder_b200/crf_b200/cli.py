@@ -127,9 +127,11 @@ def _run_fasta(parser, args):
         else:
             counts = _whole_fasta_to_bed(fa, args, bed_path)
             lengths = np.diff(fa.offsets.astype(np.int64))
-            for name, length, n_found in zip(fa.names, lengths.tolist(), counts.tolist()):
-                print(f"Processing {name} ({length:,d} bp)")
-                print(f"Found {n_found:,d} repeats")
+            names, lengths, counts = fa.names, lengths.tolist(), counts.tolist()
+            for lo in range(0, len(names), 65536):            # the reference's two lines per record; batched, a reads
+                sys.stdout.write("".join(                     # file has millions of records
+                    f"Processing {n_} ({l_:,d} bp)\nFound {c_:,d} repeats\n"
+                    for n_, l_, c_ in zip(names[lo:lo + 65536], lengths[lo:lo + 65536], counts[lo:lo + 65536])))
     print(f"Wrote results to {bed_path}")
 
 
