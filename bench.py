@@ -28,7 +28,11 @@ for p in (ROOT, os.path.join(ROOT, "colab-repeat-finder_b200")):
 import numpy as np  # noqa: E402
 
 KMIN, KMAX, MIN_REPEATS, MIN_SPAN = 1, 50, 3, 9       # the reference CLI defaults (prf:86-89)
-METRIC = "Gbp/s scanned (motif 1-50)"     # BASELINE.json metric; the reads workload (--workload sr) scans motif 1-20
+
+
+def metric_name():
+    """BASELINE.json's metric; the reads workload (--workload sr, config C5) scans motif 1-20."""
+    return f"Gbp/s scanned (motif {KMIN}-{KMAX})"
 
 
 def log(*a):
@@ -130,42 +134,106 @@ def make_workload(name, device, scale):
     raise SystemExit(f"unknown workload {name}")
 
 
+def bench_config(workload_name, total_bp, world):
+    """The `config` object of the JSON line: a pure function of the workload and N, so that both arms (ours and
+    `--impl reference`) print the same one."""
+    chunked = world > 1 and workload_name != "sr"
+    return {"workload": workload_name, "motif_sizes": [KMIN, KMAX], "min_repeats": MIN_REPEATS, "min_span": MIN_SPAN,
+            "total_bp": int(total_bp),
+            "l2": "inputs larger than L2 (no flush): %.0f MB of packed planes over %d GPU(s)" % (total_bp * 0.375 / 1e6, world),
+            "partition": ("(record, 2^25-bp chunk) units + 1 Mbp halo" if chunked else
+                          "reads split by count" if workload_name.startswith("SR") else "whole records") + f" over {world} rank(s)"}
+
+
+REF_SLICE_BP = 120_000     # bases per worker process and step for the Python reference (x 50 motif sizes = 6 M tracker steps)
+
+
 def reference_arm(args):
-    """--impl reference: the reference's own CPU algorithm (C port in oracle/, all host threads) on a
-    bounded sample of the same workload.  The Python reference itself cannot travel to the GPU box."""
+    """--impl reference: the reference's own CPU implementation on this box's host cores, one JSON line.
+
+    With oracle/_ref present (oracle/make_ref.sh; it travels to the GPU box) this is the UNMODIFIED Python
+    reference: detect_repeats() (prf:10-81) as shipped, single-threaded, one process per host core over disjoint
+    slices of the workload -- the reference's own scale-out shape (1-CPU jobs over intervals,
+    hail_batch_pipeline/run_hail_batch_pipeline.py:101).  A step = every worker scans its slice once; value = bases
+    scanned per second of wall time, all workers together.  The C port's rate on the same sample is kept beside it.
+    Without oracle/_ref the C port alone is timed ("kind": "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
+    from oracle import oracle, ref
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     dev = "cuda:0" if torch.cuda.is_available() else None
     if dev:
         bases, offsets, meta = make_workload(args.workload, dev, args.scale)
+        total_bp = int(offsets[-1])
         r = min(20, len(offsets) - 2)            # chr21 of S38 (46.7 Mbp); the only record of S22
-        sample = bases[int(offsets[r]):int(offsets[r + 1])].cpu().numpy()
+        record = bases[int(offsets[r]):int(offsets[r + 1])].cpu().numpy()
         sample_name = f"record {r} of the workload"
+        del bases
+        torch.cuda.empty_cache()
     else:
         from crf_b200 import synth
-        sample, _, _ = synth.generate_records([int(46_709_983 * args.scale)], 38, device=None)
+        record, _, _ = synth.generate_records([int(46_709_983 * args.scale)], 38, device=None)
         meta = {"workload": "S38-like single record (no GPU to generate the full genome)"}
+        total_bp = record.size
         sample_name = "standalone 46.7 Mbp record"
-    from oracle import oracle
-    times = []
-    for i in range(args.warmup + args.steps):
-        res = cpu_baseline_run(sample)
-        if i >= args.warmup:
-            times.append(res["seconds"])
-    dt = float(np.mean(times))
-    gbps = sample.size / dt / 1e9
+    fs = dict(min_motif_size=KMIN, max_motif_size=KMAX, min_repeats=MIN_REPEATS, min_span=MIN_SPAN)
+    n_k = KMAX - KMIN + 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if ref.available():
+        ref.load()                                # import once; the fork()ed workers inherit it
+        slice_bp = max(1000, int(REF_SLICE_BP * 50 / n_k))
+        lo0 = min(record.size // 4, 2_000_000)    # past the telomeric N block
+        slice_bp = min(slice_bp, max(1, (record.size - lo0) // cores))
+        slices = [bytes(record[lo0 + i * slice_bp:lo0 + (i + 1) * slice_bp]).decode("latin-1") for i in range(cores)]
+        sample_bp = sum(len(s) for s in slices)
+        pool = ref.make_pool(cores)
+        times, rows = [], None
+        for i in range(args.warmup + args.steps):
+            wall, _, rows = ref.run_slices(pool, slices, fs)
+            if i >= args.warmup:
+                times.append(wall)
+        pool.close()
+        dt = float(np.mean(times))
+        gbps = sample_bp / dt / 1e9
+        # the C port on the same bases (one thread per motif size), and its rows against the reference's
+        flat = np.frombuffer("".join(slices).encode("latin-1"), dtype=np.uint8)
+        port = cpu_baseline_run(flat)
+        port_rows = 0
+        same = True
+        for i, sl in enumerate(slices):
+            o = oracle.detect_repeats_by_k(sl, argparse.Namespace(**fs))
+            same = same and (o == rows[i])
+            port_rows += len(o)
+        cpu = {"value": gbps, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+               "sample": f"{cores} slices of {slice_bp} bp from {sample_name} (from position {lo0}), {n_k} motif sizes, "
+                         f"{dt:.2f} s per step; UNMODIFIED Python reference (oracle/_ref, detect_repeats as shipped, "
+                         f"single-threaded), one process per host core; measured, not extrapolated: the whole "
+                         f"{total_bp} bp workload at this rate = {total_bp / gbps / 1e9 / 3600:.1f} h on these {cores} cores",
+               "per_core_tracker_steps_per_s": sample_bp * n_k / dt / cores,
+               "port": {"value": port["bp"] / port["seconds"] / 1e9, "unit": "Gbp/s", "cores": port["threads"],
+                        "what": "C port of the tracker loop (oracle/crf_oracle.c) on the same bases, one thread per motif size",
+                        "rows_equal_reference": bool(same), "rows": port_rows},
+               "python": sys.version.split()[0]}
+    else:
+        times = []
+        for i in range(args.warmup + args.steps):
+            res = cpu_baseline_run(record)
+            if i >= args.warmup:
+                times.append(res["seconds"])
+        dt = float(np.mean(times))
+        gbps = record.size / dt / 1e9
+        cpu = {"value": gbps, "unit": "Gbp/s", "cores": res["threads"], "kind": "port",
+               "sample": f"{sample_name}, {record.size} bp x {n_k} motif sizes per step; oracle/_ref is absent, so this "
+                         f"is the C port of the tracker loop (oracle/crf_oracle.c), one thread per motif size; "
+                         f"host has {oracle.max_threads()} cores"}
     line = {
-        "impl": "reference", "metric": METRIC, "value": gbps, "unit": "Gbp/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(), "value": gbps, "unit": "Gbp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": meta["workload"], "motif_sizes": [KMIN, KMAX], "min_repeats": MIN_REPEATS,
-                   "min_span": MIN_SPAN},
-        "cpu_baseline": {"value": gbps, "unit": "Gbp/s", "cores": res["threads"], "kind": "port",
-                         "sample": f"{sample_name}, {sample.size} bp x {KMAX - KMIN + 1} motif sizes per step; "
-                                   f"C port of the tracker loop (oracle/crf_oracle.c), one thread per motif size; "
-                                   f"host has {oracle.max_threads()} cores"},
+        "config": bench_config(meta["workload"], total_bp, world),
+        "cpu_baseline": cpu,
         "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -188,7 +256,7 @@ def main():
     global KMAX
     if args.workload == "sr":
         KMAX = 20
-    if args.warmup < 3:
+    if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
     if args.impl == "reference":
         return reference_arm(args)
@@ -499,7 +567,7 @@ def main():
                "parity_on_sample": parity}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(), "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": meta["workload"], "motif_sizes": [KMIN, KMAX], "min_repeats": MIN_REPEATS,

@@ -8,7 +8,8 @@ OUT = os.path.join(_HERE, "libcrf.so")
 SOURCES = ["crf_api.cu"]
 HEADERS = ["crf_device.cuh", "crf_scan.cuh", "crf_aux.cuh", "crf_fasta.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC,-pthread"]
+              "-shared", "-cudart", "shared", "-Xcompiler", "-fPIC,-pthread"]   # cudart linked dynamically: the runtime's own
+                                                                               # symbol table stays out of the shipped .so
 LINK_FLAGS = ["-lz"]
 
 
@@ -23,8 +24,16 @@ def _stale(out, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _nvcc_path():
+    return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def have_nvcc():
+    return os.path.exists(_nvcc_path())
+
+
 def _nvcc(out, sources, verbose):
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    nvcc = _nvcc_path()
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
           [os.path.join(CSRC, f) for f in sources] + LINK_FLAGS
     subprocess.check_call(cmd)

@@ -25,6 +25,10 @@ def native_artefacts():
     if pkg not in sys.path:
         sys.path.insert(0, pkg)
     from crf_b200 import build as crf_build
-    from oracle import oracle
-    crf_build.build()
+    from oracle import oracle, ref
     oracle.build()
+    ref.build()                                  # copies the Python reference to oracle/_ref where /root/reference exists
+    if crf_build.have_nvcc():
+        crf_build.build()
+    # without nvcc the CPU-only suites (oracle, partition, host logic) still run; tests that need libcrf.so fail
+    # loudly in _cabi.lib() if no prebuilt library is there
