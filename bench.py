@@ -148,6 +148,51 @@ def bench_config(workload_name, total_bp, world):
 REF_SLICE_BP = 120_000     # bases per worker process and step for the Python reference (x 50 motif sizes = 6 M tracker steps)
 
 
+def python_reference_sample(record, sample_name, total_bp, warmup, steps):
+    """Time the UNMODIFIED Python reference (oracle/_ref) on `cores` disjoint slices of `record`, one process per host
+    core, `steps` timed passes; the C port runs the same bases once for comparison.  Returns the cpu_baseline object."""
+    from oracle import oracle, ref
+    fs = dict(min_motif_size=KMIN, max_motif_size=KMAX, min_repeats=MIN_REPEATS, min_span=MIN_SPAN)
+    n_k = KMAX - KMIN + 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ref.load()                                # import once; the fork()ed workers inherit it
+    slice_bp = max(1000, int(REF_SLICE_BP * 50 / n_k))
+    lo0 = min(record.size // 4, 2_000_000)    # past the telomeric N block
+    slice_bp = min(slice_bp, max(1, (record.size - lo0) // cores))
+    slices = [bytes(record[lo0 + i * slice_bp:lo0 + (i + 1) * slice_bp]).decode("latin-1") for i in range(cores)]
+    sample_bp = sum(len(s) for s in slices)
+    pool = ref.make_pool(cores)
+    times, rows = [], None
+    for i in range(warmup + steps):
+        wall, _, rows = ref.run_slices(pool, slices, fs)
+        if i >= warmup:
+            times.append(wall)
+    pool.close()
+    dt = float(np.mean(times))
+    gbps = sample_bp / dt / 1e9
+    # the C port on the same bases (one thread per motif size), and its rows against the reference's
+    flat = np.frombuffer("".join(slices).encode("latin-1"), dtype=np.uint8)
+    port = cpu_baseline_run(flat)
+    port_rows = 0
+    same = True
+    for i, sl in enumerate(slices):
+        o = oracle.detect_repeats_by_k(sl, argparse.Namespace(**fs))
+        same = same and (o == rows[i])
+        port_rows += len(o)
+    return {"value": gbps, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+            "sample": f"{cores} slices of {slice_bp} bp from {sample_name} (from position {lo0}), {n_k} motif sizes, "
+                      f"{dt:.2f} s per pass, {steps} timed pass(es); UNMODIFIED Python reference (oracle/_ref, "
+                      f"detect_repeats as shipped, single-threaded), one process per host core; measured, not "
+                      f"extrapolated: the whole {total_bp} bp workload at this rate = {total_bp / gbps / 1e9 / 3600:.1f} h "
+                      f"on these {cores} cores",
+            "seconds_per_pass": dt,
+            "per_core_tracker_steps_per_s": sample_bp * n_k / dt / cores,
+            "port": {"value": port["bp"] / port["seconds"] / 1e9, "unit": "Gbp/s", "cores": port["threads"],
+                     "what": "C port of the tracker loop (oracle/crf_oracle.c) on the same bases, one thread per motif size",
+                     "rows_equal_reference": bool(same), "rows": port_rows},
+            "python": sys.version.split()[0]}
+
+
 def reference_arm(args):
     """--impl reference: the reference's own CPU implementation on this box's host cores, one JSON line.
 
@@ -178,44 +223,10 @@ def reference_arm(args):
         meta = {"workload": "S38-like single record (no GPU to generate the full genome)"}
         total_bp = record.size
         sample_name = "standalone 46.7 Mbp record"
-    fs = dict(min_motif_size=KMIN, max_motif_size=KMAX, min_repeats=MIN_REPEATS, min_span=MIN_SPAN)
     n_k = KMAX - KMIN + 1
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if ref.available():
-        ref.load()                                # import once; the fork()ed workers inherit it
-        slice_bp = max(1000, int(REF_SLICE_BP * 50 / n_k))
-        lo0 = min(record.size // 4, 2_000_000)    # past the telomeric N block
-        slice_bp = min(slice_bp, max(1, (record.size - lo0) // cores))
-        slices = [bytes(record[lo0 + i * slice_bp:lo0 + (i + 1) * slice_bp]).decode("latin-1") for i in range(cores)]
-        sample_bp = sum(len(s) for s in slices)
-        pool = ref.make_pool(cores)
-        times, rows = [], None
-        for i in range(args.warmup + args.steps):
-            wall, _, rows = ref.run_slices(pool, slices, fs)
-            if i >= args.warmup:
-                times.append(wall)
-        pool.close()
-        dt = float(np.mean(times))
-        gbps = sample_bp / dt / 1e9
-        # the C port on the same bases (one thread per motif size), and its rows against the reference's
-        flat = np.frombuffer("".join(slices).encode("latin-1"), dtype=np.uint8)
-        port = cpu_baseline_run(flat)
-        port_rows = 0
-        same = True
-        for i, sl in enumerate(slices):
-            o = oracle.detect_repeats_by_k(sl, argparse.Namespace(**fs))
-            same = same and (o == rows[i])
-            port_rows += len(o)
-        cpu = {"value": gbps, "unit": "Gbp/s", "cores": cores, "kind": "reference",
-               "sample": f"{cores} slices of {slice_bp} bp from {sample_name} (from position {lo0}), {n_k} motif sizes, "
-                         f"{dt:.2f} s per step; UNMODIFIED Python reference (oracle/_ref, detect_repeats as shipped, "
-                         f"single-threaded), one process per host core; measured, not extrapolated: the whole "
-                         f"{total_bp} bp workload at this rate = {total_bp / gbps / 1e9 / 3600:.1f} h on these {cores} cores",
-               "per_core_tracker_steps_per_s": sample_bp * n_k / dt / cores,
-               "port": {"value": port["bp"] / port["seconds"] / 1e9, "unit": "Gbp/s", "cores": port["threads"],
-                        "what": "C port of the tracker loop (oracle/crf_oracle.c) on the same bases, one thread per motif size",
-                        "rows_equal_reference": bool(same), "rows": port_rows},
-               "python": sys.version.split()[0]}
+        cpu = python_reference_sample(record, sample_name, total_bp, args.warmup, args.steps)
+        gbps, dt = cpu["value"], cpu["seconds_per_pass"]
     else:
         times = []
         for i in range(args.warmup + args.steps):
@@ -280,8 +291,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    from crf_b200 import multi
     ctx = _cabi.Context(local_rank)
-    stream = torch.cuda.Stream(device=dev)          # one stream for torch, NCCL waits and the library: the CUDA
+    stream = torch.cuda.Stream(device=dev)          # one stream for torch and the library: the CUDA
     torch.cuda.set_stream(stream)                   # events below see every kernel of the step
     ctx.set_stream(stream.cuda_stream)
 
@@ -293,111 +305,20 @@ def main():
     total_bp = int(offsets[-1])
     log(f"[rank {rank}] generated {meta['workload']} in {time.time() - t0:.1f}s")
 
-    # ---- this rank's share: contiguous (record, chunk) units with halo; reads are split by count ----
-    if args.workload == "sr":
-        n_rec = len(lengths)
-        lo_r, hi_r = n_rec * rank // world, n_rec * (rank + 1) // world
-        plan, mine = None, []
-        starts = offsets[lo_r:hi_r].astype(np.uint64)
-        lens = np.diff(offsets[lo_r:hi_r + 1]).astype(np.uint64)
-        own_lo = own_hi = None
-        n_units, my_bp = n_rec, int(lens.sum())
-    else:
-        plan = partition.Plan(lengths, world, chunk=args_chunk(world), halo=partition.DEFAULT_HALO,
-                              kmax=KMAX, min_repeats=MIN_REPEATS, min_span=MIN_SPAN)
-        mine = plan.units_of(rank)
-        starts, lens, own_lo, own_hi = plan.load_args(rank, offsets)
-        if world == 1:
-            own_lo = own_hi = None                      # whole records: nothing to own or stitch
-        n_units, my_bp = len(plan.units), int(sum(u.d1 - u.d0 for u in mine))
+    # ---- this rank's share: contiguous (record, chunk) units with halo; reads are split by count.  The whole N-rank data
+    # ---- path (scan, assembly, rows pushed into rank 0's buffer over NVLink) is crf_b200.multi.RankScan ----
     knobs = {"words_per_thread": args.words_per_thread} if args.words_per_thread else {}
-
-    seq = ctx.load_ranges(bases.data_ptr(), starts, lens, own_lo, own_hi, max_motif_cap=KMAX, on_device=True)
+    comm = multi.DistComm(dist, rank, world)
+    rs = multi.RankScan(ctx, comm, bases.data_ptr(), offsets[:-1], lengths, KMIN, KMAX, MIN_REPEATS, MIN_SPAN,
+                        on_device=True, chunk=args_chunk(world), reads=(args.workload == "sr"), knobs=knobs)
+    seq = rs.seq
     info = seq.info()
-
-    def one_step():
-        return seq.scan(KMIN, KMAX, MIN_REPEATS, MIN_SPAN, **knobs)
-
-    if world > 1 and plan is not None:   # results come out in chromosome coordinates; open-ended results are counted by the library
-        seq.set_output_map(out_record=[u.record for u in mine], out_shift=[u.d0 for u in mine],
-                           open_ended=[int(u.d1 < u.rec_len) for u in mine])
-    gstate = {"cap": 0, "buf": None, "out": None}
-    MAX_OPEN = 32
-
-    trace = {"on": False, "t": []}
-
-    def mark(name):
-        if trace["on"]:
-            torch.cuda.synchronize()
-            trace["t"].append((name, time.perf_counter()))
-
-    def gather_to_rank0(n):
-        """N > 1: compacted results -> rank 0 (the only collective of the path: one 16-byte all-gather of
-        (count, open count), one gather of the rows); runs that left their unit's data (longer than the halo)
-        are stitched first.  Returns the whole-job result count."""
-        if world == 1:
-            return n
-        n_open = int(seq.stats().n_open)
-        open_rows = seq.fetch_open() if (n_open and plan is not None) else np.zeros((0, 5), np.uint32)
-
-        def fetch_rows():                             # this rank's rows -> its slot of the gather buffer (device to device)
-            cap_, buf_ = gstate["cap"], gstate["buf"]
-            cols = [buf_[i * cap_:i * cap_ + n] for i in range(4)]
-            seq.fetch_device(*(c.data_ptr() for c in cols), n)
-            return cols
-        cols = fetch_rows() if gstate["cap"] >= n else None   # queued before the header exchange blocks the host
-        # one small all-gather carries every rank's row count and its open-ended rows (record, start, end, k)
-        hdr = torch.full((2 + 4 * MAX_OPEN,), -1, dtype=torch.int64)
-        hdr[0], hdr[1] = n, len(open_rows)
-        if 0 < len(open_rows) <= MAX_OPEN:
-            hdr[2:2 + 4 * len(open_rows)] = torch.from_numpy(open_rows[:, 1:].astype(np.int64).reshape(-1))
-        hdrs = torch.empty(world * hdr.numel(), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(hdrs, hdr.to(dev))
-        hdrs = hdrs.cpu().view(world, -1)
-        mark('hdr all-gather')
-        counts = hdrs[:, 0].tolist()
-        n_open_all = hdrs[:, 1].tolist()
-        if max(counts) > gstate["cap"]:
-            cap = int(max(counts) * 1.05) + 1024
-            gstate["cap"] = cap
-            gstate["buf"] = torch.zeros(4 * cap, dtype=torch.int32, device=dev)
-            gstate["out"] = [torch.empty_like(gstate["buf"]) for _ in range(world)] if rank == 0 else None
-            cols = None
-        if cols is None:
-            cols = fetch_rows()
-        buf, en = gstate["buf"], cols[2]
-        mark('fetch_device')
-        if sum(n_open_all) and plan is not None:      # a repeat longer than the halo crossed a unit end
-            run_end = lambda unit, lp, k: seq.run_end(unit.index - plan.bounds[rank], lp, k)   # noqa: E731
-            if max(n_open_all) <= MAX_OPEN:
-                open_all = [tuple(hdrs[r, 2 + 4 * i:6 + 4 * i].tolist()) for r in range(world) for i in range(n_open_all[r])]
-
-                def exchange(ans):                    # one all-reduce per hop
-                    t = torch.full((len(open_all),), -1, dtype=torch.int64)
-                    for i, v in ans.items():
-                        t[i] = v
-                    t = t.to(dev)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                    return {i: v for i, v in enumerate(t.cpu().tolist()) if v >= 0}
-                fixed = partition.stitch(plan, open_all, run_end, exchange, rank)
-            else:
-                fixed = partition.stitch_collective(plan, [tuple(int(x) for x in row[1:]) for row in open_rows],
-                                                    run_end, rank, world, dist, dev)
-            mine_fixed = {(r_, s_, k_): e_ for (r_, s_, e_, k_) in fixed}
-            for row in open_rows:
-                new_end = mine_fixed[(int(row[1]), int(row[2]), int(row[4]))]
-                seq.patch_end(int(row[0]), new_end)
-                en[int(row[0])] = new_end
-        mark('stitch')
-        dist.gather(buf, gstate["out"], dst=0)       # rank order == genome order: concatenation is the sorted result
-        torch.cuda.synchronize()                     # keep the NCCL copy kernels out of the next step's scan kernel:
-        mark('gather')                               # overlapped, they wait for free SMs and the steps queue up
-        return int(sum(counts))
+    my_bp, n_units, mine = rs.my_bp, rs.n_units, rs.units
 
     # ---- device-resident timing ----
     for _ in range(args.warmup):
-        n_res = one_step()
-        gather_to_rank0(n_res)
+        rs.step_async()
+        rs.finish()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -411,18 +332,36 @@ def main():
         dist.barrier()                               # all ranks enter the timed region together
     torch.cuda.synchronize()
     ev0.record(stream)
-    step_t = [time.perf_counter()]
-    for _ in range(args.steps):
-        n_res = one_step()
-        st_ = seq.stats()
+    if world == 1:
+        for _ in range(args.steps):                  # one synchronous crf_scan per step (its counters come back every time)
+            rs.step_async()
+            total_results = rs.finish()
+            st_ = seq.stats()
+            kernel_ms.append(st_.kernel_ms)
+            scan_ms.append(st_.scan_ms)
+            launches += st_.launches
+    else:
+        # N ranks: every step is kernel launches only -- counts and rows travel GPU to GPU -- so the K steps are queued back
+        # to back and the host waits once; finish() then checks the status word of every one of the K steps
+        done = 0
+        while done < args.steps:
+            burst = min(32, args.steps - done)
+            for _ in range(burst):
+                rs.step_async()
+            done += burst
+            if done < args.steps:
+                total_results = rs.finish()
+                if rs.steps_repeated:
+                    raise SystemExit("bench: a timed step had to be repeated (buffers were sized during warm-up?)")
+    ev1.record(stream)
+    if world > 1:
+        total_results = rs.finish()                  # one stream synchronisation; status of every queued step
+        if rs.steps_repeated:
+            raise SystemExit("bench: a timed step had to be repeated (buffers were sized during warm-up?)")
+        st_ = seq.stats()                            # events of the last step
         kernel_ms.append(st_.kernel_ms)
         scan_ms.append(st_.scan_ms)
-        launches += st_.launches
-        total_results = gather_to_rank0(n_res)
-        step_t.append(time.perf_counter())
-    if world > 1:
-        dist.barrier()
-    ev1.record(stream)
+        launches = st_.launches * args.steps
     torch.cuda.synchronize()
     elapsed_ms = ev0.elapsed_time(ev1)
     time.sleep(0.3)
@@ -433,27 +372,43 @@ def main():
         elapsed_ms = float(t.item())
         dist.barrier()
     ms_per_step = elapsed_ms / args.steps
-    if args.trace:
-        log(f"[rank {rank}] host time per timed step (ms): " + " ".join(f"{(b - a) * 1e3:.2f}" for a, b in zip(step_t, step_t[1:])))
-        trace["on"] = True
-        mark("start")
-        n_t = one_step()
-        mark("scan")
-        gather_to_rank0(n_t)
-        trace["on"] = False
-        t0_ = trace["t"][0][1]
-        log(f"[rank {rank}] trace: " + ", ".join(f"{nm} +{(t - t0_) * 1e3:.3f} ms" for nm, t in trace["t"][1:]))
+    if args.trace:                                   # device time of each stage of one more step, per rank
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        marks[0].record(stream)
+        rs.step_async()
+        marks[1].record(stream)
+        rs.finish()
+        st_ = seq.stats()
+        log(f"[rank {rank}] trace: scan kernel {st_.kernel_ms:.3f} ms, scan+assembly {st_.scan_ms:.3f} ms, "
+            f"whole step incl. push/settle {marks[0].elapsed_time(marks[1]):.3f} ms, rows {int(st_.n_results)}")
     value = total_bp / (ms_per_step * 1e-3) / 1e9
     stats = seq.stats()
 
-    # ---- end to end: host buffers in, results out, every step ----
-    e2e = None
-    span_lo, span_hi = int(starts.min()), int((starts + lens).max())   # this rank's contiguous share (+halo)
-    host = torch.empty(span_hi - span_lo, dtype=torch.uint8, pin_memory=True)
-    host.copy_(bases[span_lo:span_hi])
-    h_starts = starts - np.uint64(span_lo)
+    # ---- parity of what the step produced (rank 0 holds the whole job's rows) ----
+    parity = None
+    if rank == 0:
+        rec, st, en, kk = rs.fetch()
+        import hashlib
+        sha = hashlib.sha256()
+        for a_ in (rec, st, en, kk):
+            sha.update(np.ascontiguousarray(a_, dtype=np.uint32).tobytes())
+        parity = {"rows": int(len(rec)), "rows_sha256": sha.hexdigest()}
+        try:                                         # hash of the same workload's rows from a single-GPU run that was
+            with open(os.path.join(ROOT, "tests", "golden", "workload_rows_sha256.json")) as f:    # checked against the oracle
+                known = json.load(f).get(f"{args.workload}:{args.scale}:{KMIN}-{KMAX}")
+            parity["equals_single_gpu_run"] = (known == parity["rows_sha256"]) if known else None
+        except OSError:
+            parity["equals_single_gpu_run"] = None
+
+    # ---- end to end: host buffers in, results out (on rank 0), every step ----
+    span_lo, span_hi = rs.span()                                         # this rank's contiguous share (+halo)
+    host = torch.empty(max(span_hi - span_lo, 1), dtype=torch.uint8, pin_memory=True)
+    host[:span_hi - span_lo].copy_(bases[span_lo:span_hi])
     torch.cuda.synchronize()
-    host_np = host.numpy()
+    host_np = host.numpy()[:span_hi - span_lo]
     e2e_times = []
     pinned_out = None
     d2h = 0
@@ -462,14 +417,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        with ctx.load_ranges(host_np, h_starts, lens, own_lo, own_hi, max_motif_cap=KMAX, on_device=False) as s2:
-            n2 = s2.scan(KMIN, KMAX, MIN_REPEATS, MIN_SPAN, **knobs)
+        rs.reload(host_np, on_device=False, base_offset=span_lo)
+        rs.step_async()
+        n2 = rs.finish()
+        if rank == 0:
             if pinned_out is None or pinned_out.shape[1] < n2:          # result rows land in pinned host memory
                 pinned_out = torch.empty((4, int(n2 * 1.1) + 1024), dtype=torch.int32, pin_memory=True)
-            s2.fetch_host(*(pinned_out[j].data_ptr() for j in range(4)), pinned_out.shape[1])
+            if world == 1:
+                rs.seq.fetch_host(*(pinned_out[j].data_ptr() for j in range(4)), pinned_out.shape[1])
+            else:
+                rs.xchg.fetch_to(*(pinned_out[j].data_ptr() for j in range(4)), n2)
+            d2h = 16 * n2
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()                                              # the step ends when rank 0 holds the rows
         dt = time.perf_counter() - t0
-        d2h = 16 * n2
         if i > 0:
             e2e_times.append(dt)
     e2e_dt = float(np.mean(e2e_times))
@@ -477,15 +439,16 @@ def main():
         t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
-        tb = torch.tensor([float(host.numel()), float(d2h)], dtype=torch.float64, device=dev)
+        tb = torch.tensor([float(span_hi - span_lo), float(d2h)], dtype=torch.float64, device=dev)
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)
         h2d_total, d2h_total = int(tb[0].item()), int(tb[1].item())
     else:
-        h2d_total, d2h_total = host.numel(), d2h
+        h2d_total, d2h_total = span_hi - span_lo, d2h
     e2e = {"value": total_bp / e2e_dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d_total,
            "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_dt * 1e3}
 
     if rank != 0:
+        rs.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -530,7 +493,8 @@ def main():
         "traffic": traffic,
         "kernel": "crf::scan_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         "algorithmic_ops_per_launch": alg_ops, "algorithmic_bytes_per_launch": alg_bytes,
-        "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/r01_scan_kernel_ncu.txt)",
+        "traffic_unit": "bytes of DRAM read+write per launch; NOT measured in this run: replayed from the committed "
+                        "`ncu --set full` capture of the same kernel and workload (profiles/scan_kernel_traffic.json)",
         "peak_source": "INT32 ALU pipe (LOP3+SHF) measured live by crf_tools_alu_peak" if bound_int else hbm_src,
         "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": hbm_src},
         "stated_roofline_ms": max(t_hbm, t_int) * 1e3,
@@ -538,48 +502,57 @@ def main():
                 "per motif size at the ALU-pipe peak (SURVEY.md 8d); no tensor-core work on this path",
     }
 
-    # ---- CPU baseline on a bounded sample of the same workload + parity on that sample ----
+    # ---- parity on a sample at every N (the gathered rows of one record against the oracle), and at N = 1 the CPU
+    # ---- baseline: the Python reference on a bounded sample of the same workload, the C port beside it ----
+    from oracle import oracle, ref
+    r = 0 if len(lengths) == 1 else 20              # chr21 of S38 (46.7 Mbp x 50 motif sizes)
+    if args.workload == "sr":                       # reads: the first 200 000 reads, concatenated with N gaps
+        nr = min(200_000, len(lengths))
+        gapped = torch.full((nr, 150 + KMAX), ord("N"), dtype=torch.uint8, device=dev)
+        gapped[:, :150] = bases[:nr * 150].reshape(nr, 150)
+        sample = gapped.flatten().cpu().numpy()
+        sample_name = f"the first {nr} reads of the workload"
+    else:
+        sample = bases[int(offsets[r]):int(offsets[r + 1])].cpu().numpy()
+        sample_name = f"record {r} of the workload"
+    if not args.no_cpu_baseline:
+        res = cpu_baseline_run(sample)
+        o_s, o_e, o_m = res["rows"]
+        if args.workload == "sr":
+            o_rec = o_s // (150 + KMAX)
+            sel = rec < nr
+            ok = (np.array_equal(rec[sel], o_rec) and np.array_equal(st[sel], o_s - o_rec * (150 + KMAX)) and
+                  np.array_equal(en[sel], o_e - o_rec * (150 + KMAX)) and np.array_equal(kk[sel], o_m))
+        else:
+            sel = rec == r
+            ok = np.array_equal(st[sel], o_s) and np.array_equal(en[sel], o_e) and np.array_equal(kk[sel], o_m)
+        parity["parity_on_sample"] = bool(ok)
+        parity["sample"] = f"{sample_name}: {int(sel.sum())} gathered rows vs the oracle, row by row"
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = 0 if len(lengths) == 1 else 20          # chr21 of S38 (46.7 Mbp x 50 motif sizes)
-        if args.workload == "sr":                   # reads: the first 200 000 reads, concatenated with N gaps
-            nr = min(200_000, len(lengths))
-            block = bases[:nr * 150].reshape(nr, 150)
-            gapped = torch.full((nr, 150 + KMAX), ord("N"), dtype=torch.uint8, device=dev)
-            gapped[:, :150] = block
-            sample = gapped.flatten().cpu().numpy()
+        port = {"value": res["bp"] / res["seconds"] / 1e9, "unit": "Gbp/s", "cores": res["threads"],
+                "what": f"C port of the reference's tracker loop (oracle/crf_oracle.c) on {sample_name}, {res['bp']} bp x "
+                        f"{n_k} motif sizes, {res['seconds']:.2f} s, one thread per motif size"}
+        if ref.available() and args.workload != "sr":
+            cpu = python_reference_sample(sample, sample_name, total_bp, 0, 1)
+            cpu["port_on_whole_record"] = port
         else:
-            sample = bases[int(offsets[r]):int(offsets[r + 1])].cpu().numpy()
-        res = cpu_baseline_run(sample)
-        rec, st, en, kk = seq.fetch(int(stats.n_results))
-        unit_of_r = [i for i, u in enumerate(mine) if u.record == r]
-        parity = None
-        if len(unit_of_r) == 1 and args.workload != "sr":  # record scanned as one unit: compare row by row
-            sel = rec == unit_of_r[0]
-            o_s, o_e, o_m = res["rows"]
-            parity = bool(np.array_equal(st[sel], o_s) and np.array_equal(en[sel], o_e) and
-                          np.array_equal(kk[sel], o_m))
-        from oracle import oracle
-        cpu = {"value": res["bp"] / res["seconds"] / 1e9, "unit": "Gbp/s", "cores": res["threads"], "kind": "port",
-               "sample": f"record {r} of the workload, {res['bp']} bp x {n_k} motif sizes, {res['seconds']:.2f} s; "
-                         f"C port of the reference's tracker loop (oracle/crf_oracle.c), one thread per motif size, "
-                         f"host has {oracle.max_threads()} cores",
-               "parity_on_sample": parity}
+            cpu = dict(port, kind="port", sample=port.pop("what"))
+        cpu["parity_on_sample"] = parity.get("parity_on_sample")
 
     line = {
         "metric": metric_name(), "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": meta["workload"], "motif_sizes": [KMIN, KMAX], "min_repeats": MIN_REPEATS,
-                   "min_span": MIN_SPAN, "total_bp": total_bp, "results_per_step": int(total_results),
-                   "l2": "inputs larger than L2 (packed planes %.0f MB per GPU)" % (info.packed_bytes / 1e6),
-                   "partition": f"{n_units} (record, chunk) units over {world} rank(s)"},
+        "config": bench_config(meta["workload"], total_bp, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "results_per_step": int(total_results), "units": n_units,
         "scan_stats": {"scan_ms": float(np.mean(scan_ms)), "kernel_ms": k_ms, "candidates": int(stats.n_candidates),
                        "long_runs": int(stats.n_long), "spilled": int(stats.n_spilled), "tiles": int(stats.n_tiles)},
     }
     emit(line)
+    rs.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -4,7 +4,9 @@ This is the only way the Python host code reaches the GPU.  There is no CPU fall
 shared library is missing or a call fails, an exception is raised.
 """
 import ctypes
+import functools
 import os
+import threading
 
 import numpy as np
 
@@ -18,10 +20,16 @@ CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_C
 #: every symbol include/crf.h declares (tests check the library exports all of them)
 EXPORTS = [
     "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
-    "crf_ctx_synchronize", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
+    "crf_ctx_synchronize", "crf_load_limit", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
     "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end", "crf_write_rows",
     "crf_fasta_open", "crf_fasta_info", "crf_fasta_data", "crf_fasta_close",
+    "crf_xchg_create", "crf_xchg_destroy", "crf_xchg_export", "crf_xchg_connect_ipc", "crf_xchg_connect_local",
+    "crf_xchg_set_timeout", "crf_scan_gather", "crf_xchg_push", "crf_xchg_wait", "crf_xchg_fetch", "crf_xchg_patch_end",
 ]
+
+IPC_HANDLE_BYTES = 64
+XCHG_MAX_WORLD = 16
+XCHG_OK, XCHG_VOID_STEP, XCHG_ROOT_FULL, XCHG_TIMEOUT = range(4)
 
 
 class CrfError(RuntimeError):
@@ -48,6 +56,13 @@ class ScanStats(ctypes.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class XchgResult(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_uint32), ("worst_status", ctypes.c_uint32), ("steps_checked", ctypes.c_uint32),
+                ("step", ctypes.c_uint32), ("any_open", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("total_rows", ctypes.c_uint64), ("total_open", ctypes.c_uint64),
+                ("my_offset", ctypes.c_uint64), ("rows_of_rank", ctypes.c_uint64 * XCHG_MAX_WORLD)]
 
 
 _lib = None
@@ -86,9 +101,22 @@ def lib():
         L.crf_fasta_info.argtypes = [vp, P(u64), P(u64), P(i)]
         L.crf_fasta_data.argtypes = [vp, P(vp), P(vp), P(vp), P(u64)]
         L.crf_fasta_close.argtypes = [vp]
+        L.crf_xchg_create.argtypes = [vp, u32, u32, u64, P(vp)]
+        L.crf_xchg_destroy.argtypes = [vp]
+        L.crf_xchg_export.argtypes = [vp, vp]
+        L.crf_xchg_connect_ipc.argtypes = [vp, u32, vp]
+        L.crf_xchg_connect_local.argtypes = [vp, u32, vp]
+        L.crf_xchg_set_timeout.argtypes = [vp, ctypes.c_double]
+        L.crf_scan_gather.argtypes = [vp, P(ScanParams), vp]
+        L.crf_xchg_push.argtypes = [vp, vp]
+        L.crf_xchg_wait.argtypes = [vp, P(XchgResult)]
+        L.crf_xchg_fetch.argtypes = [vp, vp, vp, vp, vp, u64, u64, i]
+        L.crf_xchg_patch_end.argtypes = [vp, vp, vp, u32]
+        L.crf_load_limit.argtypes = [u32]
         for name in EXPORTS:
-            if name != "crf_last_error":
+            if name not in ("crf_last_error", "crf_load_limit"):
                 getattr(L, name).restype = i
+        L.crf_load_limit.restype = u64
         _lib = L
     return _lib
 
@@ -106,11 +134,28 @@ def _check(rc):
     raise CrfError(f"libcrf error {rc}: {msg}")
 
 
+def _serialised(method):
+    """Calls on one context (and on its sequences / exchange blocks) must not overlap (include/crf.h "Threading"):
+    api.get_context() hands the same Context to every thread of the process, so the binding takes the context's lock."""
+    @functools.wraps(method)
+    def wrapper(self, *a, **kw):
+        ctx = self if isinstance(self, Context) else (getattr(self, "ctx", None) or a[0])   # __init__(self, ctx, ...)
+        with ctx._lock:
+            return method(self, *a, **kw)
+    return wrapper
+
+
+def load_limit(max_motif_cap):
+    """Layout positions (sum of record length + max_motif_cap) one load can hold (crf_load_limit)."""
+    return int(lib().crf_load_limit(int(max_motif_cap)))
+
+
 class Context:
     """One CUDA device (crf_ctx)."""
 
     def __init__(self, device=0):
         self._h = ctypes.c_void_p()
+        self._lock = threading.RLock()
         self.device = device
         _check(lib().crf_ctx_create(device, ctypes.byref(self._h)))
 
@@ -145,6 +190,7 @@ class Context:
 class Sequence:
     """Records resident in HBM as packed planes (crf_seq)."""
 
+    @_serialised
     def __init__(self, ctx, bases, offsets, max_motif_cap, on_device, ranges=None):
         self.ctx = ctx
         self._h = ctypes.c_void_p()
@@ -189,6 +235,7 @@ class Sequence:
                                         ctypes.byref(self._h)))
         del keep
 
+    @_serialised
     def set_output_map(self, out_record=None, out_shift=None, open_ended=None):
         """Report results in the coordinates of the chromosomes the units were cut from (crf_seq_set_output_map)."""
         arrs = [None if a is None else np.ascontiguousarray(a, dtype=dt)
@@ -204,32 +251,53 @@ class Sequence:
         _check(lib().crf_seq_info(self._h, ctypes.byref(out)))
         return out
 
+    @staticmethod
+    def _params(min_motif_size, max_motif_size, min_repeats, min_span, knobs):
+        return ScanParams(int(min_motif_size), int(max_motif_size), int(min_repeats), int(min_span),
+                          int(knobs.get("words_per_thread", 0)), int(knobs.get("tile_out_cap", 0)),
+                          int(knobs.get("walk_limit_words", 0)), int(knobs.get("result_cap", 0)),
+                          int(knobs.get("flags", 0)))
+
+    @_serialised
     def scan(self, min_motif_size, max_motif_size, min_repeats, min_span, **knobs):
-        pr = ScanParams(int(min_motif_size), int(max_motif_size), int(min_repeats), int(min_span),
-                        int(knobs.get("words_per_thread", 0)), int(knobs.get("tile_out_cap", 0)),
-                        int(knobs.get("walk_limit_words", 0)), int(knobs.get("result_cap", 0)),
-                        int(knobs.get("flags", 0)))
+        pr = self._params(min_motif_size, max_motif_size, min_repeats, min_span, knobs)
         n = ctypes.c_uint64()
         _check(lib().crf_scan(self._h, ctypes.byref(pr), ctypes.byref(n)))
         return n.value
 
+    @_serialised
+    def scan_gather(self, xchg, min_motif_size, max_motif_size, min_repeats, min_span, **knobs):
+        """crf_scan_gather: scan + push of the rows to rank 0, asynchronous (Xchg.wait() tells how it went)."""
+        pr = self._params(min_motif_size, max_motif_size, min_repeats, min_span, knobs)
+        _check(lib().crf_scan_gather(self._h, ctypes.byref(pr), xchg._h))
+
+    @_serialised
+    def push(self, xchg):
+        """crf_xchg_push: rows of the last completed scan() -> rank 0 (asynchronous)."""
+        _check(lib().crf_xchg_push(self._h, xchg._h))
+
+    @_serialised
     def fetch(self, n):
         rec, start, end, k = (np.empty(n, np.uint32) for _ in range(4))
         _check(lib().crf_fetch(self._h, rec.ctypes.data, start.ctypes.data, end.ctypes.data, k.ctypes.data, n, 0))
         return rec, start, end, k
 
+    @_serialised
     def fetch_device(self, rec_ptr, start_ptr, end_ptr, k_ptr, capacity):
         _check(lib().crf_fetch(self._h, rec_ptr, start_ptr, end_ptr, k_ptr, capacity, 1))
 
+    @_serialised
     def fetch_host(self, rec_ptr, start_ptr, end_ptr, k_ptr, capacity):
         """Fetch into caller-owned host buffers given by address (e.g. pinned memory)."""
         _check(lib().crf_fetch(self._h, rec_ptr, start_ptr, end_ptr, k_ptr, capacity, 0))
 
+    @_serialised
     def stats(self):
         out = ScanStats()
         _check(lib().crf_scan_stats(self._h, ctypes.byref(out)))
         return out
 
+    @_serialised
     def fetch_open(self, cap=256):
         """(n, 5) uint32 rows (row index, record, start, end, k) of the open-ended results, in result order."""
         rows = np.zeros((cap, 5), np.uint32)
@@ -237,14 +305,17 @@ class Sequence:
         _check(lib().crf_fetch_open(self._h, rows.ctypes.data, cap, ctypes.byref(n)))
         return rows[:min(n.value, cap)]
 
+    @_serialised
     def patch_end(self, row, new_end):
         _check(lib().crf_patch_end(self._h, int(row), int(new_end)))
 
+    @_serialised
     def run_end(self, record, pos, k):
         out = ctypes.c_uint32()
         _check(lib().crf_run_end(self._h, int(record), int(pos), int(k), ctypes.byref(out)))
         return out.value
 
+    @_serialised
     def close(self):
         if self._h:
             lib().crf_seq_destroy(self._h)
@@ -255,6 +326,60 @@ class Sequence:
 
     def __exit__(self, *exc):
         self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Xchg:
+    """One rank's exchange block for the multi-GPU gather (crf_xchg, csrc/crf_xchg.cuh)."""
+
+    def __init__(self, ctx, rank, world, row_cap):
+        self.ctx, self.rank, self.world, self.row_cap = ctx, int(rank), int(world), int(row_cap)
+        self._h = ctypes.c_void_p()
+        _check(lib().crf_xchg_create(ctx._h, self.rank, self.world, self.row_cap, ctypes.byref(self._h)))
+
+    def export(self):
+        buf = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib().crf_xchg_export(self._h, buf))
+        return buf.raw
+
+    def connect_ipc(self, peer, handle):
+        buf = ctypes.create_string_buffer(bytes(handle), IPC_HANDLE_BYTES)
+        _check(lib().crf_xchg_connect_ipc(self._h, int(peer), buf))
+
+    def connect_local(self, peer, other):
+        _check(lib().crf_xchg_connect_local(self._h, int(peer), other._h))
+
+    def set_timeout(self, seconds):
+        _check(lib().crf_xchg_set_timeout(self._h, float(seconds)))
+
+    def wait(self):
+        res = XchgResult()
+        _check(lib().crf_xchg_wait(self._h, ctypes.byref(res)))
+        return res
+
+    def fetch(self, n, first=0):
+        rec, start, end, k = (np.empty(n, np.uint32) for _ in range(4))
+        _check(lib().crf_xchg_fetch(self._h, rec.ctypes.data, start.ctypes.data, end.ctypes.data, k.ctypes.data,
+                                    int(first), int(n), 0))
+        return rec, start, end, k
+
+    def fetch_to(self, rec_ptr, start_ptr, end_ptr, k_ptr, n, first=0, on_device=False):
+        _check(lib().crf_xchg_fetch(self._h, rec_ptr, start_ptr, end_ptr, k_ptr, int(first), int(n), int(bool(on_device))))
+
+    def patch_end(self, rows, new_end):
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        new_end = np.ascontiguousarray(new_end, dtype=np.uint32)
+        _check(lib().crf_xchg_patch_end(self._h, rows.ctypes.data, new_end.ctypes.data, rows.size))
+
+    def close(self):
+        if self._h:
+            lib().crf_xchg_destroy(self._h)
+            self._h = ctypes.c_void_p()
 
     def __del__(self):
         try:

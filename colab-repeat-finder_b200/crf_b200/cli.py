@@ -36,6 +36,11 @@ _OTHER_OPTIONS = [
     (("--verbose",), dict(action="store_true", help="Accepted for compatibility.")),
     (("--debug",), dict(action="store_true", help="Accepted for compatibility.")),
     (("--show-progress-bar",), dict(action="store_true", help="Accepted for compatibility.")),
+    # not in the reference: its scale-out is a separate Hail Batch pipeline (run_hail_batch_pipeline.py:96-123)
+    (("--devices",), dict(default=os.environ.get("CRF_DEVICES"),
+                          help="GPUs for whole-FASTA runs, e.g. 0-7 or 0,2,3 (default: $CRF_DEVICES, else one GPU). "
+                               "The records are cut into chunks, every GPU scans its share and the rows are gathered on "
+                               "the first one over NVLink; the BED file is identical to a single-GPU run.")),
 ]
 
 
@@ -64,35 +69,68 @@ def _check_filters(parser, args):
         parser.error(f"--min-span is set to {args.min_span}. It must be at least 1.")
 
 
-MAX_LOAD_BASES = 3_500_000_000   # one device load holds < 2^32 layout positions (records + gaps); larger files go in groups
+def parse_devices(text):
+    """"0-3" / "0,2,5" / "1" -> list of device indices (None or "" -> one device: api.default_device())."""
+    if text is None or str(text).strip() == "":
+        return [api.default_device()]
+    out = []
+    for part in str(text).split(","):
+        part = part.strip()
+        if "-" in part:
+            lo, hi = part.split("-", 1)
+            out.extend(range(int(lo), int(hi) + 1))
+        else:
+            out.append(int(part))
+    if not out or min(out) < 0:
+        raise ValueError(f"invalid device list {text!r}")
+    return out
+
+
+def group_records(lengths, max_motif_size, limit=None):
+    """Cut the record list into consecutive groups that each fit one device load: a load lays every record out
+    as length + max_motif_size positions and holds at most crf_load_limit() of them (32-bit positions on the
+    device).  A single record above the limit is its own group (and is refused by the load with a clear message).
+    Returns [(first, last)), ...]."""
+    limit = _cabi.load_limit(max_motif_size) if limit is None else limit
+    groups, first, n = [], 0, len(lengths)
+    while first < n:
+        last, need = first, 0
+        while last < n and (last == first or need + int(lengths[last]) + max_motif_size <= limit):
+            need += int(lengths[last]) + max_motif_size
+            last += 1
+        groups.append((first, last))
+        first = last
+    return groups
 
 
 def _whole_fasta_to_bed(fa, args, bed_path):
-    """Every record of the file: as few loads as the 2^32-position limit allows (one for a human genome), one scan
-    per load, native row writer.  The groups are slices of the reader's buffer (no copies on the Python side).
-    Returns the row count per record."""
-    ctx = api.get_context()
+    """Every record of the file: as few loads as the position limit allows (one for a human genome), one scan per
+    load (on one GPU, or split over --devices), native row writer.  The groups are slices of the reader's buffer (no
+    copies on the Python side).  Returns the row count per record."""
+    devices = parse_devices(getattr(args, "devices", None))
     lengths = np.diff(fa.offsets.astype(np.int64))
     counts = np.zeros(fa.n_records, dtype=np.int64)
     open(bed_path, "wb").close()
-    first = 0
-    while first < fa.n_records:
-        last, total = first, 0
-        while last < fa.n_records and (last == first or total + int(lengths[last]) <= MAX_LOAD_BASES):
-            total += int(lengths[last])
-            last += 1
+    for first, last in group_records(lengths, args.max_motif_size):
+        total = int(lengths[first:last].sum())
         base0 = int(fa.offsets[first])
         blob = fa.bases[base0:base0 + total]
         offsets = fa.offsets[first:last + 1] - np.uint64(base0)
         if total:
-            with ctx.load(blob, offsets, max_motif_cap=args.max_motif_size) as seq:
-                n = seq.scan(args.min_motif_size, args.max_motif_size, args.min_repeats, args.min_span)
-                rec, start, end, k = seq.fetch(n)
+            if len(devices) > 1:
+                from . import multi
+                many_short = (last - first) > 4096 and int(lengths[first:last].max()) < (1 << 20)
+                rec, start, end, k = multi.scan_on_devices(
+                    devices, blob, offsets[:-1], lengths[first:last], args.min_motif_size, args.max_motif_size,
+                    args.min_repeats, args.min_span, reads=many_short, contexts=[api.get_context(d) for d in devices])
+            else:
+                with api.get_context(devices[0]).load(blob, offsets, max_motif_cap=args.max_motif_size) as seq:
+                    n = seq.scan(args.min_motif_size, args.max_motif_size, args.min_repeats, args.min_span)
+                    rec, start, end, k = seq.fetch(n)
             whole_file = first == 0 and last == fa.n_records          # the usual case: hand the name table over as it is
             _cabi.write_rows(bed_path, fa.names_blob if whole_file else fa.names[first:last], blob, offsets, rec, start,
                              end, k, append=True)
             np.add.at(counts, rec.astype(np.int64) + first, 1)
-        first = last
     return counts
 
 

@@ -1,0 +1,299 @@
+"""Multi-GPU scan: every rank scans its share of the (record, chunk) units and the GPUs concatenate their sorted
+rows on rank 0 over NVLink peer memory (crf_xchg, csrc/crf_xchg.cuh) -- no host round trip inside a step.
+
+The B200-native counterpart of the reference's scale-out (hail_batch_pipeline/run_hail_batch_pipeline.py:76-77,
+96-123, 153: one CPU job per 500 kb interval, BED files concatenated, `sort | uniq`).  Two ways to run N ranks:
+
+  * one process per GPU (torchrun): `DistComm(torch.distributed)`; exchange blocks are shared through CUDA IPC;
+  * one process, one thread per GPU (the CLI's --devices): `ThreadComm`; plain peer access.
+
+Either way the step is `RankScan.step_async()` on every rank (kernel launches only) and `RankScan.finish()` (one
+stream synchronisation; the rare cases -- a buffer outgrown, a repeat longer than the halo -- are settled there).
+"""
+import threading
+
+import numpy as np
+
+from . import _cabi, partition
+
+
+class DistComm:
+    """Ranks are processes of a torch.distributed group (any backend).  Used at set-up (IPC handles) and for the
+    rare stitch of runs longer than the halo; never inside a step."""
+    same_process = False
+
+    def __init__(self, dist, rank, world):
+        self.dist, self.rank, self.world = dist, rank, world
+
+    def allgather_obj(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+class ThreadComm:
+    """Ranks are threads of this process, one per device (ThreadComm.split(world) gives one endpoint per rank)."""
+    same_process = True
+
+    class _Shared:
+        def __init__(self, world):
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots = [None] * world
+
+    def __init__(self, shared, rank):
+        self._s, self.rank, self.world = shared, rank, shared.world
+
+    @classmethod
+    def split(cls, world):
+        shared = cls._Shared(world)
+        return [cls(shared, r) for r in range(world)]
+
+    def allgather_obj(self, obj):
+        s = self._s
+        s.slots[self.rank] = obj
+        s.barrier.wait()
+        out = list(s.slots)
+        s.barrier.wait()
+        return out
+
+
+def default_row_cap(total_bp):
+    """Rows rank 0's buffer holds: 1 per 32 bp of the whole job (a human genome has ~2 per kbp), 16 bytes each."""
+    return int(min(0xFFFFFFF0, max(1 << 20, total_bp // 32)))
+
+
+def global_rows(rows_of_rank, rank, local_rows):
+    """Row numbers inside rank 0's buffer of `rank`'s local result rows (rank order = genome order)."""
+    offsets = np.concatenate([[0], np.cumsum(np.asarray(rows_of_rank, dtype=np.int64))])
+    return np.asarray(local_rows, dtype=np.int64) + int(offsets[rank])
+
+
+class RankScan:
+    """One rank (one GPU) of a partitioned scan.
+
+    bases / record_starts / lengths describe ALL records (every rank sees the same description; `bases` is this
+    rank's view of the bytes: a host array or, with on_device, a device pointer).  reads=True splits the records by
+    count instead of cutting them into chunks (config C5: many short independent sequences)."""
+
+    def __init__(self, ctx, comm, bases, record_starts, lengths, kmin, kmax, min_repeats, min_span, on_device=False,
+                 chunk=partition.DEFAULT_CHUNK, halo=partition.DEFAULT_HALO, reads=False, row_cap=None, knobs=None,
+                 timeout_s=None, base_offset=0):
+        self.ctx, self.comm = ctx, comm
+        self.rank, self.world = comm.rank, comm.world
+        self.filters = (int(kmin), int(kmax), int(min_repeats), int(min_span))
+        self.knobs = dict(knobs or {})
+        lengths = [int(x) for x in lengths]
+        self.total_bp = int(sum(lengths))
+        self.reads = reads
+        if reads:
+            n_rec = len(lengths)
+            lo, hi = n_rec * self.rank // self.world, n_rec * (self.rank + 1) // self.world
+            self.plan, self.units = None, []
+            self.first_record = lo
+            starts = np.asarray(record_starts[lo:hi], dtype=np.uint64)
+            lens = np.asarray(lengths[lo:hi], dtype=np.uint64)
+            own_lo = own_hi = None
+            self.my_bp = int(lens.sum())
+            self.n_units = n_rec
+        else:
+            whole = self.world == 1 and chunk >= max(lengths + [1])
+            self.plan = partition.Plan(lengths, self.world, chunk=chunk, halo=halo, kmax=kmax, min_repeats=min_repeats,
+                                       min_span=min_span)
+            self.units = self.plan.units_of(self.rank)
+            starts, lens, own_lo, own_hi = self.plan.load_args(self.rank, record_starts)
+            if whole:
+                own_lo = own_hi = None
+            self.my_bp = int(sum(u.u1 - u.u0 for u in self.units))
+            self.n_units = len(self.plan.units)
+        self.load_args = (starts, lens, own_lo, own_hi)
+        self.seq = None
+        self.reload(bases, on_device=on_device, base_offset=base_offset)
+        self.xchg = None
+        if self.world > 1:
+            self.xchg = _cabi.Xchg(ctx, self.rank, self.world, row_cap or default_row_cap(self.total_bp))
+            if timeout_s:
+                self.xchg.set_timeout(timeout_s)
+            if comm.same_process:
+                peers = comm.allgather_obj(self.xchg)
+                for r, other in enumerate(peers):
+                    if r != self.rank:
+                        self.xchg.connect_local(r, other)
+                comm.allgather_obj(None)               # every rank is connected before anyone pushes
+            else:
+                handles = comm.allgather_obj(self.xchg.export())
+                for r, h in enumerate(handles):
+                    if r != self.rank:
+                        self.xchg.connect_ipc(r, h)
+                comm.allgather_obj(None)
+        self.last = None
+
+    def span(self):
+        """[lo, hi) of the caller's base buffer this rank reads (its units plus their halos)."""
+        starts, lens = self.load_args[0], self.load_args[1]
+        if not len(starts):
+            return 0, 0
+        return int(starts.min()), int((starts + lens).max())
+
+    def reload(self, bases, on_device=False, base_offset=0):
+        """(Re-)upload this rank's share.  `bases` starts at position `base_offset` of the buffer the record_starts refer
+        to (a rank that keeps only its own span() on the host passes span()[0])."""
+        if self.seq is not None:
+            self.seq.close()
+            self.seq = None
+        starts, lens, own_lo, own_hi = self.load_args
+        kmax = self.filters[1]
+        if len(starts):
+            self.seq = self.ctx.load_ranges(bases, starts - np.uint64(base_offset), lens, own_lo, own_hi,
+                                            max_motif_cap=kmax, on_device=on_device)
+            if self.reads:
+                if self.world > 1:
+                    self.seq.set_output_map(out_record=np.arange(self.first_record, self.first_record + len(starts),
+                                                                 dtype=np.uint32))
+            elif self.world > 1 or own_lo is not None:
+                self.seq.set_output_map(out_record=[u.record for u in self.units], out_shift=[u.d0 for u in self.units],
+                                        open_ended=[int(u.d1 < u.rec_len) for u in self.units])
+        elif self.world > 1:
+            # a rank without units still takes part in the exchange: it pushes zero rows (an empty record to scan)
+            self.seq = self.ctx.load_ranges(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(1, np.uint64),
+                                            max_motif_cap=kmax)
+
+    # ---- the step -------------------------------------------------------------------------------------------
+    def step_async(self):
+        """Queue one whole step on this rank's stream (scan, assembly, push to rank 0); returns at once."""
+        kmin, kmax, mr, ms = self.filters
+        if self.world == 1:
+            self._n = self.seq.scan(kmin, kmax, mr, ms, **self.knobs)
+        else:
+            self.seq.scan_gather(self.xchg, kmin, kmax, mr, ms, **self.knobs)
+
+    def finish(self):
+        """Wait for the queued steps; settle the rare cases.  Returns the whole-job row count (the rows are on rank 0)."""
+        if self.world == 1:
+            self.last = None
+            if self.plan is not None and self.load_args[2] is not None and self.seq.stats().n_open:
+                self._stitch_local()
+            return self._n
+        kmin, kmax, mr, ms = self.filters
+        res = self.xchg.wait()
+        self.steps_repeated = 0
+        if res.worst_status == _cabi.XCHG_VOID_STEP:
+            # some rank outgrew a buffer (first step of a new workload, usually): every rank repeats the step the slow
+            # way -- crf_scan sizes everything -- and pushes again; the status is the same on all ranks, so all agree
+            self.seq.scan(kmin, kmax, mr, ms, **self.knobs)
+            self.seq.push(self.xchg)
+            res = self.xchg.wait()
+            self.steps_repeated = 1
+        if res.worst_status == _cabi.XCHG_ROOT_FULL:
+            raise _cabi.CrfError(f"{res.total_rows} rows do not fit rank 0's gather buffer ({self.xchg.row_cap} rows): "
+                                 f"pass a larger row_cap")
+        if res.worst_status != _cabi.XCHG_OK:
+            raise _cabi.CrfError(f"multi-GPU gather failed with status {res.worst_status}")
+        self.last = res
+        if res.any_open and self.plan is not None:
+            self._stitch(res)
+        return int(res.total_rows)
+
+    def _stitch(self, res):
+        """A repeat longer than the halo reached the end of its unit's data: follow it on whoever holds the next bases
+        (crf_run_end), hop by hop, then patch the ends inside rank 0's buffer.  Rare; host-driven."""
+        n_open = int(self.seq.stats().n_open)
+        mine = self.seq.fetch_open(cap=max(n_open, 1)) if n_open else np.zeros((0, 5), np.uint32)
+        per_rank = self.comm.allgather_obj([tuple(int(x) for x in row) for row in mine])
+        open_all = [row[1:] for part in per_rank for row in part]          # (record, start, end_lower_bound, k)
+        first = self.plan.bounds[self.rank]
+
+        def run_end(unit, local_pos, k):
+            return self.seq.run_end(unit.index - first, local_pos, k)
+
+        def exchange(answers):
+            merged = {}
+            for part in self.comm.allgather_obj(answers):
+                merged.update(part)
+            return merged
+
+        fixed = partition.stitch(self.plan, open_all, run_end, exchange, self.rank)
+        if self.rank == 0:
+            rows, ends, i = [], [], 0
+            for r, part in enumerate(per_rank):
+                g = global_rows(res.rows_of_rank[:self.world], r, [row[0] for row in part])
+                for j in range(len(part)):
+                    rows.append(int(g[j]))
+                    ends.append(fixed[i][2])
+                    i += 1
+            self.xchg.patch_end(rows, ends)
+
+    def _stitch_local(self):
+        """One rank, records cut into chunks: finish the open-ended rows in place."""
+        rows = self.seq.fetch_open(cap=int(self.seq.stats().n_open))
+        fixed = partition.stitch(self.plan, [tuple(int(x) for x in r[1:]) for r in rows],
+                                 lambda unit, lp, k: self.seq.run_end(unit.index, lp, k))
+        for row, (_r, _s, e, _k) in zip(rows, fixed):
+            self.seq.patch_end(int(row[0]), e)
+
+    def fetch(self):
+        """Rank 0: the whole job's rows (record, start, end, k), sorted by (record, start, end)."""
+        if self.world == 1:
+            rec, st, en, k = self.seq.fetch(self._n)
+            if self.plan is not None and self.load_args[2] is None:
+                rec = np.array([u.record for u in self.units], dtype=np.uint32)[rec] if len(rec) else rec
+            return rec, st, en, k
+        if self.rank != 0:
+            raise _cabi.CrfError("the gathered rows live on rank 0")
+        return self.xchg.fetch(int(self.last.total_rows))
+
+    def close(self):
+        if self.seq is not None:
+            self.seq.close()
+            self.seq = None
+        if self.xchg is not None:
+            self.comm.allgather_obj(None)              # nobody still pushes into a block that is about to go away
+            self.xchg.close()
+            self.xchg = None
+
+
+def scan_on_devices(devices, bases, record_starts, lengths, kmin, kmax, min_repeats, min_span, chunk=partition.DEFAULT_CHUNK,
+                    halo=partition.DEFAULT_HALO, reads=False, contexts=None, knobs=None, timeout_s=None):
+    """One process, one thread per device: scan host `bases` on all `devices`; returns (record, start, end, k) of the
+    whole job.  `contexts`: reuse these _cabi.Context objects (one per device) instead of creating new ones."""
+    world = len(devices)
+    comms = ThreadComm.split(world)
+    ctxs = list(contexts) if contexts else [_cabi.Context(d) for d in devices]
+    for i in range(world):                     # ranks never share a context (= a stream): a rank waits for its peers
+        if any(ctxs[i] is c for c in ctxs[:i]):
+            ctxs[i] = _cabi.Context(devices[i])
+    out, errors = {}, []
+
+    def work(rank):
+        rs = None
+        try:
+            rs = RankScan(ctxs[rank], comms[rank], bases, record_starts, lengths, kmin, kmax, min_repeats, min_span,
+                          chunk=chunk, halo=halo, reads=reads, knobs=knobs, timeout_s=timeout_s)
+            rs.step_async()
+            rs.finish()
+            if rank == 0:
+                out["rows"] = rs.fetch()
+        except BaseException as exc:          # noqa: BLE001 -- re-raised in the caller's thread
+            errors.append(exc)
+            comms[rank]._s.barrier.abort()
+        finally:
+            try:
+                if rs is not None:
+                    rs.close()
+            except threading.BrokenBarrierError:
+                pass
+
+    if world == 1:
+        work(0)
+    else:
+        threads = [threading.Thread(target=work, args=(r,), name=f"crf-rank{r}") for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        real = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or errors)[0]
+    return out["rows"]

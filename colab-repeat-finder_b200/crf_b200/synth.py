@@ -61,6 +61,12 @@ class _Backend:
             return self.torch.empty(n, dtype=self.torch.uint8, device=self.device)
         return np.empty(n, dtype=np.uint8)
 
+    def sync(self):
+        """The generators run on torch's stream, the library on its own: the bytes must be complete before a device
+        pointer is handed to crf_seq_load_ascii."""
+        if self.torch and self.device.type == "cuda":
+            self.torch.cuda.synchronize(self.device)
+
 
 def hash32(x):
     """lowbias32 on int64 arrays holding values in [0, 2^32) (wrap-around products are masked)."""
@@ -153,6 +159,7 @@ def generate_records(lengths, seed, device=None, kmax=50, lower_case=True, telom
         idx = be.arange(0, ln) % k
         out[int(offsets[r]) + s:int(offsets[r]) + s + ln] = reps[idx]
         meta["satellites"].append((r, s, s + ln, k))
+    be.sync()
     return out, offsets, meta
 
 
@@ -177,6 +184,7 @@ def s22(device=None, scale=1.0, seed=22):
         return int(x * scale)
     for s, e in [(0, 10_510_000), (12_904_726, 15_168_968), (18_238_733, 18_339_255), (50_808_468, 50_818_468)]:
         bases[sc(s):min(length, sc(e))] = ord("N")
+    _Backend(device).sync()
     meta["names"] = ["chr22"]
     meta["workload"] = f"S22 synthetic chr22-shaped record, {length} bp, seed {seed}"
     return bases, offsets, meta
@@ -196,6 +204,7 @@ def sr(n_reads, read_len=150, device=None, seed=150):
         seg = bases[lo:lo + p.shape[0]]
         n_byte = seg * 0 + ord("N")
         bases[lo:lo + p.shape[0]] = be.where(is_n, n_byte, seg)
+    be.sync()
     offsets = np.arange(0, total + 1, read_len, dtype=np.uint64)
     meta["workload"] = f"SR {n_reads} reads x {read_len} bp, seed {seed}"
     return bases, offsets, meta
@@ -232,6 +241,7 @@ def sx(length, chunk, device=None, seed=4, kset=(1, 2, 3, 7, 16, 31, 32, 33, 50)
         bases[length - 20_000:length - 19_000] = ord("N")
         bases[length - 19_000:length - 15_000] = be.from_numpy(lut[np.array([0, 3])])[be.arange(0, 4000) % 2]
         bases[length - 15_000:length - 14_990] = ord("N")
+    be.sync()
     meta["planted"] = planted
     meta["workload"] = f"SX chunk-crossing repeats, {length} bp, chunk {chunk}, seed {seed}"
     return bases, offsets, meta

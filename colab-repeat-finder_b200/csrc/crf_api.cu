@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <unordered_map>
 #include <utility>
 #include <new>
@@ -16,6 +17,7 @@
 #include "../../include/crf.h"
 #include "crf_aux.cuh"
 #include "crf_scan.cuh"
+#include "crf_xchg.cuh"
 
 using namespace crf;
 
@@ -53,9 +55,15 @@ struct crf_ctx {
     cudaStream_t stream;
     cudaStream_t copy_stream = nullptr;                 // host -> device chunks of a pipelined upload (load_impl)
     cudaEvent_t copy_done = nullptr;
+    std::mutex mu;                                      // guards cache / live (sequences of one context may be destroyed
+                                                        // from another thread than the one that is loading)
     std::vector<std::pair<void *, size_t>> cache;       // free blocks
     std::unordered_map<void *, size_t> live;            // blocks handed out -> size
     size_t cached_bytes = 0;
+    // timing events and the page-locked counter block are per context, not per load: creating them cost more than a
+    // small scan (calls on one context are serialised by the caller, crf.h)
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long *h_counters = nullptr;
 };
 static const size_t CACHE_LIMIT_BYTES = 24ull << 30;
 static thread_local crf_ctx *g_ctx = nullptr;          // context of the API call in progress
@@ -63,6 +71,8 @@ static thread_local crf_ctx *g_ctx = nullptr;          // context of the API cal
 static cudaError_t ctx_malloc(void **p, size_t bytes) {
     bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
     crf_ctx *c = g_ctx;
+    std::unique_lock<std::mutex> lock;
+    if (c) lock = std::unique_lock<std::mutex>(c->mu);
     if (c) {
         size_t best = (size_t)-1;
         for (size_t i = 0; i < c->cache.size(); ++i) {
@@ -91,6 +101,8 @@ static cudaError_t ctx_malloc(void **p, size_t bytes) {
 static void ctx_free(void *p) {
     if (!p) return;
     crf_ctx *c = g_ctx;
+    std::unique_lock<std::mutex> lock;
+    if (c) lock = std::unique_lock<std::mutex>(c->mu);
     if (c) {
         auto it = c->live.find(p);
         if (it != c->live.end()) {
@@ -105,6 +117,18 @@ static void ctx_free(void *p) {
     }
     cudaFree(p);
 }
+
+// Everything one scan launch needs; kept with the sequence so that a second assembly pass (long spill list, more
+// open-ended rows than the list held) and the statistics can be produced after the counters have come back.
+struct ScanPlan {
+    crf_scan_params pr;
+    int T;
+    uint32_t n_tiles, outcap, ggrid, tgrid, launches;
+    size_t smem;
+    bool single_copy;
+    GatherParams g;
+    TranslateParams tp;
+};
 
 struct crf_seq {
     crf_ctx *ctx = nullptr;
@@ -130,8 +154,10 @@ struct crf_seq {
     uint32_t *o_rec = nullptr, *o_start = nullptr, *o_end = nullptr, *o_k = nullptr;
     uint32_t *tile_cnt = nullptr, *tile_base = nullptr, *tile_off = nullptr;
     uint32_t tiles_cap = 0;
-    unsigned long long *d_counters = nullptr, *h_counters = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long *d_counters = nullptr, *h_counters = nullptr;   // h_counters: the context's page-locked block
+    cudaEvent_t *ev = nullptr;                                         // the context's events
+    uint32_t open_cap = 0;                                             // rows d_open_rows holds
+    ScanPlan *plan = nullptr;                                          // launch parameters of the scan in flight / last run
     crf_scan_stats_t stats = {};
     crf_seq_info_t info = {};
     uint64_t n_results = 0;
@@ -173,6 +199,9 @@ extern "C" int crf_ctx_create(int device, crf_ctx **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming);
+    for (auto &ev : c->ev)
+        if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_counters, C_COUNT * sizeof(unsigned long long));
     if (e != cudaSuccess) { delete c; set_err("cudaStreamCreate failed: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
     c->stream = c->own_stream;
     *out = c;
@@ -188,6 +217,9 @@ extern "C" int crf_ctx_destroy(crf_ctx *c) {
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->copy_done);
+    for (auto &ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
     delete c;
     return CRF_OK;
 }
@@ -242,15 +274,19 @@ static void free_seq(crf_seq *s) {
     dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
     dev_free(s->tile_cnt); dev_free(s->tile_base); dev_free(s->tile_off);
     dev_free(s->d_counters);
-    if (s->h_counters) cudaFreeHost(s->h_counters);
-    for (auto &e : s->ev)
-        if (e) cudaEventDestroy(e);
+    delete s->plan;
     delete s;
 }
 
 static const uint32_t EX_CAP = 1u << 22;       // exotic symbols kept per load
 static const uint32_t TILE_WORDS_MAX = 4096;   // THREADS * 16
 static const uint32_t MAX_K = 65535;
+
+static uint64_t layout_limit(uint32_t max_motif_cap) {
+    return 0xFFFFFFFFull - 32ull * (2ull * TILE_WORDS_MAX + (max_motif_cap >> 5) + 64);
+}
+// One load holds at most this many layout positions: sum over records of (length + max_motif_cap).
+extern "C" uint64_t crf_load_limit(uint32_t max_motif_cap) { return layout_limit(max_motif_cap); }
 
 static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, const uint64_t *lengths,
                      const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
@@ -259,17 +295,18 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     s->ctx = c;
     s->n_records = n_records;
     s->cap = max_motif_cap;
-    for (auto &e : s->ev) CU(cudaEventCreate(&e));
-    CU(cudaMallocHost((void **)&s->h_counters, C_COUNT * sizeof(unsigned long long)));
+    s->ev = c->ev;
+    s->h_counters = c->h_counters;
     CHECK(dev_alloc(&s->d_counters, C_COUNT));
-    CHECK(dev_alloc(&s->d_open_rows, 5 * OPEN_CAP));
+    s->open_cap = OPEN_CAP_INITIAL;
+    CHECK(dev_alloc(&s->d_open_rows, 5 * (size_t)s->open_cap));
 
     // layout: record r at dev_off[r], followed by a gap of max_motif_cap masked positions
     s->h_rec_dev_off.resize(n_records);
     s->h_rec_len.resize(n_records);
     std::vector<uint32_t> len32(n_records);
     uint64_t pos = 0, total = 0, src_lo = ~0ull, src_hi = 0;
-    const uint64_t limit = 0xFFFFFFFFull - 32ull * (2ull * TILE_WORDS_MAX + (max_motif_cap >> 5) + 64);
+    const uint64_t limit = layout_limit(max_motif_cap);
     for (uint32_t r = 0; r < n_records; ++r) {
         const uint64_t len = lengths[r];
         if (pos > limit || len > limit) { pos = limit + 1; break; }
@@ -601,8 +638,7 @@ static int launch_scan(const ScanParams &sp, uint32_t n_tiles, size_t smem, cuda
     return CRF_OK;
 }
 
-extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_results) {
-    if (!s || !pr) { set_err("crf_scan: null argument"); return CRF_ERR_ARG; }
+static int scan_validate(const crf_seq *s, const crf_scan_params *pr) {
     // the four checks of perfect_repeat_finder.py:23-30
     if (pr->min_motif_size < 1) { set_err("min_motif_size is set to %u. It must be at least 1.", pr->min_motif_size); return CRF_ERR_ARG; }
     if (pr->max_motif_size < pr->min_motif_size) { set_err("max_motif_size is set to %u. It must be at least min_motif_size.", pr->max_motif_size); return CRF_ERR_ARG; }
@@ -619,13 +655,17 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
     }
     const int T = pr->words_per_thread ? (int)pr->words_per_thread : 8;
     if (T != 1 && T != 2 && T != 4 && T != 8 && T != 16) { set_err("words_per_thread must be 1, 2, 4, 8 or 16"); return CRF_ERR_ARG; }
+    const uint32_t outcap = pr->tile_out_cap ? pr->tile_out_cap : 1024;
+    if (outcap > 4096) { set_err("tile_out_cap must be <= 4096"); return CRF_ERR_ARG; }
+    return CRF_OK;
+}
+
+// per-k table, tile arrays, launch geometry (no kernel launches; one blocking upload when the filters changed)
+static int scan_prepare(crf_seq *s, const crf_scan_params *pr, ScanPlan &pl) {
     crf_ctx *c = s->ctx;
     cudaStream_t st = c->stream;
-    CU(cudaSetDevice(c->device));
-    g_ctx = c;
-    s->have_results = false;
-
-    // per-k table
+    pl.pr = *pr;
+    pl.T = pr->words_per_thread ? (int)pr->words_per_thread : 8;
     if (s->ktab_cap < pr->max_motif_size + 1) {
         dev_free(s->d_ktab);
         s->ktab_cap = 0;
@@ -655,80 +695,138 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
         CU(cudaStreamSynchronize(st));  // tab / segs are locals
         s->ktab_for = *pr;
     }
-
-    const uint32_t TW = THREADS * T;
-    const uint32_t n_tiles = (s->n_words + TW - 1) / TW;
-    if (s->tiles_cap < n_tiles + 1) {
+    const uint32_t TW = THREADS * pl.T;
+    pl.n_tiles = (s->n_words + TW - 1) / TW;
+    if (s->tiles_cap < pl.n_tiles + 1) {
         dev_free(s->tile_cnt); dev_free(s->tile_base); dev_free(s->tile_off);
         s->tiles_cap = 0;
-        CHECK(dev_alloc(&s->tile_cnt, (size_t)n_tiles + 8));   // slack: tile_offsets_kernel reads uint4
-        CHECK(dev_alloc(&s->tile_base, (size_t)n_tiles + 1));
-        CHECK(dev_alloc(&s->tile_off, (size_t)n_tiles + 1));
-        s->tiles_cap = n_tiles + 1;
+        CHECK(dev_alloc(&s->tile_cnt, (size_t)pl.n_tiles + 8));   // slack: tile_offsets_kernel reads uint4
+        CHECK(dev_alloc(&s->tile_base, (size_t)pl.n_tiles + 1));
+        CHECK(dev_alloc(&s->tile_off, (size_t)pl.n_tiles + 1));
+        s->tiles_cap = pl.n_tiles + 1;
     }
-    uint32_t cap = pr->result_cap ? pr->result_cap : std::max<uint32_t>(1u << 16, s->layout_len / 96);
-    cap = std::max(cap, s->res_cap);
-    const uint32_t outcap = pr->tile_out_cap ? pr->tile_out_cap : 1024;
-    if (outcap > 4096) { set_err("tile_out_cap must be <= 4096"); return CRF_ERR_ARG; }
-    const size_t smem = scan_smem_bytes(T, pr->max_motif_size, outcap);
+    pl.outcap = pr->tile_out_cap ? pr->tile_out_cap : 1024;
+    pl.smem = scan_smem_bytes(pl.T, pr->max_motif_size, pl.outcap);
+    pl.single_copy = pr->min_repeats == 1;    // see single_copy_filter_kernel
+    return CRF_OK;
+}
 
-    uint32_t reruns = 0, launches = 0;
+static uint32_t default_result_cap(const crf_seq *s, const crf_scan_params *pr) {
+    const uint32_t cap = pr->result_cap ? pr->result_cap : std::max<uint32_t>(1u << 16, s->layout_len / 96);
+    return std::max(cap, s->res_cap);
+}
+
+static int launch_translate(crf_seq *s, ScanPlan &pl, cudaStream_t st) {
+    pl.tp.open_rows = s->d_open_rows;
+    pl.tp.open_cap = s->open_cap;
+    translate_kernel<<<pl.tgrid, 256, 0, st>>>(pl.tp);
+    CU(cudaGetLastError());
+    ++pl.launches;
+    return CRF_OK;
+}
+
+// memset -> scan -> tile offsets -> spill sort -> gather -> (single-copy filter) -> translate, all asynchronous on the
+// context's stream, result buffers of s->res_cap rows.  ev[0] .. ev[3] bracket the whole / the scan kernel.
+static int scan_enqueue(crf_seq *s, ScanPlan &pl) {
+    cudaStream_t st = s->ctx->stream;
+    const crf_scan_params *pr = &pl.pr;
+    ScanParams sp;
+    sp.H = s->H; sp.L = s->L; sp.NM = s->NM; sp.X = s->X;
+    sp.ktab = s->d_ktab; sp.segs = s->d_segs; sp.n_segs = s->n_segs;
+    sp.ex_key = s->ex_key; sp.n_exotic = s->n_exotic;
+    sp.rec_dev_off = s->d_rec_dev_off; sp.own_lo = s->d_own_lo; sp.own_hi = s->d_own_hi; sp.n_records = s->n_records;
+    sp.n_words = s->n_words;
+    sp.kmin = pr->min_motif_size; sp.kmax = pr->max_motif_size;
+    sp.outcap = pl.outcap;
+    sp.walk_limit = pr->walk_limit_words ? pr->walk_limit_words : 64;
+    sp.debug_flags = (pr->flags >> 16) & 0xFFFFu;
+    sp.sup_enabled = s->sup_enabled;
+    sp.stage_key = s->stage_key; sp.stage_k = s->stage_k; sp.stage_cap = s->res_cap;
+    sp.tile_cnt = s->tile_cnt; sp.tile_base = s->tile_base;
+    sp.spill_key = s->spill_key; sp.spill_k = s->spill_k; sp.spill_cap = s->res_cap;
+    sp.counters = s->d_counters;
+    pl.launches = 0;
+
+    CU(cudaEventRecord(s->ev[0], st));
+    CU(cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
+    CU(cudaEventRecord(s->ev[1], st));
+    const uint32_t n_tiles = pl.n_tiles;
+    if (pl.T == 1) CHECK(launch_scan<1>(sp, n_tiles, pl.smem, st));
+    else if (pl.T == 2) CHECK(launch_scan<2>(sp, n_tiles, pl.smem, st));
+    else if (pl.T == 4) CHECK(launch_scan<4>(sp, n_tiles, pl.smem, st));
+    else if (pl.T == 8) CHECK(launch_scan<8>(sp, n_tiles, pl.smem, st));
+    else CHECK(launch_scan<16>(sp, n_tiles, pl.smem, st));
+    CU(cudaEventRecord(s->ev[2], st));
+    tile_offsets_kernel<<<1, 1024, 0, st>>>(s->tile_cnt, s->tile_off, n_tiles, s->d_counters);
+    spill_sort_small_kernel<<<1, 1024, 0, st>>>(s->spill_key, s->spill_k, s->res_cap, s->d_counters);
+    GatherParams &g = pl.g;
+    g.stage_key = s->stage_key; g.stage_k = s->stage_k;
+    g.tile_cnt = s->tile_cnt; g.tile_base = s->tile_base; g.tile_off = s->tile_off;
+    g.spill_key = s->spill_key; g.spill_k = s->spill_k;
+    g.fin_key = s->fin_key; g.fin_k = s->fin_k;
+    g.n_tiles = n_tiles; g.fin_cap = s->res_cap; g.stage_cap = s->res_cap; g.spill_cap = s->res_cap;
+    g.tile_words = THREADS * pl.T; g.spill_sorted = 0;
+    g.counters = s->d_counters;
+    pl.ggrid = (n_tiles * 32 + 255) / 256;
+    gather_kernel<<<pl.ggrid, 256, 0, st>>>(g);
+    pl.launches += 4;
+    if (pl.single_copy) {
+        single_copy_filter_kernel<<<1, 1024, 0, st>>>(s->fin_key, s->fin_k, s->NM, s->X, s->n_words_alloc, s->res_cap,
+                                                      s->d_counters);
+        ++pl.launches;
+    }
+    pl.tgrid = std::min<uint32_t>(148 * 8, (s->res_cap + 255) / 256);
+    TranslateParams &tp = pl.tp;
+    tp.fin_key = s->fin_key; tp.fin_k = s->fin_k; tp.rec_dev_off = s->d_rec_dev_off; tp.rec_len = s->d_rec_len;
+    tp.map_rec = s->d_map_rec; tp.map_shift = s->d_map_shift; tp.map_open = s->d_map_open;
+    tp.n_records = s->n_records; tp.fin_cap = s->res_cap; tp.counters = s->d_counters;
+    tp.o_rec = s->o_rec; tp.o_start = s->o_start; tp.o_end = s->o_end; tp.o_k = s->o_k;
+    CHECK(launch_translate(s, pl, st));
+    CU(cudaEventRecord(s->ev[3], st));
+    return CRF_OK;
+}
+
+// after the counters of a completed scan are on the host
+static int scan_fill_stats(crf_seq *s, const ScanPlan &pl, uint32_t reruns) {
+    const unsigned long long n_total = s->h_counters[C_STAGE] + s->h_counters[C_SPILL];
+    float ms_all = 0, ms_k = 0;
+    CU(cudaEventElapsedTime(&ms_all, s->ev[0], s->ev[3]));
+    CU(cudaEventElapsedTime(&ms_k, s->ev[1], s->ev[2]));
+    const unsigned long long n_kept = pl.single_copy ? s->h_counters[C_TOTAL] : n_total;
+    s->n_results = n_kept;
+    s->have_results = true;
+    s->stats.scan_ms = ms_all;
+    s->stats.kernel_ms = ms_k;
+    s->stats.n_results = n_kept;
+    s->stats.n_tiles = pl.n_tiles;
+    s->stats.n_spilled = s->h_counters[C_SPILL];
+    s->stats.n_long = s->h_counters[C_LONG];
+    s->stats.n_open = s->h_counters[C_OPEN];
+    s->stats.n_candidates = s->h_counters[C_CAND];
+    s->stats.word_k_pairs = (uint64_t)s->n_words * (pl.pr.max_motif_size - pl.pr.min_motif_size + 1);
+    s->stats.reruns = reruns;
+    s->stats.launches = pl.launches;
+    return CRF_OK;
+}
+
+extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_results) {
+    if (!s || !pr) { set_err("crf_scan: null argument"); return CRF_ERR_ARG; }
+    CHECK(scan_validate(s, pr));
+    crf_ctx *c = s->ctx;
+    cudaStream_t st = c->stream;
+    CU(cudaSetDevice(c->device));
+    g_ctx = c;
+    s->have_results = false;
+    if (!s->plan) s->plan = new (std::nothrow) ScanPlan;
+    if (!s->plan) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    ScanPlan &pl = *s->plan;
+    CHECK(scan_prepare(s, pr, pl));
+    uint32_t cap = default_result_cap(s, pr);
+
+    uint32_t reruns = 0;
     for (;;) {
         CHECK(ensure_result_buffers(s, cap));
-        ScanParams sp;
-        sp.H = s->H; sp.L = s->L; sp.NM = s->NM; sp.X = s->X;
-        sp.ktab = s->d_ktab; sp.segs = s->d_segs; sp.n_segs = s->n_segs;
-        sp.ex_key = s->ex_key; sp.n_exotic = s->n_exotic;
-        sp.rec_dev_off = s->d_rec_dev_off; sp.own_lo = s->d_own_lo; sp.own_hi = s->d_own_hi; sp.n_records = s->n_records;
-        sp.n_words = s->n_words;
-        sp.kmin = pr->min_motif_size; sp.kmax = pr->max_motif_size;
-        sp.outcap = outcap;
-        sp.walk_limit = pr->walk_limit_words ? pr->walk_limit_words : 64;
-        sp.debug_flags = (pr->flags >> 16) & 0xFFFFu;
-        sp.sup_enabled = s->sup_enabled;
-        sp.stage_key = s->stage_key; sp.stage_k = s->stage_k; sp.stage_cap = s->res_cap;
-        sp.tile_cnt = s->tile_cnt; sp.tile_base = s->tile_base;
-        sp.spill_key = s->spill_key; sp.spill_k = s->spill_k; sp.spill_cap = s->res_cap;
-        sp.counters = s->d_counters;
-
-        CU(cudaEventRecord(s->ev[0], st));
-        CU(cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
-        CU(cudaEventRecord(s->ev[1], st));
-        if (T == 1) CHECK(launch_scan<1>(sp, n_tiles, smem, st));
-        else if (T == 2) CHECK(launch_scan<2>(sp, n_tiles, smem, st));
-        else if (T == 4) CHECK(launch_scan<4>(sp, n_tiles, smem, st));
-        else if (T == 8) CHECK(launch_scan<8>(sp, n_tiles, smem, st));
-        else CHECK(launch_scan<16>(sp, n_tiles, smem, st));
-        CU(cudaEventRecord(s->ev[2], st));
-        tile_offsets_kernel<<<1, 1024, 0, st>>>(s->tile_cnt, s->tile_off, n_tiles, s->d_counters);
-        spill_sort_small_kernel<<<1, 1024, 0, st>>>(s->spill_key, s->spill_k, s->res_cap, s->d_counters);
-        GatherParams g;
-        g.stage_key = s->stage_key; g.stage_k = s->stage_k;
-        g.tile_cnt = s->tile_cnt; g.tile_base = s->tile_base; g.tile_off = s->tile_off;
-        g.spill_key = s->spill_key; g.spill_k = s->spill_k;
-        g.fin_key = s->fin_key; g.fin_k = s->fin_k;
-        g.n_tiles = n_tiles; g.fin_cap = s->res_cap; g.stage_cap = s->res_cap; g.spill_cap = s->res_cap;
-        g.tile_words = TW; g.spill_sorted = 0;
-        g.counters = s->d_counters;
-        const uint32_t ggrid = (n_tiles * 32 + 255) / 256;
-        gather_kernel<<<ggrid, 256, 0, st>>>(g);
-        const bool single_copy = pr->min_repeats == 1;    // see single_copy_filter_kernel
-        if (single_copy) {
-            single_copy_filter_kernel<<<1, 1024, 0, st>>>(s->fin_key, s->fin_k, s->NM, s->X, s->n_words_alloc, s->res_cap,
-                                                          s->d_counters);
-            ++launches;
-        }
-        const uint32_t tgrid = std::min<uint32_t>(148 * 8, (s->res_cap + 255) / 256);
-        TranslateParams tp;
-        tp.fin_key = s->fin_key; tp.fin_k = s->fin_k; tp.rec_dev_off = s->d_rec_dev_off; tp.rec_len = s->d_rec_len;
-        tp.map_rec = s->d_map_rec; tp.map_shift = s->d_map_shift; tp.map_open = s->d_map_open;
-        tp.n_records = s->n_records; tp.fin_cap = s->res_cap; tp.counters = s->d_counters;
-        tp.o_rec = s->o_rec; tp.o_start = s->o_start; tp.o_end = s->o_end; tp.o_k = s->o_k;
-        tp.open_rows = s->d_open_rows;
-        translate_kernel<<<tgrid, 256, 0, st>>>(tp);
-        CU(cudaGetLastError());
-        launches += 5;
-        CU(cudaEventRecord(s->ev[3], st));
+        CHECK(scan_enqueue(s, pl));
         CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
 
@@ -740,40 +838,36 @@ extern "C" int crf_scan(crf_seq *s, const crf_scan_params *pr, uint64_t *n_resul
             ++reruns;
             continue;
         }
+        bool again = false;
         if (n_spill > SPILL_SMALL) {  // a long spill list: sort it with the global network, then gather again
-            CHECK(bitonic_sort(st, s->spill_key, s->spill_k, (uint32_t)n_spill, &launches));
-            g.spill_sorted = 1;
-            gather_kernel<<<ggrid, 256, 0, st>>>(g);
-            if (single_copy) {
+            CHECK(bitonic_sort(st, s->spill_key, s->spill_k, (uint32_t)n_spill, &pl.launches));
+            pl.g.spill_sorted = 1;
+            gather_kernel<<<pl.ggrid, 256, 0, st>>>(pl.g);
+            ++pl.launches;
+            if (pl.single_copy) {
                 single_copy_filter_kernel<<<1, 1024, 0, st>>>(s->fin_key, s->fin_k, s->NM, s->X, s->n_words_alloc,
                                                               s->res_cap, s->d_counters);
-                ++launches;
+                ++pl.launches;
             }
+            again = true;
+        }
+        if (s->h_counters[C_OPEN] > s->open_cap) {   // more open-ended rows than the list held: grow it, translate again
+            uint32_t *bigger = nullptr;
+            const uint32_t want = (uint32_t)std::min<unsigned long long>(s->h_counters[C_OPEN] + 64, 0x0FFFFFFFull);
+            CHECK(dev_alloc(&bigger, 5 * (size_t)want));
+            dev_free(s->d_open_rows);
+            s->d_open_rows = bigger;
+            s->open_cap = want;
+            again = true;
+        }
+        if (again) {
             CU(cudaMemsetAsync(s->d_counters + C_OPEN, 0, sizeof(unsigned long long), st));
-            translate_kernel<<<tgrid, 256, 0, st>>>(tp);
-            CU(cudaGetLastError());
-            launches += 2;
+            CHECK(launch_translate(s, pl, st));
             CU(cudaEventRecord(s->ev[3], st));
             CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
         }
-        float ms_all = 0, ms_k = 0;
-        CU(cudaEventElapsedTime(&ms_all, s->ev[0], s->ev[3]));
-        CU(cudaEventElapsedTime(&ms_k, s->ev[1], s->ev[2]));
-        const unsigned long long n_kept = single_copy ? s->h_counters[C_TOTAL] : n_total;
-        s->n_results = n_kept;
-        s->have_results = true;
-        s->stats.scan_ms = ms_all;
-        s->stats.kernel_ms = ms_k;
-        s->stats.n_results = n_kept;
-        s->stats.n_tiles = n_tiles;
-        s->stats.n_spilled = n_spill;
-        s->stats.n_long = s->h_counters[C_LONG];
-        s->stats.n_open = s->h_counters[C_OPEN];
-        s->stats.n_candidates = s->h_counters[C_CAND];
-        s->stats.word_k_pairs = (uint64_t)s->n_words * (pr->max_motif_size - pr->min_motif_size + 1);
-        s->stats.reruns = reruns;
-        s->stats.launches = launches;
+        CHECK(scan_fill_stats(s, pl, reruns));
         break;
     }
     if (n_results) *n_results = s->n_results;
@@ -812,19 +906,16 @@ extern "C" int crf_fetch_open(crf_seq *s, uint32_t *rows, uint32_t cap, uint32_t
     if (!s || !n_open) { set_err("crf_fetch_open: null argument"); return CRF_ERR_ARG; }
     if (!s->have_results) { set_err("crf_fetch_open: no scan results"); return CRF_ERR_ARG; }
     *n_open = (uint32_t)std::min<uint64_t>(s->stats.n_open, 0xFFFFFFFFull);
-    const uint32_t n = std::min<uint32_t>(std::min<uint32_t>(*n_open, cap), OPEN_CAP);
-    if (*n_open > OPEN_CAP) {
-        set_err("crf_fetch_open: %u open-ended results, at most %u are kept per scan (use a longer halo)", *n_open, OPEN_CAP);
-        return CRF_ERR_UNSUPPORTED;
-    }
+    const uint32_t n = std::min<uint32_t>(std::min<uint32_t>(*n_open, cap), s->open_cap);
     if (!n) return CRF_OK;
     if (!rows) { set_err("crf_fetch_open: null rows"); return CRF_ERR_ARG; }
     CU(cudaSetDevice(s->ctx->device));
-    std::vector<uint32_t> tmp(5 * (size_t)n);
+    const uint32_t have = std::min<uint32_t>(*n_open, s->open_cap);   // rows the device list holds (crf_scan grew it to fit)
+    std::vector<uint32_t> tmp(5 * (size_t)have);
     CU(cudaMemcpyAsync(tmp.data(), s->d_open_rows, tmp.size() * 4, cudaMemcpyDeviceToHost, s->ctx->stream));
     CU(cudaStreamSynchronize(s->ctx->stream));
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    std::vector<uint32_t> order(have);
+    for (uint32_t i = 0; i < have; ++i) order[i] = i;
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return tmp[5 * a] < tmp[5 * b]; });  // result order
     for (uint32_t i = 0; i < n; ++i) memcpy(rows + 5 * i, &tmp[5 * order[i]], 20);
     return CRF_OK;
@@ -854,6 +945,256 @@ extern "C" int crf_run_end(crf_seq *s, uint32_t record, uint32_t pos, uint32_t k
     CU(cudaMemcpyAsync(s->h_counters, d_out, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *run_end = *reinterpret_cast<uint32_t *>(s->h_counters) - d0;
+    return CRF_OK;
+}
+
+// ---- multi-GPU gather over peer memory (crf_xchg.cuh) ---------------------------------------------
+static const size_t XCHG_ROWS_OFFSET = (sizeof(XchgBlock) + 255) & ~(size_t)255;
+static const uint32_t XCHG_RING = 64;
+
+struct crf_xchg {
+    crf_ctx *ctx = nullptr;
+    uint32_t rank = 0, world = 1;
+    uint64_t row_cap = 0;
+    void *base = nullptr;                        // this rank's block (+ the row buffer on the root)
+    size_t bytes = 0;
+    void *peer_base[XCHG_MAX_WORLD] = {};
+    bool peer_ipc[XCHG_MAX_WORLD] = {};
+    bool connected[XCHG_MAX_WORLD] = {};
+    uint32_t step = 0, first_unchecked = 1;      // steps are numbered from 1
+    unsigned long long *h_ring = nullptr;        // page-locked: XCHG_RING x XCHG_RESULT_WORDS
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    crf_seq *pending_seq = nullptr;              // sequence whose asynchronous scan feeds the step in flight
+    uint32_t pending_reruns = 0;
+};
+
+extern "C" int crf_xchg_create(crf_ctx *c, uint32_t rank, uint32_t world, uint64_t row_cap, crf_xchg **out) {
+    if (!c || !out) { set_err("crf_xchg_create: null argument"); return CRF_ERR_ARG; }
+    *out = nullptr;
+    if (world < 1 || world > XCHG_MAX_WORLD || rank >= world) {
+        set_err("crf_xchg_create: rank %u / world %u (at most %u ranks)", rank, world, XCHG_MAX_WORLD);
+        return CRF_ERR_ARG;
+    }
+    if (row_cap > 0xFFFFFFF0ull) { set_err("crf_xchg_create: row_cap must be below 2^32"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(c->device));
+    crf_xchg *x = new (std::nothrow) crf_xchg;
+    if (!x) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    x->ctx = c; x->rank = rank; x->world = world; x->row_cap = row_cap;
+    x->bytes = XCHG_ROWS_OFFSET + (rank == 0 ? (size_t)row_cap * 16 : 0);
+    // a plain cudaMalloc (not the context's block cache): the block is exported to other processes
+    cudaError_t e = cudaMalloc(&x->base, x->bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->base, 0, XCHG_ROWS_OFFSET);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&x->h_ring, (size_t)XCHG_RING * XCHG_RESULT_WORDS * 8);
+    if (e != cudaSuccess) {
+        if (x->base) cudaFree(x->base);
+        delete x;
+        set_err("crf_xchg_create: %s", cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? CRF_ERR_NOMEM : CRF_ERR_CUDA;
+    }
+    memset(x->h_ring, 0, (size_t)XCHG_RING * XCHG_RESULT_WORDS * 8);
+    x->peer_base[rank] = x->base;
+    x->connected[rank] = true;
+    *out = x;
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_export(crf_xchg *x, uint8_t *handle) {
+    if (!x || !handle) { set_err("crf_xchg_export: null argument"); return CRF_ERR_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == CRF_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(x->ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, x->base));
+    memcpy(handle, &h, sizeof(h));
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_connect_ipc(crf_xchg *x, uint32_t peer, const uint8_t *handle) {
+    if (!x || !handle || peer >= x->world || peer == x->rank) { set_err("crf_xchg_connect_ipc: bad argument"); return CRF_ERR_ARG; }
+    if (x->connected[peer]) { set_err("crf_xchg_connect_ipc: rank %u is already connected", peer); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(x->ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peer_base[peer] = ptr;
+    x->peer_ipc[peer] = true;
+    x->connected[peer] = true;
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_connect_local(crf_xchg *x, uint32_t peer, crf_xchg *other) {
+    if (!x || !other || peer >= x->world || peer == x->rank || other->rank != peer) {
+        set_err("crf_xchg_connect_local: bad argument");
+        return CRF_ERR_ARG;
+    }
+    if (x->connected[peer]) { set_err("crf_xchg_connect_local: rank %u is already connected", peer); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(x->ctx->device));
+    if (other->ctx->device != x->ctx->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, x->ctx->device, other->ctx->device));
+        if (!can) { set_err("crf_xchg_connect_local: device %d cannot access device %d", x->ctx->device, other->ctx->device); return CRF_ERR_UNSUPPORTED; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(other->ctx->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) { set_err("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
+    }
+    x->peer_base[peer] = other->base;
+    x->connected[peer] = true;
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_destroy(crf_xchg *x) {
+    if (!x) return CRF_OK;
+    cudaSetDevice(x->ctx->device);
+    cudaStreamSynchronize(x->ctx->stream);
+    for (uint32_t r = 0; r < x->world; ++r)
+        if (x->peer_ipc[r] && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+    if (x->base) cudaFree(x->base);
+    if (x->h_ring) cudaFreeHost(x->h_ring);
+    delete x;
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_set_timeout(crf_xchg *x, double seconds) {
+    if (!x || !(seconds > 0)) { set_err("crf_xchg_set_timeout: bad argument"); return CRF_ERR_ARG; }
+    x->timeout_ns = (unsigned long long)(seconds * 1e9);
+    return CRF_OK;
+}
+
+// push + settle of the rows the sequence holds (results of the scan queued before it on the stream)
+static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted) {
+    for (uint32_t r = 0; r < x->world; ++r)
+        if (!x->connected[r]) { set_err("crf_xchg: rank %u is not connected", r); return CRF_ERR_ARG; }
+    if (x->step + 1 - x->first_unchecked >= XCHG_RING) {
+        set_err("crf_xchg: %u steps in flight without crf_xchg_wait (at most %u)", XCHG_RING, XCHG_RING);
+        return CRF_ERR_ARG;
+    }
+    cudaStream_t st = x->ctx->stream;
+    ++x->step;
+    PushParams pp = {};
+    pp.self = (XchgBlock *)x->base;
+    for (uint32_t r = 0; r < x->world; ++r) pp.peer[r] = (XchgBlock *)x->peer_base[r];
+    pp.root_rows = (uint32_t *)((char *)x->peer_base[0] + XCHG_ROWS_OFFSET);
+    pp.row_cap = x->row_cap;
+    pp.rank = x->rank; pp.world = x->world; pp.step = x->step;
+    pp.o_rec = s->o_rec; pp.o_start = s->o_start; pp.o_end = s->o_end; pp.o_k = s->o_k;
+    pp.counters = s->d_counters;
+    pp.res_cap = s->res_cap; pp.open_cap = s->open_cap;
+    pp.trusted = trusted ? 1u : 0u;
+    pp.timeout_ns = x->timeout_ns;
+    push_kernel<<<148 * 2, 256, 0, st>>>(pp);
+    SettleParams sp = {};
+    sp.self = (XchgBlock *)x->base;
+    sp.row_cap = x->row_cap; sp.rank = x->rank; sp.world = x->world; sp.step = x->step; sp.timeout_ns = x->timeout_ns;
+    settle_kernel<<<1, 32, 0, st>>>(sp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(x->h_ring + (size_t)(x->step % XCHG_RING) * XCHG_RESULT_WORDS, ((XchgBlock *)x->base)->result,
+                       XCHG_RESULT_WORDS * 8, cudaMemcpyDeviceToHost, st));
+    return CRF_OK;
+}
+
+extern "C" int crf_scan_gather(crf_seq *s, const crf_scan_params *pr, crf_xchg *x) {
+    if (!s || !pr || !x) { set_err("crf_scan_gather: null argument"); return CRF_ERR_ARG; }
+    if (s->ctx != x->ctx) { set_err("crf_scan_gather: sequence and exchange belong to different contexts"); return CRF_ERR_ARG; }
+    CHECK(scan_validate(s, pr));
+    crf_ctx *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    g_ctx = c;
+    s->have_results = false;
+    if (!s->plan) s->plan = new (std::nothrow) ScanPlan;
+    if (!s->plan) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    CHECK(scan_prepare(s, pr, *s->plan));
+    CHECK(ensure_result_buffers(s, default_result_cap(s, pr)));
+    CHECK(scan_enqueue(s, *s->plan));
+    CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CHECK(xchg_enqueue(s, x, false));
+    x->pending_seq = s;
+    s->plan->launches += 2;
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_push(crf_seq *s, crf_xchg *x) {
+    if (!s || !x) { set_err("crf_xchg_push: null argument"); return CRF_ERR_ARG; }
+    if (s->ctx != x->ctx) { set_err("crf_xchg_push: sequence and exchange belong to different contexts"); return CRF_ERR_ARG; }
+    if (!s->have_results) { set_err("crf_xchg_push: no scan results"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(s->ctx->device));
+    CHECK(xchg_enqueue(s, x, true));
+    x->pending_seq = nullptr;
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_wait(crf_xchg *x, crf_xchg_result_t *res) {
+    if (!x || !res) { set_err("crf_xchg_wait: null argument"); return CRF_ERR_ARG; }
+    if (x->step == 0) { set_err("crf_xchg_wait: nothing was pushed"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(x->ctx->device));
+    CU(cudaStreamSynchronize(x->ctx->stream));
+    uint32_t worst = XCHG_OK;
+    for (uint32_t st = x->first_unchecked; st <= x->step; ++st)
+        worst = std::max<uint32_t>(worst, (uint32_t)x->h_ring[(size_t)(st % XCHG_RING) * XCHG_RESULT_WORDS]);
+    res->steps_checked = x->step + 1 - x->first_unchecked;
+    x->first_unchecked = x->step + 1;
+    const unsigned long long *r = x->h_ring + (size_t)(x->step % XCHG_RING) * XCHG_RESULT_WORDS;
+    res->status = (uint32_t)r[0];
+    res->worst_status = worst;
+    res->total_rows = r[1];
+    res->total_open = r[2];
+    res->my_offset = r[3];
+    res->any_open = (uint32_t)r[4];
+    res->step = x->step;
+    for (uint32_t q = 0; q < XCHG_MAX_WORLD; ++q) res->rows_of_rank[q] = q < x->world ? r[8 + q] : 0;
+    if (res->status == XCHG_TIMEOUT) {
+        set_err("crf_xchg_wait: a peer rank did not arrive within %.1f s", x->timeout_ns * 1e-9);
+        return CRF_ERR_CUDA;
+    }
+    if (x->pending_seq && res->status == XCHG_OK) {   // the asynchronous scan behind this step: its counters are on the host now
+        crf_seq *s = x->pending_seq;
+        CHECK(scan_fill_stats(s, *s->plan, 0));
+    }
+    x->pending_seq = nullptr;
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_fetch(crf_xchg *x, uint32_t *record, uint32_t *start, uint32_t *end, uint32_t *motif_size,
+                              uint64_t first_row, uint64_t n_rows, int dst_on_device) {
+    if (!x) { set_err("crf_xchg_fetch: null exchange"); return CRF_ERR_ARG; }
+    if (x->rank != 0) { set_err("crf_xchg_fetch: the gathered rows live on rank 0"); return CRF_ERR_ARG; }
+    if (first_row + n_rows > x->row_cap) { set_err("crf_xchg_fetch: rows beyond the buffer"); return CRF_ERR_ARG; }
+    if (!n_rows) return CRF_OK;
+    if (!record || !start || !end || !motif_size) { set_err("crf_xchg_fetch: null output array"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(x->ctx->device));
+    cudaStream_t st = x->ctx->stream;
+    const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const uint32_t *rows = (const uint32_t *)((char *)x->base + XCHG_ROWS_OFFSET) + first_row;
+    uint32_t *dst[4] = {record, start, end, motif_size};
+    for (int j = 0; j < 4; ++j) CU(cudaMemcpyAsync(dst[j], rows + (size_t)j * x->row_cap, (size_t)n_rows * 4, kind, st));
+    CU(cudaStreamSynchronize(st));
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_patch_end(crf_xchg *x, const uint64_t *rows, const uint32_t *new_end, uint32_t n) {
+    if (!x || (n && (!rows || !new_end))) { set_err("crf_xchg_patch_end: null argument"); return CRF_ERR_ARG; }
+    if (x->rank != 0) { set_err("crf_xchg_patch_end: the gathered rows live on rank 0"); return CRF_ERR_ARG; }
+    if (!n) return CRF_OK;
+    CU(cudaSetDevice(x->ctx->device));
+    g_ctx = x->ctx;
+    cudaStream_t st = x->ctx->stream;
+    uint64_t *d_idx = nullptr;
+    uint32_t *d_end = nullptr;
+    CHECK(dev_alloc(&d_idx, n));
+    int rc = dev_alloc(&d_end, n);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        e = cudaMemcpyAsync(d_idx, rows, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_end, new_end, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            patch_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>((uint32_t *)((char *)x->base + XCHG_ROWS_OFFSET), x->row_cap, d_idx, d_end, n);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    dev_free(d_idx);
+    dev_free(d_end);
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_err("crf_xchg_patch_end: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
     return CRF_OK;
 }
 

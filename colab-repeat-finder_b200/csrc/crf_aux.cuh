@@ -237,10 +237,11 @@ struct TranslateParams {
     uint32_t n_records, fin_cap;
     unsigned long long *counters;
     uint32_t *o_rec, *o_start, *o_end, *o_k;
-    uint32_t *open_rows;                   // OPEN_CAP x 5: row, record, start, end, k of open-ended results
+    uint32_t *open_rows;                   // open_cap x 5: row, record, start, end, k of open-ended results
+    uint32_t open_cap;                     // (the host grows the list and translates again when it was too short)
 };
 
-constexpr uint32_t OPEN_CAP = 256;
+constexpr uint32_t OPEN_CAP_INITIAL = 256;
 
 __global__ void __launch_bounds__(256) translate_kernel(const TranslateParams t) {
     const unsigned long long n = t.counters[C_TOTAL];
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256) translate_kernel(const TranslateParams t)
         t.o_k[i] = t.fin_k[i];
         if (t.map_open && t.map_open[lo] && en - d0 == t.rec_len[lo]) {  // reached the end of an open-ended record
             const unsigned long long slot = atomicAdd(t.counters + C_OPEN, 1ull);
-            if (slot < OPEN_CAP) {
+            if (slot < t.open_cap) {
                 uint32_t *row = t.open_rows + 5 * slot;
                 row[0] = i; row[1] = orec; row[2] = st - d0 + shift; row[3] = en - d0 + shift; row[4] = t.fin_k[i];
             }

@@ -1,0 +1,203 @@
+// crf_xchg.cuh -- gathering the compacted rows of N GPUs on rank 0 ("root") over NVLink peer memory.
+//
+// The reference scales out by fanning intervals over CPU jobs and concatenating their BED files
+// (hail_batch_pipeline/run_hail_batch_pipeline.py:76-77, 115-123, 153).  Here every GPU scans a contiguous
+// range of (record, chunk) units, so rank order is genome order and the final list is the concatenation of
+// the ranks' sorted rows.  That concatenation is the only exchange of the path and it is done by the GPUs
+// themselves, without a host round trip and without a collective library:
+//
+//   * every rank owns one exchange block in its HBM (XchgBlock + on the root the row buffer), mapped into
+//     every peer's address space (CUDA IPC between processes, plain peer access inside one process);
+//   * push_kernel (one launch per rank and step): publishes this rank's row count to every peer with one
+//     8-byte store that carries the step number (so the store is its own flag), waits for the counts of the
+//     ranks before it -- they arrive in its OWN memory --, and stores its rows straight into the root's
+//     buffer at the prefix offset (coalesced 4-byte peer stores); the last block then posts a done word on the root;
+//   * settle_kernel (one warp): waits until the counts of ALL ranks (on the root also the done words) of this
+//     step have arrived and writes status / totals for the host.
+// Two slots per rank (step parity) are enough: no rank can be two steps ahead of another one, because a step
+// cannot complete on the root before every rank has pushed, and no rank > 0 can push before the root has
+// published its count of that step.
+#pragma once
+#include "crf_aux.cuh"
+
+namespace crf {
+
+constexpr uint32_t XCHG_MAX_WORLD = 16;
+constexpr uint32_t XCHG_RESULT_WORDS = 8 + XCHG_MAX_WORLD;
+
+// slot word: [63:40] step (24 bits)  [39] void  [38] the rank has open-ended rows  [31:0] value
+constexpr unsigned long long XCHG_VOID = 1ull << 39;
+constexpr unsigned long long XCHG_HAS_OPEN = 1ull << 38;
+__host__ __device__ __forceinline__ unsigned long long xchg_enc(uint32_t step, bool is_void, uint32_t value, bool has_open = false) {
+    return ((unsigned long long)(step & 0xFFFFFFu) << 40) | (is_void ? XCHG_VOID : 0ull) | (has_open ? XCHG_HAS_OPEN : 0ull) | value;
+}
+__host__ __device__ __forceinline__ bool xchg_is_step(unsigned long long w, uint32_t step) {
+    return (uint32_t)(w >> 40) == (step & 0xFFFFFFu);
+}
+
+struct XchgBlock {
+    unsigned long long count_slot[2][XCHG_MAX_WORLD];  // [step parity][rank]: written by that rank's push_kernel
+    unsigned long long done_slot[2][XCHG_MAX_WORLD];   // root only: rows of [rank] have landed (value = its open-ended rows)
+    unsigned long long my_offset;                      // where this rank's rows start in the root buffer (last push)
+    unsigned int blocks_done;                          // last-block counter of push_kernel
+    unsigned int pad_;
+    unsigned long long result[XCHG_RESULT_WORDS];      // settle_kernel: [0] status [1] total rows [2] total open
+                                                       // [3] my offset [4] some rank has open-ended rows
+                                                       // [8 + r] rows of rank r
+};
+
+enum XchgStatus : uint32_t {
+    XCHG_OK = 0,
+    XCHG_VOID_STEP = 1,   // some rank's scan outgrew its buffers (or has a long spill list): repeat the step the slow way
+    XCHG_ROOT_FULL = 2,   // the rows of all ranks do not fit the root buffer
+    XCHG_TIMEOUT = 3,     // a peer never showed up
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// spin until the slot carries `step`; false on timeout
+__device__ inline bool wait_slot(const unsigned long long *slot, uint32_t step, unsigned long long timeout_ns,
+                                 unsigned long long *out) {
+    unsigned long long v = ld_acquire_sys(slot);
+    if (!xchg_is_step(v, step)) {
+        const unsigned long long t0 = global_timer_ns();
+        for (;;) {
+            __nanosleep(200);
+            v = ld_acquire_sys(slot);
+            if (xchg_is_step(v, step)) break;
+            if (global_timer_ns() - t0 > timeout_ns) { *out = v; return false; }
+        }
+    }
+    *out = v;
+    return true;
+}
+
+struct PushParams {
+    XchgBlock *self;
+    XchgBlock *peer[XCHG_MAX_WORLD];     // rank r's block in this rank's address space (peer[rank] == self)
+    uint32_t *root_rows;                 // root buffer: 4 arrays of row_cap (record, start, end, k)
+    uint64_t row_cap;
+    uint32_t rank, world, step;
+    const uint32_t *o_rec, *o_start, *o_end, *o_k;
+    const unsigned long long *counters;
+    uint32_t res_cap, open_cap;
+    uint32_t trusted;                    // the host has already checked (and fixed up) the scan these rows come from
+    unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(256) push_kernel(const PushParams p) {
+    __shared__ unsigned long long s_off;
+    __shared__ uint32_t s_ok;
+    const uint32_t par = p.step & 1u;
+    const unsigned long long n_stage = p.counters[C_STAGE], n_spill = p.counters[C_SPILL];
+    const unsigned long long n_total = p.counters[C_TOTAL], n_open = p.counters[C_OPEN];
+    // the conditions under which crf_scan would have grown a buffer, sorted a long spill list or re-run
+    const bool valid = p.trusted || (n_stage <= p.res_cap && n_spill <= p.res_cap && n_spill <= SPILL_SMALL &&
+                                     n_total <= p.res_cap && n_open <= p.open_cap);
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            const unsigned long long w = xchg_enc(p.step, !valid, valid ? (uint32_t)n_total : 0u, n_open != 0);
+            for (uint32_t q = 0; q < p.world; ++q) st_release_sys(&p.peer[q]->count_slot[par][p.rank], w);
+        }
+        unsigned long long off = 0;
+        bool ok = valid;
+        for (uint32_t q = 0; q < p.rank; ++q) {          // counts of the ranks before me (they land in my own memory)
+            unsigned long long w;
+            if (!wait_slot(&p.self->count_slot[par][q], p.step, p.timeout_ns, &w) || (w & XCHG_VOID)) ok = false;
+            off += (uint32_t)w;
+        }
+        if (off + n_total > p.row_cap) ok = false;
+        s_off = off;
+        s_ok = ok ? 1u : 0u;
+    }
+    __syncthreads();
+    const unsigned long long off = s_off;
+    if (s_ok) {
+        uint32_t *d_rec = p.root_rows + off, *d_start = d_rec + p.row_cap, *d_end = d_start + p.row_cap, *d_k = d_end + p.row_cap;
+        const uint32_t n = (uint32_t)n_total, stride = gridDim.x * blockDim.x;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            d_rec[i] = p.o_rec[i];
+            d_start[i] = p.o_start[i];
+            d_end[i] = p.o_end[i];
+            d_k[i] = p.o_k[i];
+        }
+    }
+    __threadfence_system();                               // my rows are visible on the root before the done word can be
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&p.self->blocks_done, 1u);
+        if (prev == gridDim.x - 1) {                      // last block of this launch
+            p.self->blocks_done = 0;
+            p.self->my_offset = off;
+            __threadfence_system();
+            st_release_sys(&p.peer[0]->done_slot[par][p.rank], xchg_enc(p.step, !s_ok, (uint32_t)min(n_open, 0xFFFFFFFFull)));
+        }
+    }
+}
+
+struct SettleParams {
+    XchgBlock *self;
+    uint64_t row_cap;
+    uint32_t rank, world, step;
+    unsigned long long timeout_ns;
+};
+
+// one warp: lane q waits for rank q
+__global__ void __launch_bounds__(32) settle_kernel(const SettleParams p) {
+    const uint32_t lane = threadIdx.x, par = p.step & 1u;
+    unsigned long long cnt = 0, done = 0;
+    bool arrived = true, is_void = false, has_open = false;
+    if (lane < p.world) {
+        arrived = wait_slot(&p.self->count_slot[par][lane], p.step, p.timeout_ns, &cnt);
+        is_void = (cnt & XCHG_VOID) != 0;
+        has_open = (cnt & XCHG_HAS_OPEN) != 0;
+        if (p.rank == 0 && arrived) {
+            arrived = wait_slot(&p.self->done_slot[par][lane], p.step, p.timeout_ns, &done);
+            is_void = is_void || (done & XCHG_VOID) != 0;
+        }
+    }
+    const uint32_t n = (lane < p.world && arrived) ? (uint32_t)cnt : 0u;
+    const uint32_t nopen = (lane < p.world && arrived) ? (uint32_t)done : 0u;
+    unsigned long long total = n, open_total = nopen;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+        open_total += __shfl_xor_sync(0xFFFFFFFFu, open_total, o);
+    }
+    const bool any_timeout = __any_sync(0xFFFFFFFFu, !arrived);
+    const bool any_void = __any_sync(0xFFFFFFFFu, is_void);
+    const bool any_open = __any_sync(0xFFFFFFFFu, has_open);
+    if (lane < p.world) p.self->result[8 + lane] = n;
+    if (lane == 0) {
+        uint32_t status = XCHG_OK;
+        if (any_timeout) status = XCHG_TIMEOUT;
+        else if (total > p.row_cap) status = XCHG_ROOT_FULL;
+        else if (any_void) status = XCHG_VOID_STEP;
+        p.self->result[0] = status;
+        p.self->result[1] = total;
+        p.self->result[2] = open_total;
+        p.self->result[3] = p.self->my_offset;
+        p.self->result[4] = any_open ? 1ull : 0ull;
+    }
+}
+
+// root: overwrite the end of gathered rows (stitched open-ended runs), idx = global row numbers
+__global__ void __launch_bounds__(256) patch_rows_kernel(uint32_t *root_rows, uint64_t row_cap, const uint64_t *idx,
+                                                         const uint32_t *new_end, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && idx[i] < row_cap) root_rows[2 * row_cap + idx[i]] = new_end[i];
+}
+
+}  // namespace crf

@@ -63,6 +63,9 @@ int crf_seq_load_ascii_ranges(crf_ctx *ctx, const uint8_t *bases, const uint64_t
                               const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records,
                               uint32_t max_motif_cap, int bases_on_device, crf_seq **seq);
 int crf_seq_destroy(crf_seq *seq);
+/* Layout positions one load can hold: the sum over its records of (length + max_motif_cap) must not exceed this
+ * (positions are 32-bit on the device); callers with more split the records over several loads. */
+uint64_t crf_load_limit(uint32_t max_motif_cap);
 /* Optional, for partitioned loads: report record r of this load as record out_record[r] with start/end
  * shifted by out_shift[r] (a unit's offset inside its chromosome), and count as "open" every result that
  * ends exactly at the end of a record flagged in open_ended[r] (the unit's data stops before the
@@ -148,6 +151,56 @@ int crf_patch_end(crf_seq *seq, uint64_t row, uint32_t new_end);
  * M_k[pos] == 1, else *run_end = pos).  *run_end = first position >= pos that does not match.
  * Used to stitch runs that leave a partition (chunk/GPU) -- see DESIGN.md "multi-GPU". */
 int crf_run_end(crf_seq *seq, uint32_t record, uint32_t pos, uint32_t k, uint32_t *run_end);
+
+/* ---- multi-GPU: gathering the compacted rows of N GPUs on rank 0 over NVLink peer memory -----------------
+ * The reference scales out by fanning `--interval` jobs over CPU workers and concatenating their BED files
+ * (hail_batch_pipeline/run_hail_batch_pipeline.py:76-77, 115-123, 153).  Here each rank (one GPU: one process
+ * under torchrun, or one thread of a single process) scans a contiguous range of (record, chunk) units, so the
+ * final list is the concatenation of the ranks' sorted rows in rank order.  An exchange block per rank, mapped
+ * into every peer (CUDA IPC between processes, peer access inside one process), lets the GPUs do that
+ * concatenation themselves: counts are exchanged with 8-byte peer stores, every rank writes its rows straight
+ * into rank 0's buffer at its prefix offset, no host round trip and no collective library inside a step
+ * (csrc/crf_xchg.cuh).  All ranks must make the same sequence of crf_scan_gather / crf_xchg_push calls.
+ */
+typedef struct crf_xchg crf_xchg;
+#define CRF_IPC_HANDLE_BYTES 64
+#define CRF_XCHG_MAX_WORLD 16
+/* row_cap = rows rank 0's buffer holds (16 bytes each; only rank 0 allocates them). */
+int crf_xchg_create(crf_ctx *ctx, uint32_t rank, uint32_t world, uint64_t row_cap, crf_xchg **xchg);
+int crf_xchg_destroy(crf_xchg *xchg);
+/* Ranks in different processes: export a CRF_IPC_HANDLE_BYTES handle, pass it around (any transport), connect. */
+int crf_xchg_export(crf_xchg *xchg, uint8_t *handle);
+int crf_xchg_connect_ipc(crf_xchg *xchg, uint32_t peer_rank, const uint8_t *handle);
+/* Ranks of one process (one context per device, one thread per context). */
+int crf_xchg_connect_local(crf_xchg *xchg, uint32_t peer_rank, crf_xchg *peer);
+int crf_xchg_set_timeout(crf_xchg *xchg, double seconds); /* how long a kernel waits for a peer (default 20 s) */
+
+/* crf_scan + push in one go, fully asynchronous: nothing is copied back and the host does not wait.  If the scan
+ * outgrows a buffer, has a long spill list or more open-ended rows than their list holds, the step is void on
+ * every rank (status 1): repeat it with crf_scan (which grows what was too small) followed by crf_xchg_push. */
+int crf_scan_gather(crf_seq *seq, const crf_scan_params *params, crf_xchg *xchg);
+/* Push the rows of the last completed crf_scan (asynchronous). */
+int crf_xchg_push(crf_seq *seq, crf_xchg *xchg);
+
+typedef struct {
+    uint32_t status;        /* of the last step: 0 ok, 1 void (repeat the slow way), 2 rank 0's buffer too small, 3 timeout */
+    uint32_t worst_status;  /* over all steps since the previous crf_xchg_wait */
+    uint32_t steps_checked;
+    uint32_t step;          /* number of the last step (from 1) */
+    uint32_t any_open;      /* some rank has open-ended rows (same answer on every rank): stitch before using the rows */
+    uint32_t reserved;
+    uint64_t total_rows;    /* rows of all ranks (they are on rank 0, in rank order = genome order) */
+    uint64_t total_open;    /* rank 0 only: open-ended rows of all ranks (runs that left their unit's data) */
+    uint64_t my_offset;     /* first row of this rank inside rank 0's buffer */
+    uint64_t rows_of_rank[CRF_XCHG_MAX_WORLD];
+} crf_xchg_result_t;
+/* Wait until this rank's part of every queued step is complete (on rank 0: until all rows have landed). */
+int crf_xchg_wait(crf_xchg *xchg, crf_xchg_result_t *result);
+/* Rank 0: copy gathered rows [first_row, first_row + n_rows) out (see crf_fetch for the columns). */
+int crf_xchg_fetch(crf_xchg *xchg, uint32_t *record, uint32_t *start, uint32_t *end, uint32_t *motif_size,
+                   uint64_t first_row, uint64_t n_rows, int dst_on_device);
+/* Rank 0: overwrite the end of gathered rows (global row numbers) -- stitched open-ended runs. */
+int crf_xchg_patch_end(crf_xchg *xchg, const uint64_t *rows, const uint32_t *new_end, uint32_t n);
 
 /* ---- output (host only, no GPU) -------------------------------------------------------------
  * Writes result rows as text, replacing the per-row Python of prf:148-149 (BED: chrom, start, end, motif) and

@@ -19,9 +19,17 @@ ap.add_argument("--no-sup", action="store_true")
 ap.add_argument("--outcap", type=int, default=0)
 ap.add_argument("--wpt", type=int, default=0)
 ap.add_argument("--kmin", type=int, default=1)
-ap.add_argument("--kmax", type=int, default=50)
+ap.add_argument("--kmax", type=int, default=0)
+ap.add_argument("--workload", default="s38", choices=["s38", "s22", "sr"])
 args = ap.parse_args()
-bases, offsets, meta = synth.s38(device="cuda:0", scale=args.scale)
+if not args.kmax:
+    args.kmax = 20 if args.workload == "sr" else 50
+if args.workload == "s38":
+    bases, offsets, meta = synth.s38(device="cuda:0", scale=args.scale)
+elif args.workload == "s22":
+    bases, offsets, meta = synth.s22(device="cuda:0", scale=args.scale)
+else:
+    bases, offsets, meta = synth.sr(int(10_000_000 * args.scale), device="cuda:0")
 torch.cuda.synchronize()
 ctx = _cabi.Context(0)
 seq = ctx.load(bases.data_ptr(), offsets, max_motif_cap=args.kmax, on_device=True)

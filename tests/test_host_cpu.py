@@ -302,14 +302,36 @@ def test_cli_whole_fasta_glue_with_a_stand_in_scan(tmp_path, monkeypatch, capsys
         want += [f"{name.split()[0]}\t{s}\t{e}\t{m}\n" for s, e, m in oracle.detect_repeats(seq, fs)]
     monkeypatch.setattr(api, "get_context", lambda device=None: FakeContext())
     monkeypatch.chdir(tmp_path)
-    for limit in (cli.MAX_LOAD_BASES, 3500, 1):           # one load / several groups / one record per load
-        monkeypatch.setattr(cli, "MAX_LOAD_BASES", limit)
+    from crf_b200 import _cabi
+    real_limit = _cabi.load_limit(12)
+    assert 4_200_000_000 < real_limit < 2 ** 32           # what libcrf itself enforces (crf_load_limit)
+    for limit in (real_limit, 3500, 1):                   # one load / several groups / one record per load
+        monkeypatch.setattr(_cabi, "load_limit", lambda cap, limit=limit: limit)
         assert cli.main([str(fa), "-max", "12", "-o", str(tmp_path / "sub" / "glue_out")]) == 0
         assert (tmp_path / "glue_out.bed").read_text() == "".join(want)          # basename(prefix), in the CWD (prf:116)
         out = capsys.readouterr().out
         assert "Processing chrB (50 bp)" in out and "Processing empty (0 bp)" in out and "Found 0 repeats" in out
         assert out.rstrip().endswith("Wrote results to glue_out.bed")
     assert len(want) > 30
+
+
+def test_cli_groups_records_by_layout_positions_not_bases():
+    """A load lays every record out as length + max_motif_size positions (inter-record gap), so many short records need
+    far more positions than bases: 150-bp reads with -max 50 fill a load at 3/4 of its bases.  The groups must respect
+    the library's own limit (crf_load_limit), whatever the record shape."""
+    from crf_b200 import _cabi
+    limit = _cabi.load_limit(50)
+    n = 30_000_000                                          # 4.5 Gbp of reads -> 6.0e9 positions: two loads
+    groups = cli.group_records(np.full(n, 150, dtype=np.int64), 50)
+    assert len(groups) == 2 and groups[0][0] == 0 and groups[-1][1] == n
+    for first, last in groups:
+        assert (last - first) * 200 <= limit
+    assert groups[0][1] * 200 + 200 > limit                 # ... and the first one is as full as it can be
+    # patched small limit, ragged records, one record larger than the limit stays alone
+    lengths = [10, 500, 20, 20, 20, 3000, 5]
+    groups = cli.group_records(lengths, 50, limit=600)
+    assert groups == [(0, 1), (1, 2), (2, 5), (5, 6), (6, 7)]
+    assert cli.group_records([], 50) == []
 
 
 def test_tracker_module_compat():
