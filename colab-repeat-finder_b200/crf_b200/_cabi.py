@@ -20,7 +20,8 @@ CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_C
 #: every symbol include/crf.h declares (tests check the library exports all of them)
 EXPORTS = [
     "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
-    "crf_ctx_synchronize", "crf_load_limit", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
+    "crf_ctx_synchronize", "crf_load_limit", "crf_seq_load_packed", "crf_seq_load_packed_ranges", "crf_pack_ascii",
+    "crf_fasta_packed", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
     "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end", "crf_write_rows",
     "crf_fasta_open", "crf_fasta_info", "crf_fasta_data", "crf_fasta_close",
     "crf_xchg_create", "crf_xchg_destroy", "crf_xchg_export", "crf_xchg_connect_ipc", "crf_xchg_connect_local",
@@ -87,6 +88,10 @@ def lib():
         L.crf_ctx_synchronize.argtypes = [vp]
         L.crf_seq_load_ascii.argtypes = [vp, vp, vp, u32, u32, i, P(vp)]
         L.crf_seq_load_ascii_ranges.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, i, P(vp)]
+        L.crf_seq_load_packed.argtypes = [vp, vp, vp, vp, vp, u64, vp, u32, u32, i, P(vp)]
+        L.crf_seq_load_packed_ranges.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, u32, u32, i, P(vp)]
+        L.crf_pack_ascii.argtypes = [vp, u64, u32, vp, vp, vp, vp, u64, P(u64)]
+        L.crf_fasta_packed.argtypes = [vp, u32, P(vp), P(vp), P(vp), P(vp), P(u64)]
         L.crf_seq_set_output_map.argtypes = [vp, vp, vp, vp]
         L.crf_seq_destroy.argtypes = [vp]
         L.crf_seq_info.argtypes = [vp, P(SeqInfo)]
@@ -175,6 +180,13 @@ class Context:
         sub-range per record (crf_seq_load_ascii_ranges)."""
         return Sequence(self, bases, None, max_motif_cap, on_device, ranges=(starts, lengths, own_lo, own_hi))
 
+    def load_packed(self, planes, offsets=None, max_motif_cap=50, ranges=None):
+        """planes: a PackedPlanes (host, from pack_ascii() / Fasta.packed()).  offsets: n_records + 1 record boundaries
+        in the planes' position space (default: one record), or ranges=(starts, lengths, own_lo, own_hi)."""
+        if offsets is None and ranges is None:
+            offsets = np.array([0, planes.n_bases], dtype=np.uint64)
+        return Sequence(self, None, offsets, max_motif_cap, False, ranges=ranges, packed=planes)
+
     def close(self):
         if self._h:
             lib().crf_ctx_destroy(self._h)
@@ -191,10 +203,34 @@ class Sequence:
     """Records resident in HBM as packed planes (crf_seq)."""
 
     @_serialised
-    def __init__(self, ctx, bases, offsets, max_motif_cap, on_device, ranges=None):
+    def __init__(self, ctx, bases, offsets, max_motif_cap, on_device, ranges=None, packed=None):
         self.ctx = ctx
         self._h = ctypes.c_void_p()
         keep = None
+        if packed is not None:
+            pk = packed
+            ex_ptr = pk.exotic.ctypes.data if pk.exotic.size else 0
+            if ranges is not None:
+                starts, lengths, own_lo, own_hi = (None if a is None else np.ascontiguousarray(a, dtype=np.uint64)
+                                                   for a in ranges)
+                self.n_records = starts.size
+                self.lengths = lengths
+                _check(lib().crf_seq_load_packed_ranges(
+                    ctx._h, pk.H_ptr, pk.L_ptr, pk.NM_ptr, ctypes.c_void_p(ex_ptr), pk.exotic.size,
+                    ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(lengths.ctypes.data),
+                    ctypes.c_void_p(own_lo.ctypes.data if own_lo is not None else 0),
+                    ctypes.c_void_p(own_hi.ctypes.data if own_hi is not None else 0),
+                    self.n_records, int(max_motif_cap), int(bool(pk.on_device)), ctypes.byref(self._h)))
+                return
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            if offsets.ndim != 1 or offsets.size < 2:
+                raise ValueError("offsets must hold n_records + 1 entries")
+            self.offsets = offsets
+            self.n_records = offsets.size - 1
+            _check(lib().crf_seq_load_packed(ctx._h, pk.H_ptr, pk.L_ptr, pk.NM_ptr, ctypes.c_void_p(ex_ptr), pk.exotic.size,
+                                             ctypes.c_void_p(offsets.ctypes.data), self.n_records, int(max_motif_cap),
+                                             int(bool(pk.on_device)), ctypes.byref(self._h)))
+            return
         if on_device:
             ptr = int(bases)
             if offsets is None and ranges is None:
@@ -334,6 +370,57 @@ class Sequence:
             pass
 
 
+class PackedPlanes:
+    """2-bit planes + not-ACGT mask of `n_bases` positions (what crf_seq_load_packed uploads): three uint32 arrays (or raw
+    pointers) of ceil(n_bases / 32) words and the sorted exotic list (position << 8 | upper-cased byte)."""
+
+    def __init__(self, n_bases, H, L, NM, exotic, keep=None, on_device=False):
+        self.n_bases = int(n_bases)
+        self.H, self.L, self.NM = H, L, NM
+        self.exotic = np.ascontiguousarray(exotic, dtype=np.uint64)
+        self.on_device = on_device
+        self._keep = keep
+
+        def ptr(a):
+            return ctypes.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else int(a))
+        self.H_ptr, self.L_ptr, self.NM_ptr = ptr(H), ptr(L), ptr(NM)
+
+    @property
+    def n_words(self):
+        return (self.n_bases + 31) // 32
+
+    @property
+    def nbytes(self):
+        return 12 * self.n_words + 8 * int(self.exotic.size)
+
+
+def pack_ascii(bases, n_threads=0, out=None):
+    """Host-only: ASCII bases (bytes / uint8 array) -> PackedPlanes (crf_pack_ascii; threaded, AVX2 when available).
+    out: optional (H, L, NM) uint32 arrays to fill (e.g. views of pinned memory)."""
+    if isinstance(bases, np.ndarray):
+        if bases.dtype != np.uint8 or not bases.flags.c_contiguous:
+            raise ValueError("bases must be a C-contiguous uint8 array")
+        arr = bases
+    else:
+        arr = np.frombuffer(bytes(bases), dtype=np.uint8)
+    n = arr.size
+    nw = (n + 31) // 32
+    H, L, NM = out if out is not None else (np.empty(max(nw, 1), np.uint32) for _ in range(3))
+    cap = 1024
+    while True:
+        exo = np.empty(cap, np.uint64)
+        n_exo = ctypes.c_uint64()
+        rc = lib().crf_pack_ascii(ctypes.c_void_p(arr.ctypes.data if n else 0), n, int(n_threads), ctypes.c_void_p(H.ctypes.data),
+                                  ctypes.c_void_p(L.ctypes.data), ctypes.c_void_p(NM.ctypes.data),
+                                  ctypes.c_void_p(exo.ctypes.data), cap, ctypes.byref(n_exo))
+        if rc == CRF_ERR_CAPACITY:
+            cap = int(n_exo.value) + 16
+            continue
+        _check(rc)
+        break
+    return PackedPlanes(n, H, L, NM, exo[:n_exo.value].copy(), keep=arr)
+
+
 class Xchg:
     """One rank's exchange block for the multi-GPU gather (crf_xchg, csrc/crf_xchg.cuh)."""
 
@@ -419,6 +506,16 @@ class Fasta:
     def record(self, i):
         """uint8 view of record i."""
         return self.bases[int(self.offsets[i]):int(self.offsets[i + 1])]
+
+    def packed(self, n_threads=0):
+        """PackedPlanes of the whole file (crf_fasta_packed: made on first use, page-locked when the reader is)."""
+        H, L, NM, ex = (ctypes.c_void_p() for _ in range(4))
+        n_ex = ctypes.c_uint64()
+        _check(lib().crf_fasta_packed(self._h, int(n_threads), ctypes.byref(H), ctypes.byref(L), ctypes.byref(NM),
+                                      ctypes.byref(ex), ctypes.byref(n_ex)))
+        exotic = np.ctypeslib.as_array(ctypes.cast(ex, ctypes.POINTER(ctypes.c_uint64)), shape=(n_ex.value,)).copy() \
+            if n_ex.value else np.zeros(0, np.uint64)
+        return PackedPlanes(self.total_bases, H.value, L.value, NM.value, exotic, keep=self)
 
     def close(self):
         if self._h:

@@ -146,8 +146,14 @@ class RankScan:
         starts, lens, own_lo, own_hi = self.load_args
         kmax = self.filters[1]
         if len(starts):
-            self.seq = self.ctx.load_ranges(bases, starts - np.uint64(base_offset), lens, own_lo, own_hi,
-                                            max_motif_cap=kmax, on_device=on_device)
+            if isinstance(bases, _cabi.PackedPlanes):          # planes packed on the host: 0.375 B/bp over PCIe
+                if base_offset % 32:
+                    raise ValueError("packed planes must start at a multiple of 32 positions")
+                self.seq = self.ctx.load_packed(bases, max_motif_cap=kmax,
+                                                ranges=(starts - np.uint64(base_offset), lens, own_lo, own_hi))
+            else:
+                self.seq = self.ctx.load_ranges(bases, starts - np.uint64(base_offset), lens, own_lo, own_hi,
+                                                max_motif_cap=kmax, on_device=on_device)
             if self.reads:
                 if self.world > 1:
                     self.seq.set_output_map(out_record=np.arange(self.first_record, self.first_record + len(starts),
@@ -256,8 +262,8 @@ class RankScan:
 
 def scan_on_devices(devices, bases, record_starts, lengths, kmin, kmax, min_repeats, min_span, chunk=partition.DEFAULT_CHUNK,
                     halo=partition.DEFAULT_HALO, reads=False, contexts=None, knobs=None, timeout_s=None):
-    """One process, one thread per device: scan host `bases` on all `devices`; returns (record, start, end, k) of the
-    whole job.  `contexts`: reuse these _cabi.Context objects (one per device) instead of creating new ones."""
+    """One process, one thread per device: scan host `bases` (a uint8 array, or _cabi.PackedPlanes) on all `devices`;
+    returns (record, start, end, k) of the whole job.  `contexts`: reuse these _cabi.Context objects (one per device) instead of creating new ones."""
     world = len(devices)
     comms = ThreadComm.split(world)
     ctxs = list(contexts) if contexts else [_cabi.Context(d) for d in devices]

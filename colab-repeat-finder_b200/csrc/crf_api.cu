@@ -180,6 +180,16 @@ extern "C" const char *crf_last_error(void) { return g_err; }
 extern "C" int crf_abi_version(void) { return 1; }
 
 // ---- context ------------------------------------------------------------------------------------
+// CUDA loads a kernel lazily at its first launch, and that load may wait until the kernels already running on the device
+// have finished.  A step of the multi-GPU gather has tiny kernels that wait for peers; a first launch must never queue
+// up behind one of them, so every kernel of the library is loaded when a context is created.
+template <typename K>
+static cudaError_t preload(K kernel) {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, kernel);
+}
+static cudaError_t preload_kernels();
+
 extern "C" int crf_ctx_create(int device, crf_ctx **out) {
     if (!out) { set_err("crf_ctx_create: null out pointer"); return CRF_ERR_ARG; }
     *out = nullptr;
@@ -202,6 +212,7 @@ extern "C" int crf_ctx_create(int device, crf_ctx **out) {
     for (auto &ev : c->ev)
         if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_counters, C_COUNT * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = preload_kernels();
     if (e != cudaSuccess) { delete c; set_err("cudaStreamCreate failed: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
     c->stream = c->own_stream;
     *out = c;
@@ -288,9 +299,19 @@ static uint64_t layout_limit(uint32_t max_motif_cap) {
 // One load holds at most this many layout positions: sum over records of (length + max_motif_cap).
 extern "C" uint64_t crf_load_limit(uint32_t max_motif_cap) { return layout_limit(max_motif_cap); }
 
-static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, const uint64_t *lengths,
+// What a load reads: ASCII bytes (one per base) or planes packed on the host (crf_pack_ascii).
+struct LoadSource {
+    const uint8_t *bases = nullptr;                     // ASCII
+    const uint32_t *pH = nullptr, *pL = nullptr, *pN = nullptr;   // packed: source position p = bit p & 31 of word p >> 5
+    const uint64_t *exotic = nullptr;                   // packed: (source position << 8 | upper-cased byte), ascending
+    uint64_t n_exotic = 0;
+    bool packed() const { return pH != nullptr; }
+};
+
+static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, const uint64_t *lengths,
                      const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
                      int on_device, crf_seq *s) {
+    const char *who = src.packed() ? "crf_seq_load_packed" : "crf_seq_load_ascii";
     cudaStream_t st = c->stream;
     s->ctx = c;
     s->n_records = n_records;
@@ -321,8 +342,8 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
         }
     }
     if (pos > limit) {
-        set_err("crf_seq_load_ascii: the records need more than %llu layout positions (per-load limit); split them "
-                "over several loads", (unsigned long long)limit);
+        set_err("%s: the records need more than %llu layout positions (per-load limit, crf_load_limit); split them "
+                "over several loads", who, (unsigned long long)limit);
         return CRF_ERR_UNSUPPORTED;
     }
     if (src_lo > src_hi) src_lo = src_hi = 0;
@@ -331,36 +352,79 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     s->n_words_alloc = (s->n_words + TILE_WORDS_MAX - 1) / TILE_WORDS_MAX * TILE_WORDS_MAX + (max_motif_cap >> 5) + 16;
 
     CU(cudaEventRecord(s->ev[0], st));
-    const uint8_t *d_src = bases;   // device view; record r starts at d_src[starts[r] - src_base]
-    uint64_t src_base = 0;
+    // The source span the records cover (units may overlap) goes up in chunks on a second stream while the pack kernel
+    // works on the layout words whose source has already arrived (the PCIe copy is ~10x longer than the packing, which
+    // then hides behind it).  Unit of the span: bytes (ASCII) or positions rounded out to whole 32-bit words (packed).
+    const bool packed = src.packed();
+    if (packed) { src_lo &= ~31ull; src_hi = (src_hi + 31) & ~31ull; }
+    const uint64_t span = src_hi - src_lo;                               // positions
+    const uint64_t UPLOAD_CHUNK = packed ? (512ull << 20) : (64ull << 20);   // positions per chunk (64 MB either way)
+    const bool pipelined = !on_device && span > 2 * UPLOAD_CHUNK;
+    const uint8_t *d_src = src.bases;                                    // device views of the source
+    const uint32_t *d_pH = src.pH, *d_pL = src.pL, *d_pN = src.pN;
+    uint64_t src_base = 0;                                               // source position of the device view's first element
     uint8_t *d_src_own = nullptr;
+    uint32_t *d_planes_own = nullptr;                                    // 3 x (span / 32 + 1) words
     uint64_t *d_src_start = nullptr;
-    // A long host buffer goes up in chunks on a second stream while the pack kernel works on the layout words whose
-    // bytes have already arrived (the PCIe copy is ~10x longer than the packing, which then hides behind it).
-    const uint64_t UPLOAD_CHUNK = 64ull << 20;
-    const uint64_t src_bytes = src_hi - src_lo;
-    const bool pipelined = !on_device && src_bytes > 2 * UPLOAD_CHUNK;
-    if (!on_device) {               // the span the records cover (units may overlap)
-        CHECK(dev_alloc(&d_src_own, (size_t)src_bytes));
-        if (src_bytes && !pipelined) CU(cudaMemcpyAsync(d_src_own, bases + src_lo, src_bytes, cudaMemcpyHostToDevice, st));
-        d_src = d_src_own;
+    const uint64_t span_words = span / 32 + 1;                           // + 1: repack_kernel reads word wi + 1
+    if (!on_device) {
+        if (packed) {
+            CHECK(dev_alloc(&d_planes_own, 3 * (size_t)span_words));
+            d_pH = d_planes_own; d_pL = d_planes_own + span_words; d_pN = d_planes_own + 2 * span_words;
+        } else {
+            CHECK(dev_alloc(&d_src_own, (size_t)span));
+            d_src = d_src_own;
+        }
         src_base = src_lo;
     }
-    std::vector<uint64_t> rel(n_records);
-    for (uint32_t r = 0; r < n_records; ++r) rel[r] = s->h_rec_len[r] ? starts[r] - src_base : 0;
+    auto copy_span = [&](uint64_t lo, uint64_t n, cudaStream_t cs) -> cudaError_t {    // source positions [src_lo + lo, + n)
+        if (!n) return cudaSuccess;
+        if (!packed) return cudaMemcpyAsync(d_src_own + lo, src.bases + src_lo + lo, n, cudaMemcpyHostToDevice, cs);
+        const uint64_t w0 = lo / 32, nw = (n + 31) / 32, h0 = src_lo / 32 + w0;
+        cudaError_t e = cudaMemcpyAsync(d_planes_own + w0, src.pH + h0, nw * 4, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_planes_own + span_words + w0, src.pL + h0, nw * 4, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_planes_own + 2 * span_words + w0, src.pN + h0, nw * 4, cudaMemcpyHostToDevice, cs);
+        return e;
+    };
+    auto free_sources = [&]() {
+        if (d_src_own) ctx_free(d_src_own);
+        if (d_planes_own) ctx_free(d_planes_own);
+        if (d_src_start) ctx_free(d_src_start);
+        d_src_own = nullptr; d_planes_own = nullptr; d_src_start = nullptr;
+    };
+    std::vector<uint64_t> rel(n_records);                                // record starts relative to the device view
+    for (uint32_t r = 0; r < n_records; ++r) rel[r] = s->h_rec_len[r] ? starts[r] - (packed ? 0 : src_base) : 0;
     std::vector<uint32_t> olo, ohi;
     if (own_lo && own_hi) {
         olo.resize(n_records);
         ohi.resize(n_records);
         for (uint32_t r = 0; r < n_records; ++r) {
             if (own_lo[r] > own_hi[r] || own_hi[r] > lengths[r]) {
-                set_err("crf_seq_load_ascii_ranges: own range of record %u is not inside the record", r);
-                if (d_src_own) ctx_free(d_src_own);
+                set_err("%s_ranges: own range of record %u is not inside the record", who, r);
+                free_sources();
                 return CRF_ERR_ARG;
             }
             olo[r] = s->h_rec_dev_off[r] + (uint32_t)own_lo[r];
             ohi[r] = s->h_rec_dev_off[r] + (uint32_t)own_hi[r];
         }
+    }
+    // exotic symbols of a packed source: source positions -> layout positions (a symbol in the halo two units share
+    // appears once per unit); records in ascending source order are walked with one cursor
+    std::vector<uint64_t> ex_layout;
+    if (packed && src.n_exotic) {
+        const uint64_t *ex = src.exotic, ne = src.n_exotic;
+        uint64_t cur = 0, prev_start = 0;
+        for (uint32_t r = 0; r < n_records; ++r) {
+            const uint64_t a = starts[r], b = a + s->h_rec_len[r];
+            if (a == b) continue;
+            if (a < prev_start || (cur < ne && a > (ex[cur] >> 8) + (1u << 16)))
+                cur = (uint64_t)(std::lower_bound(ex, ex + ne, a << 8) - ex);   // out of order, or far ahead: bisect
+            while (cur < ne && (ex[cur] >> 8) < a) ++cur;
+            prev_start = a;
+            for (uint64_t i = cur; i < ne && (ex[i] >> 8) < b; ++i)
+                ex_layout.push_back((((ex[i] >> 8) - a + s->h_rec_dev_off[r]) << 8) | (ex[i] & 0xFF));
+        }
+        std::sort(ex_layout.begin(), ex_layout.end());
     }
     int rc = dev_alloc(&d_src_start, n_records);
     if (!rc) rc = dev_alloc(&s->d_rec_len, n_records);
@@ -371,7 +435,8 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     if (!rc) rc = dev_alloc(&s->L, s->n_words_alloc);
     if (!rc) rc = dev_alloc(&s->NM, s->n_words_alloc);
     if (!rc) rc = dev_alloc(&s->X, s->n_words_alloc);
-    s->ex_cap = std::min<uint32_t>(EX_CAP, next_pow2((uint32_t)std::min<uint64_t>(std::max<uint64_t>(total, 16), EX_CAP)));
+    if (packed) s->ex_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ex_layout.size(), 16), 0xFFFFFFFFull);
+    else s->ex_cap = std::min<uint32_t>(EX_CAP, next_pow2((uint32_t)std::min<uint64_t>(std::max<uint64_t>(total, 16), EX_CAP)));
     if (!rc) rc = dev_alloc(&s->ex_key, s->ex_cap);
     cudaError_t e = cudaSuccess;
     if (!rc) {
@@ -382,67 +447,100 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
         if (e == cudaSuccess && !olo.empty()) e = cudaMemcpyAsync(s->d_own_lo, olo.data(), n4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess && !olo.empty()) e = cudaMemcpyAsync(s->d_own_hi, ohi.data(), n4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st);
+        if (e == cudaSuccess && !ex_layout.empty())
+            e = cudaMemcpyAsync(s->ex_key, ex_layout.data(), ex_layout.size() * 8, cudaMemcpyHostToDevice, st);
     }
-    if (!rc && e == cudaSuccess) {
-        PackParams pp;
-        pp.src = d_src; pp.rec_src_start = d_src_start; pp.rec_len = s->d_rec_len; pp.rec_dev_off = s->d_rec_dev_off;
-        pp.n_records = n_records;
-        pp.H = s->H; pp.L = s->L; pp.NM = s->NM; pp.X = s->X;
-        pp.ex_key = s->ex_key; pp.ex_cap = s->ex_cap; pp.ex_count = s->d_counters;
-        if (!pipelined) {
-            pp.w_lo = 0; pp.w_hi = s->n_words_alloc;
-            pack_kernel<<<(s->n_words_alloc + 255) / 256, 256, 0, st>>>(pp);
-            e = cudaGetLastError();
+    // one launch of the packer over layout words [w_lo, w_hi)
+    auto launch_pack = [&](uint32_t w_lo, uint32_t w_hi) -> cudaError_t {
+        if (w_hi <= w_lo) return cudaSuccess;
+        if (packed) {
+            RepackParams rp;
+            rp.sH = d_pH; rp.sL = d_pL; rp.sN = d_pN; rp.src_base = src_base;
+            rp.rec_src_start = d_src_start; rp.rec_len = s->d_rec_len; rp.rec_dev_off = s->d_rec_dev_off;
+            rp.n_records = n_records; rp.w_lo = w_lo; rp.w_hi = w_hi;
+            rp.H = s->H; rp.L = s->L; rp.NM = s->NM; rp.X = s->X;
+            repack_kernel<<<(w_hi - w_lo + 255) / 256, 256, 0, st>>>(rp);
         } else {
-            // src_end[r]: running maximum of where records 0..r end in the source, so "the first record whose bytes
-            // are not all there" bounds the layout words that can be packed, whatever order the records come in
+            PackParams pp;
+            pp.src = d_src; pp.rec_src_start = d_src_start; pp.rec_len = s->d_rec_len; pp.rec_dev_off = s->d_rec_dev_off;
+            pp.n_records = n_records;
+            pp.H = s->H; pp.L = s->L; pp.NM = s->NM; pp.X = s->X;
+            pp.ex_key = s->ex_key; pp.ex_cap = s->ex_cap; pp.ex_count = s->d_counters;
+            pp.w_lo = w_lo; pp.w_hi = w_hi;
+            pack_kernel<<<(w_hi - w_lo + 255) / 256, 256, 0, st>>>(pp);
+        }
+        return cudaGetLastError();
+    };
+    if (!rc && e == cudaSuccess) {
+        if (!pipelined) {
+            if (!on_device) e = copy_span(0, span, st);
+            if (e == cudaSuccess) e = launch_pack(0, s->n_words_alloc);
+        } else {
+            // src_end[r]: running maximum of where records 0..r end in the source, so "the first record whose source is
+            // not all there" bounds the layout words that can be packed, whatever order the records come in
             std::vector<uint64_t> src_end(n_records);
             uint64_t run = 0;
             for (uint32_t r = 0; r < n_records; ++r) {
-                if (s->h_rec_len[r]) run = std::max(run, rel[r] + s->h_rec_len[r]);
+                if (s->h_rec_len[r]) run = std::max(run, starts[r] - src_lo + s->h_rec_len[r]);
                 src_end[r] = run;
             }
             e = cudaEventRecord(c->copy_done, st);                       // the copies start after what is queued on st
             if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0);
             uint32_t w_done = 0;
-            for (uint64_t b = 0; b < src_bytes && e == cudaSuccess; b += UPLOAD_CHUNK) {
-                const uint64_t nb = std::min(UPLOAD_CHUNK, src_bytes - b), avail = b + nb;
-                e = cudaMemcpyAsync(d_src_own + b, bases + src_lo + b, nb, cudaMemcpyHostToDevice, c->copy_stream);
+            for (uint64_t b = 0; b < span && e == cudaSuccess; b += UPLOAD_CHUNK) {
+                const uint64_t nb = std::min(UPLOAD_CHUNK, span - b), avail = b + nb;
+                e = copy_span(b, nb, c->copy_stream);
                 if (e == cudaSuccess) e = cudaEventRecord(c->copy_done, c->copy_stream);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->copy_done, 0);
                 if (e != cudaSuccess) break;
                 uint32_t w_hi = s->n_words_alloc;
-                if (avail < src_bytes) {
+                if (avail < span) {
                     const uint32_t r = (uint32_t)(std::upper_bound(src_end.begin(), src_end.end(), avail) - src_end.begin());
                     if (r < n_records) {
-                        const uint64_t have = avail > rel[r] ? std::min<uint64_t>(avail - rel[r], s->h_rec_len[r]) : 0;
+                        const uint64_t r0 = starts[r] - src_lo;
+                        const uint64_t have = avail > r0 ? std::min<uint64_t>(avail - r0, s->h_rec_len[r]) : 0;
                         w_hi = (uint32_t)((s->h_rec_dev_off[r] + have) >> 5);
                     }
                 }
                 if (w_hi > w_done) {
-                    pp.w_lo = w_done; pp.w_hi = w_hi;
-                    pack_kernel<<<(w_hi - w_done + 255) / 256, 256, 0, st>>>(pp);
-                    e = cudaGetLastError();
+                    e = launch_pack(w_done, w_hi);
                     w_done = w_hi;
                 }
             }
             if (e != cudaSuccess) cudaStreamSynchronize(c->copy_stream);   // nothing may still write the buffer freed below
         }
+        if (e == cudaSuccess && packed && !ex_layout.empty()) {
+            exotic_apply_kernel<<<((uint32_t)ex_layout.size() + 255) / 256, 256, 0, st>>>(s->ex_key, (uint32_t)ex_layout.size(),
+                                                                                          s->H, s->L, s->X);
+            e = cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // also keeps rel/len32/olo alive long enough
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // also keeps rel/len32/olo/ex_layout alive long enough
     }
-    if (d_src_own) ctx_free(d_src_own);
-    if (d_src_start) ctx_free(d_src_start);
-    if (rc) return rc;
-    if (e != cudaSuccess) { set_err("crf_seq_load_ascii: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
+    if (rc) { free_sources(); return rc; }
+    if (e != cudaSuccess) { free_sources(); set_err("%s: %s", who, cudaGetErrorString(e)); return CRF_ERR_CUDA; }
 
-    const unsigned long long nex = s->h_counters[0];
-    if (nex > s->ex_cap) {
-        set_err("crf_seq_load_ascii: %llu symbols other than A,C,G,T,N; at most %u are supported per load", nex, EX_CAP);
-        return CRF_ERR_UNSUPPORTED;
+    unsigned long long nex = packed ? ex_layout.size() : s->h_counters[0];
+    if (!packed && nex > s->ex_cap) {
+        // more symbols other than A,C,G,T,N than the list held: size it to the count and pack once more (the source is
+        // still on the device)
+        if (nex > 0x7FFFFFFFull) { free_sources(); set_err("%s: more than 2^31 symbols other than A,C,G,T,N", who); return CRF_ERR_UNSUPPORTED; }
+        dev_free(s->ex_key);
+        s->ex_cap = next_pow2((uint32_t)nex);
+        rc = dev_alloc(&s->ex_key, s->ex_cap);
+        if (!rc) {
+            e = cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long), st);
+            if (e == cudaSuccess) e = launch_pack(0, s->n_words_alloc);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (rc) { free_sources(); return rc; }
+        if (e != cudaSuccess) { free_sources(); set_err("%s: %s", who, cudaGetErrorString(e)); return CRF_ERR_CUDA; }
+        nex = s->h_counters[0];
     }
+    free_sources();
     s->n_exotic = (uint32_t)nex;
-    if (s->n_exotic > 1) CHECK(bitonic_sort(st, s->ex_key, nullptr, s->n_exotic, nullptr));
+    if (!packed && s->n_exotic > 1) CHECK(bitonic_sort(st, s->ex_key, nullptr, s->n_exotic, nullptr));
     CU(cudaEventRecord(s->ev[1], st));
     CU(cudaStreamSynchronize(st));
     float ms = 0;
@@ -458,28 +556,30 @@ static int load_impl(crf_ctx *c, const uint8_t *bases, const uint64_t *starts, c
     return CRF_OK;
 }
 
-extern "C" int crf_seq_load_ascii_ranges(crf_ctx *c, const uint8_t *bases, const uint64_t *starts,
-                                         const uint64_t *lengths, const uint64_t *own_lo, const uint64_t *own_hi,
-                                         uint32_t n_records, uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
-    if (!c || !out || !starts || !lengths) { set_err("crf_seq_load_ascii: null argument"); return CRF_ERR_ARG; }
+static int load_checked(crf_ctx *c, const LoadSource &src, const uint64_t *starts, const uint64_t *lengths,
+                        const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
+                        int on_device, crf_seq **out, const char *who) {
+    if (!c || !out || !starts || !lengths) { set_err("%s: null argument", who); return CRF_ERR_ARG; }
     *out = nullptr;
-    if (n_records == 0) { set_err("crf_seq_load_ascii: n_records must be >= 1"); return CRF_ERR_ARG; }
-    if ((own_lo == nullptr) != (own_hi == nullptr)) { set_err("crf_seq_load_ascii_ranges: own_lo and own_hi go together"); return CRF_ERR_ARG; }
+    if (n_records == 0) { set_err("%s: n_records must be >= 1", who); return CRF_ERR_ARG; }
+    if ((own_lo == nullptr) != (own_hi == nullptr)) { set_err("%s_ranges: own_lo and own_hi go together", who); return CRF_ERR_ARG; }
     if (max_motif_cap < 1 || max_motif_cap > MAX_K) {
-        set_err("crf_seq_load_ascii: max_motif_cap %u not in [1, %u]", max_motif_cap, MAX_K);
+        set_err("%s: max_motif_cap %u not in [1, %u]", who, max_motif_cap, MAX_K);
         return max_motif_cap < 1 ? CRF_ERR_ARG : CRF_ERR_UNSUPPORTED;
     }
-    if (!bases) {
+    const bool have_src = src.packed() ? (src.pL && src.pN) : (src.bases != nullptr);
+    if (!have_src) {
         for (uint32_t r = 0; r < n_records; ++r)
-            if (lengths[r]) { set_err("crf_seq_load_ascii: null bases"); return CRF_ERR_ARG; }
+            if (lengths[r]) { set_err("%s: null %s", who, src.packed() ? "plane" : "bases"); return CRF_ERR_ARG; }
     }
+    if (src.n_exotic && !src.exotic) { set_err("%s: null exotic list", who); return CRF_ERR_ARG; }
     CU(cudaSetDevice(c->device));
     g_ctx = c;
     crf_seq *s = new (std::nothrow) crf_seq;
     if (!s) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
     int rc;
     try {
-        rc = load_impl(c, bases, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, bases_on_device, s);
+        rc = load_impl(c, src, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, on_device, s);
     } catch (const std::bad_alloc &) {
         set_err("out of host memory");
         rc = CRF_ERR_NOMEM;
@@ -489,20 +589,55 @@ extern "C" int crf_seq_load_ascii_ranges(crf_ctx *c, const uint8_t *bases, const
     return CRF_OK;
 }
 
-extern "C" int crf_seq_load_ascii(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
-                                  uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
-    if (!offsets) { set_err("crf_seq_load_ascii: null argument"); return CRF_ERR_ARG; }
-    if (n_records == 0) { set_err("crf_seq_load_ascii: n_records must be >= 1"); return CRF_ERR_ARG; }
-    std::vector<uint64_t> lengths;
+static int offsets_to_lengths(const uint64_t *offsets, uint32_t n_records, std::vector<uint64_t> &lengths, const char *who) {
+    if (!offsets) { set_err("%s: null argument", who); return CRF_ERR_ARG; }
+    if (n_records == 0) { set_err("%s: n_records must be >= 1", who); return CRF_ERR_ARG; }
     try {
         lengths.resize(n_records);
     } catch (const std::bad_alloc &) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
     for (uint32_t r = 0; r < n_records; ++r) {
-        if (offsets[r + 1] < offsets[r]) { set_err("crf_seq_load_ascii: offsets must be non-decreasing"); return CRF_ERR_ARG; }
+        if (offsets[r + 1] < offsets[r]) { set_err("%s: offsets must be non-decreasing", who); return CRF_ERR_ARG; }
         lengths[r] = offsets[r + 1] - offsets[r];
     }
+    return CRF_OK;
+}
+
+extern "C" int crf_seq_load_ascii_ranges(crf_ctx *c, const uint8_t *bases, const uint64_t *starts,
+                                         const uint64_t *lengths, const uint64_t *own_lo, const uint64_t *own_hi,
+                                         uint32_t n_records, uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
+    LoadSource src;
+    src.bases = bases;
+    return load_checked(c, src, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, bases_on_device, out, "crf_seq_load_ascii");
+}
+
+extern "C" int crf_seq_load_ascii(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
+                                  uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
+    std::vector<uint64_t> lengths;
+    CHECK(offsets_to_lengths(offsets, n_records, lengths, "crf_seq_load_ascii"));
     return crf_seq_load_ascii_ranges(c, bases, offsets, lengths.data(), nullptr, nullptr, n_records, max_motif_cap,
                                      bases_on_device, out);
+}
+
+extern "C" int crf_seq_load_packed_ranges(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint32_t *NM,
+                                          const uint64_t *exotic, uint64_t n_exotic, const uint64_t *starts,
+                                          const uint64_t *lengths, const uint64_t *own_lo, const uint64_t *own_hi,
+                                          uint32_t n_records, uint32_t max_motif_cap, int planes_on_device, crf_seq **out) {
+    if (!H) {
+        set_err("crf_seq_load_packed: null plane");
+        return CRF_ERR_ARG;
+    }
+    LoadSource src;
+    src.pH = H; src.pL = L; src.pN = NM; src.exotic = exotic; src.n_exotic = n_exotic;
+    return load_checked(c, src, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, planes_on_device, out, "crf_seq_load_packed");
+}
+
+extern "C" int crf_seq_load_packed(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint32_t *NM,
+                                   const uint64_t *exotic, uint64_t n_exotic, const uint64_t *offsets, uint32_t n_records,
+                                   uint32_t max_motif_cap, int planes_on_device, crf_seq **out) {
+    std::vector<uint64_t> lengths;
+    CHECK(offsets_to_lengths(offsets, n_records, lengths, "crf_seq_load_packed"));
+    return crf_seq_load_packed_ranges(c, H, L, NM, exotic, n_exotic, offsets, lengths.data(), nullptr, nullptr, n_records,
+                                      max_motif_cap, planes_on_device, out);
 }
 
 extern "C" int crf_seq_destroy(crf_seq *s) {
@@ -1081,6 +1216,7 @@ static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted) {
     pp.res_cap = s->res_cap; pp.open_cap = s->open_cap;
     pp.trusted = trusted ? 1u : 0u;
     pp.timeout_ns = x->timeout_ns;
+    publish_kernel<<<1, 32, 0, st>>>(pp);
     push_kernel<<<148 * 2, 256, 0, st>>>(pp);
     SettleParams sp = {};
     sp.self = (XchgBlock *)x->base;
@@ -1108,7 +1244,7 @@ extern "C" int crf_scan_gather(crf_seq *s, const crf_scan_params *pr, crf_xchg *
     CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CHECK(xchg_enqueue(s, x, false));
     x->pending_seq = s;
-    s->plan->launches += 2;
+    s->plan->launches += 3;
     return CRF_OK;
 }
 
@@ -1198,6 +1334,30 @@ extern "C" int crf_xchg_patch_end(crf_xchg *x, const uint64_t *rows, const uint3
     return CRF_OK;
 }
 
+static cudaError_t preload_kernels() {
+    cudaError_t e = preload(scan_kernel<1>);
+    if (e == cudaSuccess) e = preload(scan_kernel<2>);
+    if (e == cudaSuccess) e = preload(scan_kernel<4>);
+    if (e == cudaSuccess) e = preload(scan_kernel<8>);
+    if (e == cudaSuccess) e = preload(scan_kernel<16>);
+    if (e == cudaSuccess) e = preload(pack_kernel);
+    if (e == cudaSuccess) e = preload(repack_kernel);
+    if (e == cudaSuccess) e = preload(exotic_apply_kernel);
+    if (e == cudaSuccess) e = preload(tile_offsets_kernel);
+    if (e == cudaSuccess) e = preload(spill_sort_small_kernel);
+    if (e == cudaSuccess) e = preload(gather_kernel);
+    if (e == cudaSuccess) e = preload(translate_kernel);
+    if (e == cudaSuccess) e = preload(single_copy_filter_kernel);
+    if (e == cudaSuccess) e = preload(bitonic_step_kernel);
+    if (e == cudaSuccess) e = preload(fill_u64_kernel);
+    if (e == cudaSuccess) e = preload(run_end_kernel);
+    if (e == cudaSuccess) e = preload(publish_kernel);
+    if (e == cudaSuccess) e = preload(push_kernel);
+    if (e == cudaSuccess) e = preload(settle_kernel);
+    if (e == cudaSuccess) e = preload(patch_rows_kernel);
+    return e;
+}
+
 // ---- text output (host only) ----------------------------------------------------------------------
 static inline char *put_u32(char *p, uint32_t v) {
     char tmp[10];
@@ -1261,3 +1421,4 @@ extern "C" int crf_write_rows(const char *path, int append, int tsv, const char 
 }
 
 #include "crf_fasta.h"
+#include "crf_pack.h"

@@ -78,6 +78,80 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     p.X[w] = x;
 }
 
+// ---- repack: 2-bit planes + mask as packed on the HOST (crf_pack_ascii: all records back to back, position p of the
+// source = bit p & 31 of word p >> 5) -> the device layout (records separated by masked gaps, filler codes at masked
+// positions).  Same result as pack_kernel on the ASCII bytes, at 0.375 B/bp of input instead of 1 B/bp. ----------------
+struct RepackParams {
+    const uint32_t *sH, *sL, *sN;   // source planes; word 0 holds source positions [src_base, src_base + 32)
+    uint64_t src_base;              // multiple of 32
+    const uint64_t *rec_src_start;  // source position of each record's first base
+    const uint32_t *rec_len;
+    const uint32_t *rec_dev_off;
+    uint32_t n_records;
+    uint32_t w_lo, w_hi;            // layout words this launch packs
+    uint32_t *H, *L, *NM, *X;
+};
+
+__global__ void __launch_bounds__(256) repack_kernel(const RepackParams p) {
+    const uint32_t w = p.w_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= p.w_hi) return;
+    const uint32_t p0 = w << 5;
+    uint32_t h = 0, l = 0, nm = 0xFFFFFFFFu;                 // gaps and pads are masked
+    if (p.n_records) {
+        uint32_t lo = 0, hi = p.n_records - 1;               // last record that starts at or before p0
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (p.rec_dev_off[mid] <= p0) lo = mid; else hi = mid - 1;
+        }
+        const uint64_t p1 = (uint64_t)p0 + 32;
+        for (uint32_t r = lo; r < p.n_records; ++r) {
+            const uint32_t dev0 = p.rec_dev_off[r];
+            if ((uint64_t)dev0 >= p1) break;
+            const uint64_t rec_end = (uint64_t)dev0 + p.rec_len[r];
+            const uint64_t a = max((uint64_t)p0, (uint64_t)dev0), b = min(p1, rec_end);
+            if (a >= b) continue;
+            const uint32_t nbits = (uint32_t)(b - a), place = (uint32_t)(a - p0);
+            const uint64_t sbit = p.rec_src_start[r] - p.src_base + (a - dev0);
+            const uint64_t wi = sbit >> 5;
+            const uint32_t sh = (uint32_t)sbit & 31u;
+            const uint32_t mask = nbits == 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u);
+            const uint64_t wj = (sh && nbits > 32u - sh) ? wi + 1 : wi;   // never read beyond the last word that holds data
+            const uint32_t eh = __funnelshift_r(p.sH[wi], p.sH[wj], sh) & mask;
+            const uint32_t el = __funnelshift_r(p.sL[wi], p.sL[wj], sh) & mask;
+            const uint32_t en = __funnelshift_r(p.sN[wi], p.sN[wj], sh) & mask;
+            h |= eh << place;
+            l |= el << place;
+            nm = (nm & ~(mask << place)) | (en << place);
+        }
+    }
+    h &= ~nm;
+    l &= ~nm;
+    for (uint32_t m = nm; m;) {                               // aperiodic filler at masked positions (see pack_kernel)
+        const uint32_t b = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t code = hash32(p0 + b) & 3;
+        h |= (code >> 1) << b;
+        l |= (code & 1) << b;
+    }
+    p.H[w] = h;
+    p.L[w] = l;
+    p.NM[w] = nm;
+    p.X[w] = 0;
+}
+
+// exotic symbols of a packed load: (layout position << 8 | letter), already sorted: mark them in X and give them the
+// letter's filler code (equal letters -> equal codes, pack_kernel)
+__global__ void __launch_bounds__(256) exotic_apply_kernel(const uint64_t *ex_key, uint32_t n, uint32_t *H, uint32_t *L, uint32_t *X) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = ex_key[i];
+    const uint32_t pos = (uint32_t)(key >> 8), c = (uint32_t)(key & 0xFF);
+    const uint32_t code = hash32(c * 0x9E3779B1u) & 3, w = pos >> 5, bit = 1u << (pos & 31);
+    if (code >> 1) atomicOr(&H[w], bit); else atomicAnd(&H[w], ~bit);
+    if (code & 1) atomicOr(&L[w], bit); else atomicAnd(&L[w], ~bit);
+    atomicOr(&X[w], bit);
+}
+
 // ---- assembly: tile segments -> one (start, end)-sorted list --------------------------------
 // exclusive prefix sum of tile_cnt (single block, four tiles per thread and step; n_tiles is tens of
 // thousands at most, the arrays are allocated with slack for the vector loads)

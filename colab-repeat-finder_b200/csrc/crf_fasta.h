@@ -26,6 +26,11 @@ struct crf_fasta {
     uint8_t *bases = nullptr;
     uint64_t total = 0;
     bool pinned = false;
+    // packed planes (crf_fasta_packed): H, L, NM of plane_words words each, one allocation
+    uint32_t *planes = nullptr;
+    uint64_t plane_words = 0;
+    bool planes_pinned = false;
+    std::vector<uint64_t> exotic;
 };
 
 namespace fasta_detail {
@@ -387,6 +392,8 @@ extern "C" int crf_fasta_close(crf_fasta *fa) {
     if (!fa) return CRF_OK;
     if (fa->pinned) cudaFreeHost(fa->bases);
     else free(fa->bases);
+    if (fa->planes_pinned) cudaFreeHost(fa->planes);
+    else free(fa->planes);
     delete fa;
     return CRF_OK;
 }

@@ -8,10 +8,10 @@
 //
 //   * every rank owns one exchange block in its HBM (XchgBlock + on the root the row buffer), mapped into
 //     every peer's address space (CUDA IPC between processes, plain peer access inside one process);
-//   * push_kernel (one launch per rank and step): publishes this rank's row count to every peer with one
-//     8-byte store that carries the step number (so the store is its own flag), waits for the counts of the
-//     ranks before it -- they arrive in its OWN memory --, and stores its rows straight into the root's
-//     buffer at the prefix offset (coalesced 4-byte peer stores); the last block then posts a done word on the root;
+//   * publish_kernel (one warp per rank and step): publishes this rank's row count to every peer with one
+//     8-byte store that carries the step number (so the store is its own flag) and waits for the counts of the
+//     ranks before it -- they arrive in its OWN memory; push_kernel then stores the rank's rows straight into the
+//     root's buffer at the prefix offset (coalesced 4-byte peer stores) and its last block posts a done word there;
 //   * settle_kernel (one warp): waits until the counts of ALL ranks (on the root also the done words) of this
 //     step have arrived and writes status / totals for the host.
 // Two slots per rank (step parity) are enough: no rank can be two steps ahead of another one, because a step
@@ -40,7 +40,7 @@ struct XchgBlock {
     unsigned long long done_slot[2][XCHG_MAX_WORLD];   // root only: rows of [rank] have landed (value = its open-ended rows)
     unsigned long long my_offset;                      // where this rank's rows start in the root buffer (last push)
     unsigned int blocks_done;                          // last-block counter of push_kernel
-    unsigned int pad_;
+    unsigned int push_ok;                              // publish_kernel: this rank may push (nothing void, everything fits)
     unsigned long long result[XCHG_RESULT_WORDS];      // settle_kernel: [0] status [1] total rows [2] total open
                                                        // [3] my offset [4] some rank has open-ended rows
                                                        // [8 + r] rows of rank r
@@ -97,34 +97,45 @@ struct PushParams {
     unsigned long long timeout_ns;
 };
 
-__global__ void __launch_bounds__(256) push_kernel(const PushParams p) {
-    __shared__ unsigned long long s_off;
-    __shared__ uint32_t s_ok;
-    const uint32_t par = p.step & 1u;
+// One warp per rank and step: publish my row count, wait for the counts of the ranks before me (lane q waits for rank
+// q; they land in my OWN memory) and leave my prefix offset for push_kernel.  Only this warp ever spins -- the copy
+// kernel behind it starts when its offset is known.
+__global__ void __launch_bounds__(32) publish_kernel(const PushParams p) {
+    const uint32_t lane = threadIdx.x, par = p.step & 1u;
     const unsigned long long n_stage = p.counters[C_STAGE], n_spill = p.counters[C_SPILL];
     const unsigned long long n_total = p.counters[C_TOTAL], n_open = p.counters[C_OPEN];
     // the conditions under which crf_scan would have grown a buffer, sorted a long spill list or re-run
     const bool valid = p.trusted || (n_stage <= p.res_cap && n_spill <= p.res_cap && n_spill <= SPILL_SMALL &&
                                      n_total <= p.res_cap && n_open <= p.open_cap);
-    if (threadIdx.x == 0) {
-        if (blockIdx.x == 0) {
-            const unsigned long long w = xchg_enc(p.step, !valid, valid ? (uint32_t)n_total : 0u, n_open != 0);
-            for (uint32_t q = 0; q < p.world; ++q) st_release_sys(&p.peer[q]->count_slot[par][p.rank], w);
-        }
-        unsigned long long off = 0;
-        bool ok = valid;
-        for (uint32_t q = 0; q < p.rank; ++q) {          // counts of the ranks before me (they land in my own memory)
-            unsigned long long w;
-            if (!wait_slot(&p.self->count_slot[par][q], p.step, p.timeout_ns, &w) || (w & XCHG_VOID)) ok = false;
-            off += (uint32_t)w;
-        }
-        if (off + n_total > p.row_cap) ok = false;
-        s_off = off;
-        s_ok = ok ? 1u : 0u;
+    if (lane < p.world) {
+        const unsigned long long w = xchg_enc(p.step, !valid, valid ? (uint32_t)n_total : 0u, n_open != 0);
+        st_release_sys(&p.peer[lane]->count_slot[par][p.rank], w);
     }
-    __syncthreads();
-    const unsigned long long off = s_off;
-    if (s_ok) {
+    unsigned long long mine = 0;
+    bool bad = false;
+    if (lane < p.rank) {
+        unsigned long long w;
+        if (!wait_slot(&p.self->count_slot[par][lane], p.step, p.timeout_ns, &w) || (w & XCHG_VOID)) bad = true;
+        mine = (uint32_t)w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+    const bool any_bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane == 0) {
+        const bool ok = valid && !any_bad && mine + n_total <= p.row_cap;
+        p.self->my_offset = mine;
+        p.self->push_ok = ok ? 1u : 0u;
+    }
+}
+
+// My rows -> the root's buffer at my prefix offset (coalesced 4-byte peer stores over NVLink); the last block posts the
+// done word on the root.
+__global__ void __launch_bounds__(256) push_kernel(const PushParams p) {
+    const uint32_t par = p.step & 1u;
+    const unsigned long long off = p.self->my_offset;
+    const bool ok = p.self->push_ok != 0;
+    const unsigned long long n_total = p.counters[C_TOTAL], n_open = p.counters[C_OPEN];
+    if (ok) {
         uint32_t *d_rec = p.root_rows + off, *d_start = d_rec + p.row_cap, *d_end = d_start + p.row_cap, *d_k = d_end + p.row_cap;
         const uint32_t n = (uint32_t)n_total, stride = gridDim.x * blockDim.x;
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -140,9 +151,8 @@ __global__ void __launch_bounds__(256) push_kernel(const PushParams p) {
         const unsigned int prev = atomicAdd(&p.self->blocks_done, 1u);
         if (prev == gridDim.x - 1) {                      // last block of this launch
             p.self->blocks_done = 0;
-            p.self->my_offset = off;
             __threadfence_system();
-            st_release_sys(&p.peer[0]->done_slot[par][p.rank], xchg_enc(p.step, !s_ok, (uint32_t)min(n_open, 0xFFFFFFFFull)));
+            st_release_sys(&p.peer[0]->done_slot[par][p.rank], xchg_enc(p.step, !ok, (uint32_t)min(n_open, 0xFFFFFFFFull)));
         }
     }
 }

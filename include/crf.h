@@ -62,6 +62,27 @@ int crf_seq_load_ascii(crf_ctx *ctx, const uint8_t *bases, const uint64_t *offse
 int crf_seq_load_ascii_ranges(crf_ctx *ctx, const uint8_t *bases, const uint64_t *starts, const uint64_t *lengths,
                               const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records,
                               uint32_t max_motif_cap, int bases_on_device, crf_seq **seq);
+/* The same from planes packed on the HOST (crf_pack_ascii, or crf_fasta_packed at ingest): 0.375 bytes per base cross
+ * PCIe instead of 1.  All records back to back in one position space: position p = bit p & 31 of word p >> 5 of
+ *   H, L : the two bits of the base code (A=00 C=01 G=10 T=11; anything at masked positions),
+ *   NM   : 1 = not A/C/G/T after upper-casing (N, IUPAC codes, anything else),
+ * ceil(total / 32) words each, plus the list of symbols that are neither ACGT nor N ("exotic": only the literal N never
+ * matches, utils/perfect_repeat_tracker.py:53; other letters compare by equality) as (position << 8 | upper-cased byte),
+ * ascending.  Record r = positions [offsets[r], offsets[r+1]) resp. [starts[r], starts[r] + lengths[r]).  The device
+ * re-lays the bits out with the inter-record gaps and filler codes (repack_kernel); results are identical to the ASCII
+ * load of the same text.  planes_on_device != 0: H, L, NM (not exotic / offsets) are device pointers. */
+int crf_seq_load_packed(crf_ctx *ctx, const uint32_t *H, const uint32_t *L, const uint32_t *NM, const uint64_t *exotic,
+                        uint64_t n_exotic, const uint64_t *offsets, uint32_t n_records, uint32_t max_motif_cap,
+                        int planes_on_device, crf_seq **seq);
+int crf_seq_load_packed_ranges(crf_ctx *ctx, const uint32_t *H, const uint32_t *L, const uint32_t *NM,
+                               const uint64_t *exotic, uint64_t n_exotic, const uint64_t *starts, const uint64_t *lengths,
+                               const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
+                               int planes_on_device, crf_seq **seq);
+/* Host-only packer for the above (threaded; AVX2 when the CPU has it).  H, L, NM: ceil(n_bases / 32) words each, written
+ * in full (positions beyond n_bases are masked).  exotic: room for exotic_cap entries; *n_exotic = how many there are
+ * (CRF_ERR_CAPACITY if more than exotic_cap: call again with a longer list).  n_threads = 0: up to 16. */
+int crf_pack_ascii(const uint8_t *bases, uint64_t n_bases, uint32_t n_threads, uint32_t *H, uint32_t *L, uint32_t *NM,
+                   uint64_t *exotic, uint64_t exotic_cap, uint64_t *n_exotic);
 int crf_seq_destroy(crf_seq *seq);
 /* Layout positions one load can hold: the sum over its records of (length + max_motif_cap) must not exceed this
  * (positions are 32-bit on the device); callers with more split the records over several loads. */
@@ -223,6 +244,10 @@ int crf_fasta_open(const char *path, uint32_t n_threads, int pinned, crf_fasta *
 int crf_fasta_info(const crf_fasta *fasta, uint64_t *n_records, uint64_t *total_bases, int *pinned);
 int crf_fasta_data(const crf_fasta *fasta, const uint8_t **bases, const uint64_t **offsets, const char **names,
                    uint64_t *names_bytes);
+/* Packed planes of the whole file (all records back to back, as crf_seq_load_packed takes them), made on first call
+ * and owned by the handle; page-locked when the base buffer is. */
+int crf_fasta_packed(crf_fasta *fasta, uint32_t n_threads, const uint32_t **H, const uint32_t **L, const uint32_t **NM,
+                     const uint64_t **exotic, uint64_t *n_exotic);
 int crf_fasta_close(crf_fasta *fasta);
 
 #ifdef __cplusplus

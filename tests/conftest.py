@@ -3,6 +3,12 @@ import sys
 
 import pytest
 
+# The loopback multi-rank tests run N ranks on ONE device, each on its own stream, and a rank's tiny wait kernels spin until
+# its peers' kernels have run.  With the default 8 hardware work queues two such streams can share a queue, and the
+# peer's kernels would then sit behind the spinning one.  Must be set before CUDA is initialised.  (N real GPUs have one
+# rank per device: no such coupling.)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

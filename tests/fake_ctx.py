@@ -1,6 +1,7 @@
 """A CPU stand-in for crf_b200._cabi.Context used by the partition tests: same load_ranges / scan /
 fetch / run_end surface, answers computed with the CPU oracle.  Test infrastructure only."""
 import argparse
+import ctypes
 
 import numpy as np
 
@@ -47,7 +48,30 @@ class FakeSeq:
         self.close()
 
 
+def unpack_planes(planes):
+    """PackedPlanes -> the upper-cased text they stand for (uint8 array)."""
+    n = planes.n_bases
+    nw = (n + 31) // 32
+
+    def bits(a):
+        a = np.ctypeslib.as_array((ctypes.c_uint32 * nw).from_address(a.value)) if isinstance(a, ctypes.c_void_p) else \
+            (np.asarray(a)[:nw] if not isinstance(a, int) else np.ctypeslib.as_array((ctypes.c_uint32 * nw).from_address(a)))
+        return ((a[:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8).reshape(-1)[:n]
+    h, l, nm = bits(planes.H_ptr), bits(planes.L_ptr), bits(planes.NM_ptr)
+    out = np.frombuffer(b"ACGT", dtype=np.uint8)[(h << 1) | l].copy()
+    out[nm == 1] = ord("N")
+    for key in planes.exotic.tolist():
+        out[key >> 8] = key & 0xFF
+    return out
+
+
 class FakeContext:
+    def load_packed(self, planes, offsets=None, max_motif_cap=50, ranges=None):
+        text = unpack_planes(planes)
+        if ranges is not None:
+            return FakeSeq(text, *ranges)
+        return self.load(text, offsets, max_motif_cap)
+
     def load(self, bases, offsets=None, max_motif_cap=50, on_device=False):
         n = len(bases)
         offsets = np.array([0, n], dtype=np.uint64) if offsets is None else np.asarray(offsets, dtype=np.uint64)

@@ -326,3 +326,61 @@ def test_hail_style_interval_fanout_then_sort_uniq(mods, tmp_path, monkeypatch):
     # a repeat straddling a batch boundary comes out whole from the batch it starts in (the loop runs on while a tracker is
     # mid-repeat, prf:70-74) and left-clipped from the next one: chr1 9990-10026 (CAG)x12 and its twin 10000-10026
     assert "chr1\t9990\t10026\tCAG" in got and "chr1\t10000\t10026\tAGC" in got
+
+
+def test_packed_load_equals_ascii_load_equals_oracle(mods):
+    """crf_seq_load_packed (planes packed on the host, 0.375 B/bp over PCIe, re-laid out by repack_kernel) must give the
+    rows of crf_seq_load_ascii on the same text, which are the oracle's: ragged multi-record input with lower case, N
+    runs and IUPAC letters (equal exotic letters match, trk:53), reads, overlapping out-of-order ranges with owned
+    sub-ranges, and a text large enough for the chunked, pipelined upload."""
+    cabi, oracle = mods.cabi, mods.oracle
+    ctx = mods.api.get_context()
+    rng = random.Random(12)
+
+    def rows(seq, kmax=50):
+        n = seq.scan(1, kmax, 3, 9)
+        out = seq.fetch(n)
+        seq.close()
+        return out
+
+    # 1. ragged records with exotic letters, against the oracle per record
+    recs = [random_seq(rng, n, exotic=True) for n in (1, 31, 32, 33, 5000, 0, 64, 70_001, 12_345)]
+    recs.append("R" * 40 + "ACRACRACRACRACR" + "Y" * 9)          # exotic letters that repeat (they match each other)
+    text = np.frombuffer("".join(recs).encode(), dtype=np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(r) for r in recs])]).astype(np.uint64)
+    pk = cabi.pack_ascii(text)
+    assert pk.exotic.size > 50
+    a = rows(ctx.load(text, offsets, max_motif_cap=50))
+    b = rows(ctx.load_packed(pk, offsets, max_motif_cap=50))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 300
+    want = []
+    for r, rec in enumerate(recs):
+        want += [(r, s, e, len(m)) for s, e, m in oracle.detect_repeats_by_k(rec, ns(**DEFAULTS))]
+    assert list(zip(*(x.tolist() for x in b))) == want
+
+    # 2. reads (many short records: layout words that span several records and gaps)
+    n_reads = 50_000
+    bases, r_off, _ = mods.synth.sr(n_reads, device=None)
+    pk = cabi.pack_ascii(bases)
+    a = rows(ctx.load(bases, r_off, max_motif_cap=20), 20)
+    b = rows(ctx.load_packed(pk, r_off, max_motif_cap=20), 20)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 2000
+
+    # 3. the pipelined upload (> 1 Gbp of planes' positions), records in order; then overlapping out-of-order ranges
+    #    with owned sub-ranges and empty records
+    big, offs, _ = mods.synth.s38(device="cuda:0", scale=0.4)                 # ~1.24 Gbp, 24 records
+    host = big.cpu().numpy()
+    pk = cabi.pack_ascii(host)
+    a = rows(ctx.load(big.data_ptr(), offs, max_motif_cap=50, on_device=True))
+    b = rows(ctx.load_packed(pk, offs, max_motif_cap=50))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 2_000_000
+    nrng = np.random.default_rng(3)
+    n = len(host)
+    starts = nrng.integers(0, n - 90_000_000, size=14).astype(np.uint64)
+    lens = nrng.integers(1, 90_000_000, size=14).astype(np.uint64)
+    lens[[2, 7]] = 0
+    own_lo = (lens // np.uint64(7)).astype(np.uint64)
+    own_hi = (lens - lens // np.uint64(5)).astype(np.uint64)
+    a = rows(ctx.load_ranges(big.data_ptr(), starts, lens, own_lo, own_hi, max_motif_cap=50, on_device=True))
+    b = rows(ctx.load_packed(pk, max_motif_cap=50, ranges=(starts, lens, own_lo, own_hi)))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 500_000
