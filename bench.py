@@ -261,7 +261,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--words-per-thread", type=int, default=0)
-    ap.add_argument("--trace", action="store_true", help="print per-stage host timings of one extra step (stderr)")
+    ap.add_argument("--trace", action="store_true", help="print per-stage device timings of one extra step (stderr)")
+    ap.add_argument("--phases", type=int, default=1,
+                    help="N > 1: phases per step (the rows of one phase travel to rank 0 while the next one is scanned); "
+                         "measured slower than one phase on S38 (profiles/r02_scaling_s38.md), kept for larger jobs")
     args = ap.parse_args()
     claim_stdout()
     global KMAX
@@ -310,10 +313,9 @@ def main():
     knobs = {"words_per_thread": args.words_per_thread} if args.words_per_thread else {}
     comm = multi.DistComm(dist, rank, world)
     rs = multi.RankScan(ctx, comm, bases.data_ptr(), offsets[:-1], lengths, KMIN, KMAX, MIN_REPEATS, MIN_SPAN,
-                        on_device=True, chunk=args_chunk(world), reads=(args.workload == "sr"), knobs=knobs)
-    seq = rs.seq
-    info = seq.info()
-    my_bp, n_units, mine = rs.my_bp, rs.n_units, rs.units
+                        on_device=True, chunk=args_chunk(world), reads=(args.workload == "sr"), knobs=knobs,
+                        phases=args.phases)
+    my_bp, n_units = rs.my_bp, rs.n_units
 
     # ---- device-resident timing ----
     for _ in range(args.warmup):
@@ -336,10 +338,10 @@ def main():
         for _ in range(args.steps):                  # one synchronous crf_scan per step (its counters come back every time)
             rs.step_async()
             total_results = rs.finish()
-            st_ = seq.stats()
-            kernel_ms.append(st_.kernel_ms)
-            scan_ms.append(st_.scan_ms)
-            launches += st_.launches
+            st_ = rs.stats()
+            kernel_ms.append(st_["kernel_ms"])
+            scan_ms.append(st_["scan_ms"])
+            launches += st_["launches"]
     else:
         # N ranks: every step is kernel launches only -- counts and rows travel GPU to GPU -- so the K steps are queued back
         # to back and the host waits once; finish() then checks the status word of every one of the K steps
@@ -358,10 +360,10 @@ def main():
         total_results = rs.finish()                  # one stream synchronisation; status of every queued step
         if rs.steps_repeated:
             raise SystemExit("bench: a timed step had to be repeated (buffers were sized during warm-up?)")
-        st_ = seq.stats()                            # events of the last step
-        kernel_ms.append(st_.kernel_ms)
-        scan_ms.append(st_.scan_ms)
-        launches = st_.launches * args.steps
+        st_ = rs.stats()                             # events of the last step, summed over this rank's phases
+        kernel_ms.append(st_["kernel_ms"])
+        scan_ms.append(st_["scan_ms"])
+        launches = st_["launches"] * args.steps
     torch.cuda.synchronize()
     elapsed_ms = ev0.elapsed_time(ev1)
     time.sleep(0.3)
@@ -381,11 +383,13 @@ def main():
         rs.step_async()
         marks[1].record(stream)
         rs.finish()
-        st_ = seq.stats()
-        log(f"[rank {rank}] trace: scan kernel {st_.kernel_ms:.3f} ms, scan+assembly {st_.scan_ms:.3f} ms, "
-            f"whole step incl. push/settle {marks[0].elapsed_time(marks[1]):.3f} ms, rows {int(st_.n_results)}")
+        st_ = rs.stats()
+        xs = torch.cuda.Event(enable_timing=True)
+        log(f"[rank {rank}] trace: scan kernels {st_['kernel_ms']:.3f} ms, scan+assembly {st_['scan_ms']:.3f} ms "
+            f"({rs.phases} phase(s)), main stream busy {marks[0].elapsed_time(marks[1]):.3f} ms, rows {int(st_['n_results'])}")
+        del xs
     value = total_bp / (ms_per_step * 1e-3) / 1e9
-    stats = seq.stats()
+    stats = argparse.Namespace(**rs.stats())
 
     # ---- parity of what the step produced (rank 0 holds the whole job's rows) ----
     parity = None

@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRF_LIB_PATH") or os.path.join(_HERE, "libcrf.so")   # override: A/B builds while tuning
 
 SCAN_NO_PRIMITIVITY = 1
+SCAN_WARP_TILES = 2
+SCAN_BLOCK_TILES = 4
 
 CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_CAPACITY = range(6)
 
@@ -25,7 +27,8 @@ EXPORTS = [
     "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end", "crf_write_rows",
     "crf_fasta_open", "crf_fasta_info", "crf_fasta_data", "crf_fasta_close",
     "crf_xchg_create", "crf_xchg_destroy", "crf_xchg_export", "crf_xchg_connect_ipc", "crf_xchg_connect_local",
-    "crf_xchg_set_timeout", "crf_scan_gather", "crf_xchg_push", "crf_xchg_wait", "crf_xchg_fetch", "crf_xchg_patch_end",
+    "crf_xchg_set_timeout", "crf_scan_gather", "crf_xchg_push", "crf_xchg_wait", "crf_xchg_step_result", "crf_xchg_fetch",
+    "crf_xchg_patch_end",
 ]
 
 IPC_HANDLE_BYTES = 64
@@ -62,7 +65,7 @@ class ScanStats(ctypes.Structure):
 class XchgResult(ctypes.Structure):
     _fields_ = [("status", ctypes.c_uint32), ("worst_status", ctypes.c_uint32), ("steps_checked", ctypes.c_uint32),
                 ("step", ctypes.c_uint32), ("any_open", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
-                ("total_rows", ctypes.c_uint64), ("total_open", ctypes.c_uint64),
+                ("total_rows", ctypes.c_uint64), ("base_rows", ctypes.c_uint64), ("total_open", ctypes.c_uint64),
                 ("my_offset", ctypes.c_uint64), ("rows_of_rank", ctypes.c_uint64 * XCHG_MAX_WORLD)]
 
 
@@ -112,9 +115,10 @@ def lib():
         L.crf_xchg_connect_ipc.argtypes = [vp, u32, vp]
         L.crf_xchg_connect_local.argtypes = [vp, u32, vp]
         L.crf_xchg_set_timeout.argtypes = [vp, ctypes.c_double]
-        L.crf_scan_gather.argtypes = [vp, P(ScanParams), vp]
-        L.crf_xchg_push.argtypes = [vp, vp]
+        L.crf_scan_gather.argtypes = [vp, P(ScanParams), vp, i]
+        L.crf_xchg_push.argtypes = [vp, vp, i]
         L.crf_xchg_wait.argtypes = [vp, P(XchgResult)]
+        L.crf_xchg_step_result.argtypes = [vp, u32, P(XchgResult)]
         L.crf_xchg_fetch.argtypes = [vp, vp, vp, vp, vp, u64, u64, i]
         L.crf_xchg_patch_end.argtypes = [vp, vp, vp, u32]
         L.crf_load_limit.argtypes = [u32]
@@ -302,15 +306,16 @@ class Sequence:
         return n.value
 
     @_serialised
-    def scan_gather(self, xchg, min_motif_size, max_motif_size, min_repeats, min_span, **knobs):
-        """crf_scan_gather: scan + push of the rows to rank 0, asynchronous (Xchg.wait() tells how it went)."""
+    def scan_gather(self, xchg, min_motif_size, max_motif_size, min_repeats, min_span, append=False, **knobs):
+        """crf_scan_gather: scan + push of the rows to rank 0, asynchronous (Xchg.wait() tells how it went).
+        append: the rows go after those of the job's earlier phases."""
         pr = self._params(min_motif_size, max_motif_size, min_repeats, min_span, knobs)
-        _check(lib().crf_scan_gather(self._h, ctypes.byref(pr), xchg._h))
+        _check(lib().crf_scan_gather(self._h, ctypes.byref(pr), xchg._h, int(bool(append))))
 
     @_serialised
-    def push(self, xchg):
+    def push(self, xchg, append=False):
         """crf_xchg_push: rows of the last completed scan() -> rank 0 (asynchronous)."""
-        _check(lib().crf_xchg_push(self._h, xchg._h))
+        _check(lib().crf_xchg_push(self._h, xchg._h, int(bool(append))))
 
     @_serialised
     def fetch(self, n):
@@ -447,6 +452,12 @@ class Xchg:
     def wait(self):
         res = XchgResult()
         _check(lib().crf_xchg_wait(self._h, ctypes.byref(res)))
+        return res
+
+    def step_result(self, step):
+        """The result of one of the last 64 steps a wait() has covered."""
+        res = XchgResult()
+        _check(lib().crf_xchg_step_result(self._h, int(step), ctypes.byref(res)))
         return res
 
     def fetch(self, n, first=0):

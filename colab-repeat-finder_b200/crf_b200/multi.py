@@ -75,12 +75,18 @@ class RankScan:
     """One rank (one GPU) of a partitioned scan.
 
     bases / record_starts / lengths describe ALL records (every rank sees the same description; `bases` is this
-    rank's view of the bytes: a host array or, with on_device, a device pointer).  reads=True splits the records by
-    count instead of cutting them into chunks (config C5: many short independent sequences)."""
+    rank's view of the bytes: a host array, _cabi.PackedPlanes or, with on_device, a device pointer).  reads=True
+    splits the records by count instead of cutting them into chunks (config C5: many short independent sequences).
+
+    phases > 1 (N > 1 only): the genome-ordered unit list is cut into phases x N contiguous shares and rank r takes
+    share p * N + r in phase p -- one sequence per phase.  A step scans the phases one after the other while the rows
+    of the phase before travel to rank 0 on the exchange's own stream: the gather, which is bound by rank 0's NVLink
+    ingress, hides behind the next phase's scan.  Genome order = phase-major, rank-minor, so rank 0's buffer still
+    holds the sorted result."""
 
     def __init__(self, ctx, comm, bases, record_starts, lengths, kmin, kmax, min_repeats, min_span, on_device=False,
                  chunk=partition.DEFAULT_CHUNK, halo=partition.DEFAULT_HALO, reads=False, row_cap=None, knobs=None,
-                 timeout_s=None, base_offset=0):
+                 timeout_s=None, base_offset=0, phases=1):
         self.ctx, self.comm = ctx, comm
         self.rank, self.world = comm.rank, comm.world
         self.filters = (int(kmin), int(kmax), int(min_repeats), int(min_span))
@@ -88,28 +94,36 @@ class RankScan:
         lengths = [int(x) for x in lengths]
         self.total_bp = int(sum(lengths))
         self.reads = reads
+        self.phases = P = max(1, int(phases)) if self.world > 1 else 1
+        shares = P * self.world                       # "virtual ranks": share v = phase v // N of rank v % N
+        self.load_args, self.units = [], []
         if reads:
             n_rec = len(lengths)
-            lo, hi = n_rec * self.rank // self.world, n_rec * (self.rank + 1) // self.world
-            self.plan, self.units = None, []
-            self.first_record = lo
-            starts = np.asarray(record_starts[lo:hi], dtype=np.uint64)
-            lens = np.asarray(lengths[lo:hi], dtype=np.uint64)
-            own_lo = own_hi = None
-            self.my_bp = int(lens.sum())
+            self.plan = None
+            self.first_record = []
+            for p in range(P):
+                v = p * self.world + self.rank
+                lo, hi = n_rec * v // shares, n_rec * (v + 1) // shares
+                self.first_record.append(lo)
+                self.load_args.append((np.asarray(record_starts[lo:hi], dtype=np.uint64),
+                                       np.asarray(lengths[lo:hi], dtype=np.uint64), None, None))
+                self.units.append([])
+            self.my_bp = int(sum(int(a[1].sum()) for a in self.load_args))
             self.n_units = n_rec
         else:
             whole = self.world == 1 and chunk >= max(lengths + [1])
-            self.plan = partition.Plan(lengths, self.world, chunk=chunk, halo=halo, kmax=kmax, min_repeats=min_repeats,
+            self.plan = partition.Plan(lengths, shares, chunk=chunk, halo=halo, kmax=kmax, min_repeats=min_repeats,
                                        min_span=min_span)
-            self.units = self.plan.units_of(self.rank)
-            starts, lens, own_lo, own_hi = self.plan.load_args(self.rank, record_starts)
-            if whole:
-                own_lo = own_hi = None
-            self.my_bp = int(sum(u.u1 - u.u0 for u in self.units))
+            for p in range(P):
+                v = p * self.world + self.rank
+                starts, lens, own_lo, own_hi = self.plan.load_args(v, record_starts)
+                if whole:
+                    own_lo = own_hi = None
+                self.load_args.append((starts, lens, own_lo, own_hi))
+                self.units.append(self.plan.units_of(v))
+            self.my_bp = int(sum(u.u1 - u.u0 for us in self.units for u in us))
             self.n_units = len(self.plan.units)
-        self.load_args = (starts, lens, own_lo, own_hi)
-        self.seq = None
+        self.seqs = [None] * P
         self.reload(bases, on_device=on_device, base_offset=base_offset)
         self.xchg = None
         if self.world > 1:
@@ -129,67 +143,82 @@ class RankScan:
                         self.xchg.connect_ipc(r, h)
                 comm.allgather_obj(None)
         self.last = None
+        self.steps_repeated = 0
+
+    @property
+    def seq(self):
+        """The sequence of the first phase (single-phase callers)."""
+        return self.seqs[0]
 
     def span(self):
-        """[lo, hi) of the caller's base buffer this rank reads (its units plus their halos)."""
-        starts, lens = self.load_args[0], self.load_args[1]
-        if not len(starts):
-            return 0, 0
-        return int(starts.min()), int((starts + lens).max())
+        """[lo, hi) of the caller's base buffer this rank reads (its units plus their halos, all phases)."""
+        lo, hi = None, 0
+        for starts, lens, _, _ in self.load_args:
+            if len(starts):
+                a, b = int(starts.min()), int((starts + lens).max())
+                lo = a if lo is None else min(lo, a)
+                hi = max(hi, b)
+        return (0, 0) if lo is None else (lo, hi)
 
     def reload(self, bases, on_device=False, base_offset=0):
         """(Re-)upload this rank's share.  `bases` starts at position `base_offset` of the buffer the record_starts refer
         to (a rank that keeps only its own span() on the host passes span()[0])."""
-        if self.seq is not None:
-            self.seq.close()
-            self.seq = None
-        starts, lens, own_lo, own_hi = self.load_args
         kmax = self.filters[1]
-        if len(starts):
-            if isinstance(bases, _cabi.PackedPlanes):          # planes packed on the host: 0.375 B/bp over PCIe
-                if base_offset % 32:
-                    raise ValueError("packed planes must start at a multiple of 32 positions")
-                self.seq = self.ctx.load_packed(bases, max_motif_cap=kmax,
-                                                ranges=(starts - np.uint64(base_offset), lens, own_lo, own_hi))
+        for p, (starts, lens, own_lo, own_hi) in enumerate(self.load_args):
+            if self.seqs[p] is not None:
+                self.seqs[p].close()
+                self.seqs[p] = None
+            if len(starts):
+                if isinstance(bases, _cabi.PackedPlanes):          # planes packed on the host: 0.375 B/bp over PCIe
+                    if base_offset % 32:
+                        raise ValueError("packed planes must start at a multiple of 32 positions")
+                    seq = self.ctx.load_packed(bases, max_motif_cap=kmax,
+                                               ranges=(starts - np.uint64(base_offset), lens, own_lo, own_hi))
+                else:
+                    seq = self.ctx.load_ranges(bases, starts - np.uint64(base_offset), lens, own_lo, own_hi,
+                                               max_motif_cap=kmax, on_device=on_device)
+                if self.reads:
+                    if self.world > 1:
+                        seq.set_output_map(out_record=np.arange(self.first_record[p], self.first_record[p] + len(starts),
+                                                                dtype=np.uint32))
+                elif self.world > 1 or own_lo is not None:
+                    us = self.units[p]
+                    seq.set_output_map(out_record=[u.record for u in us], out_shift=[u.d0 for u in us],
+                                       open_ended=[int(u.d1 < u.rec_len) for u in us])
+            elif self.world > 1:
+                # a share without units still takes part in the exchange: it pushes zero rows (an empty record to scan)
+                seq = self.ctx.load_ranges(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(1, np.uint64),
+                                           max_motif_cap=kmax)
             else:
-                self.seq = self.ctx.load_ranges(bases, starts - np.uint64(base_offset), lens, own_lo, own_hi,
-                                                max_motif_cap=kmax, on_device=on_device)
-            if self.reads:
-                if self.world > 1:
-                    self.seq.set_output_map(out_record=np.arange(self.first_record, self.first_record + len(starts),
-                                                                 dtype=np.uint32))
-            elif self.world > 1 or own_lo is not None:
-                self.seq.set_output_map(out_record=[u.record for u in self.units], out_shift=[u.d0 for u in self.units],
-                                        open_ended=[int(u.d1 < u.rec_len) for u in self.units])
-        elif self.world > 1:
-            # a rank without units still takes part in the exchange: it pushes zero rows (an empty record to scan)
-            self.seq = self.ctx.load_ranges(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(1, np.uint64),
-                                            max_motif_cap=kmax)
+                seq = None
+            self.seqs[p] = seq
 
     # ---- the step -------------------------------------------------------------------------------------------
     def step_async(self):
-        """Queue one whole step on this rank's stream (scan, assembly, push to rank 0); returns at once."""
+        """Queue one whole step on this rank's streams (per phase: scan, assembly, push to rank 0); returns at once."""
         kmin, kmax, mr, ms = self.filters
         if self.world == 1:
-            self._n = self.seq.scan(kmin, kmax, mr, ms, **self.knobs)
+            self._n = self.seqs[0].scan(kmin, kmax, mr, ms, **self.knobs)
         else:
-            self.seq.scan_gather(self.xchg, kmin, kmax, mr, ms, **self.knobs)
+            for p, seq in enumerate(self.seqs):
+                seq.scan_gather(self.xchg, kmin, kmax, mr, ms, append=p > 0, **self.knobs)
 
     def finish(self):
         """Wait for the queued steps; settle the rare cases.  Returns the whole-job row count (the rows are on rank 0)."""
+        self.steps_repeated = 0
         if self.world == 1:
             self.last = None
-            if self.plan is not None and self.load_args[2] is not None and self.seq.stats().n_open:
+            if self.plan is not None and self.load_args[0][2] is not None and self.seqs[0].stats().n_open:
                 self._stitch_local()
             return self._n
         kmin, kmax, mr, ms = self.filters
         res = self.xchg.wait()
-        self.steps_repeated = 0
         if res.worst_status == _cabi.XCHG_VOID_STEP:
-            # some rank outgrew a buffer (first step of a new workload, usually): every rank repeats the step the slow
+            # some rank outgrew a buffer (first step of a new workload, usually): every rank repeats the job the slow
             # way -- crf_scan sizes everything -- and pushes again; the status is the same on all ranks, so all agree
-            self.seq.scan(kmin, kmax, mr, ms, **self.knobs)
-            self.seq.push(self.xchg)
+            for p, seq in enumerate(self.seqs):
+                seq.scan(kmin, kmax, mr, ms, **self.knobs)
+                seq.push(self.xchg, append=p > 0)
             res = self.xchg.wait()
             self.steps_repeated = 1
         if res.worst_status == _cabi.XCHG_ROOT_FULL:
@@ -198,21 +227,28 @@ class RankScan:
         if res.worst_status != _cabi.XCHG_OK:
             raise _cabi.CrfError(f"multi-GPU gather failed with status {res.worst_status}")
         self.last = res
-        if res.any_open and self.plan is not None:
-            self._stitch(res)
+        # the last job's phases: steps res.step - P + 1 .. res.step
+        self.phase_results = [res if p == self.phases - 1 else self.xchg.step_result(res.step - (self.phases - 1 - p))
+                              for p in range(self.phases)]
+        if self.plan is not None and any(r.any_open for r in self.phase_results):
+            self._stitch()
         return int(res.total_rows)
 
-    def _stitch(self, res):
+    def _stitch(self):
         """A repeat longer than the halo reached the end of its unit's data: follow it on whoever holds the next bases
         (crf_run_end), hop by hop, then patch the ends inside rank 0's buffer.  Rare; host-driven."""
-        n_open = int(self.seq.stats().n_open)
-        mine = self.seq.fetch_open(cap=max(n_open, 1)) if n_open else np.zeros((0, 5), np.uint32)
-        per_rank = self.comm.allgather_obj([tuple(int(x) for x in row) for row in mine])
-        open_all = [row[1:] for part in per_rank for row in part]          # (record, start, end_lower_bound, k)
-        first = self.plan.bounds[self.rank]
+        N = self.world
+        mine = []                                      # (phase, local row, record, start, end, k)
+        for p, seq in enumerate(self.seqs):
+            n_open = int(seq.stats().n_open)
+            if n_open:
+                mine += [(p,) + tuple(int(x) for x in row) for row in seq.fetch_open(cap=n_open)]
+        per_rank = self.comm.allgather_obj(mine)
+        open_all = [row[2:] for part in per_rank for row in part]          # (record, start, end_lower_bound, k)
 
-        def run_end(unit, local_pos, k):
-            return self.seq.run_end(unit.index - first, local_pos, k)
+        def run_end(unit, local_pos, k):               # unit belongs to one of this rank's shares
+            v = self.plan.rank_of_unit(unit.index)
+            return self.seqs[v // N].run_end(unit.index - self.plan.bounds[v], local_pos, k)
 
         def exchange(answers):
             merged = {}
@@ -220,40 +256,53 @@ class RankScan:
                 merged.update(part)
             return merged
 
-        fixed = partition.stitch(self.plan, open_all, run_end, exchange, self.rank)
+        fixed = partition.stitch(self.plan, open_all, run_end, exchange, self.rank, owner=lambda v: v % N)
         if self.rank == 0:
             rows, ends, i = [], [], 0
             for r, part in enumerate(per_rank):
-                g = global_rows(res.rows_of_rank[:self.world], r, [row[0] for row in part])
-                for j in range(len(part)):
-                    rows.append(int(g[j]))
+                for (p, local_row, *_rest) in part:
+                    pr = self.phase_results[p]
+                    g = global_rows(pr.rows_of_rank[:N], r, [local_row])
+                    rows.append(int(pr.base_rows) + int(g[0]))
                     ends.append(fixed[i][2])
                     i += 1
             self.xchg.patch_end(rows, ends)
 
     def _stitch_local(self):
         """One rank, records cut into chunks: finish the open-ended rows in place."""
-        rows = self.seq.fetch_open(cap=int(self.seq.stats().n_open))
+        seq = self.seqs[0]
+        rows = seq.fetch_open(cap=int(seq.stats().n_open))
         fixed = partition.stitch(self.plan, [tuple(int(x) for x in r[1:]) for r in rows],
-                                 lambda unit, lp, k: self.seq.run_end(unit.index, lp, k))
+                                 lambda unit, lp, k: seq.run_end(unit.index, lp, k))
         for row, (_r, _s, e, _k) in zip(rows, fixed):
-            self.seq.patch_end(int(row[0]), e)
+            seq.patch_end(int(row[0]), e)
+
+    def stats(self):
+        """Scan statistics of the last step, summed over this rank's phases (kernel_ms, scan_ms, launches, ...)."""
+        out = {}
+        for seq in self.seqs:
+            if seq is None:
+                continue
+            for name, value in seq.stats().as_dict().items():
+                out[name] = out.get(name, 0) + value
+        return out
 
     def fetch(self):
         """Rank 0: the whole job's rows (record, start, end, k), sorted by (record, start, end)."""
         if self.world == 1:
-            rec, st, en, k = self.seq.fetch(self._n)
-            if self.plan is not None and self.load_args[2] is None:
-                rec = np.array([u.record for u in self.units], dtype=np.uint32)[rec] if len(rec) else rec
+            rec, st, en, k = self.seqs[0].fetch(self._n)
+            if self.plan is not None and self.load_args[0][2] is None:
+                rec = np.array([u.record for u in self.units[0]], dtype=np.uint32)[rec] if len(rec) else rec
             return rec, st, en, k
         if self.rank != 0:
             raise _cabi.CrfError("the gathered rows live on rank 0")
         return self.xchg.fetch(int(self.last.total_rows))
 
     def close(self):
-        if self.seq is not None:
-            self.seq.close()
-            self.seq = None
+        for p, seq in enumerate(self.seqs):
+            if seq is not None:
+                seq.close()
+                self.seqs[p] = None
         if self.xchg is not None:
             self.comm.allgather_obj(None)              # nobody still pushes into a block that is about to go away
             self.xchg.close()
@@ -261,7 +310,7 @@ class RankScan:
 
 
 def scan_on_devices(devices, bases, record_starts, lengths, kmin, kmax, min_repeats, min_span, chunk=partition.DEFAULT_CHUNK,
-                    halo=partition.DEFAULT_HALO, reads=False, contexts=None, knobs=None, timeout_s=None):
+                    halo=partition.DEFAULT_HALO, reads=False, contexts=None, knobs=None, timeout_s=None, phases=1):
     """One process, one thread per device: scan host `bases` (a uint8 array, or _cabi.PackedPlanes) on all `devices`;
     returns (record, start, end, k) of the whole job.  `contexts`: reuse these _cabi.Context objects (one per device) instead of creating new ones."""
     world = len(devices)
@@ -276,7 +325,7 @@ def scan_on_devices(devices, bases, record_starts, lengths, kmin, kmax, min_repe
         rs = None
         try:
             rs = RankScan(ctxs[rank], comms[rank], bases, record_starts, lengths, kmin, kmax, min_repeats, min_span,
-                          chunk=chunk, halo=halo, reads=reads, knobs=knobs, timeout_s=timeout_s)
+                          chunk=chunk, halo=halo, reads=reads, knobs=knobs, timeout_s=timeout_s, phases=phases)
             rs.step_async()
             rs.finish()
             if rank == 0:

@@ -103,8 +103,11 @@ def localize(plan, rank, unit_local, start, end, k):
     return rec[ul], g_start, g_end, np.asarray(k, dtype=np.int64), open_mask
 
 
-def stitch(plan, open_runs, run_end_fn, exchange_fn=None, rank=0):
+def stitch(plan, open_runs, run_end_fn, exchange_fn=None, rank=0, owner=None):
     """Finish right-open runs.
+
+    owner: maps the plan's share number (plan.rank_of_unit) to the rank that holds it (default: identity; a phased
+    multi-GPU job has phases x N shares, share v on rank v % N).
 
     open_runs : list of (record, start, end_lower_bound, k) -- the same list on every rank.
     run_end_fn(unit, local_pos, k) -> local run end, callable for units of *this* rank only.
@@ -116,7 +119,8 @@ def stitch(plan, open_runs, run_end_fn, exchange_fn=None, rank=0):
         answers = {}
         for i, (rec, p, k) in pending.items():
             unit = plan.unit_owning(rec, p)
-            if plan.rank_of_unit(unit.index) == rank:
+            holder = plan.rank_of_unit(unit.index)
+            if (owner(holder) if owner else holder) == rank:
                 answers[i] = int(run_end_fn(unit, p - unit.d0, k)) + unit.d0
         if exchange_fn is not None:
             answers = exchange_fn(answers)

@@ -17,6 +17,7 @@
 #include "../../include/crf.h"
 #include "crf_aux.cuh"
 #include "crf_scan.cuh"
+#include "crf_scan_warp.cuh"
 #include "crf_xchg.cuh"
 
 using namespace crf;
@@ -62,8 +63,11 @@ struct crf_ctx {
     size_t cached_bytes = 0;
     // timing events and the page-locked counter block are per context, not per load: creating them cost more than a
     // small scan (calls on one context are serialised by the caller, crf.h)
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    unsigned long long *h_counters = nullptr;
+    // (a small pool, handed out round robin: a rank of a multi-GPU job keeps several sequences in flight)
+    static const int SLOTS = 8;
+    cudaEvent_t ev[SLOTS][5] = {};
+    unsigned long long *h_counters = nullptr;           // SLOTS x C_COUNT
+    int next_slot = 0;
 };
 static const size_t CACHE_LIMIT_BYTES = 24ull << 30;
 static thread_local crf_ctx *g_ctx = nullptr;          // context of the API call in progress
@@ -123,6 +127,8 @@ static void ctx_free(void *p) {
 struct ScanPlan {
     crf_scan_params pr;
     int T;
+    int warp_ns;                       // 0: block-tiled scan_kernel; 1 / 2: scan_warp_kernel with that many sub-tiles per warp
+    uint32_t warp_grid;
     uint32_t n_tiles, outcap, ggrid, tgrid, launches;
     size_t smem;
     bool single_copy;
@@ -157,6 +163,7 @@ struct crf_seq {
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;   // h_counters: the context's page-locked block
     cudaEvent_t *ev = nullptr;                                         // the context's events
     uint32_t open_cap = 0;                                             // rows d_open_rows holds
+    cudaEvent_t side_done = nullptr;                                   // an exchange stream still reads this sequence's rows
     ScanPlan *plan = nullptr;                                          // launch parameters of the scan in flight / last run
     crf_scan_stats_t stats = {};
     crf_seq_info_t info = {};
@@ -209,9 +216,10 @@ extern "C" int crf_ctx_create(int device, crf_ctx **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming);
-    for (auto &ev : c->ev)
-        if (e == cudaSuccess) e = cudaEventCreate(&ev);
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_counters, C_COUNT * sizeof(unsigned long long));
+    for (auto &set : c->ev)
+        for (auto &ev : set)
+            if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_counters, crf_ctx::SLOTS * C_COUNT * sizeof(unsigned long long));
     if (e == cudaSuccess) e = preload_kernels();
     if (e != cudaSuccess) { delete c; set_err("cudaStreamCreate failed: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
     c->stream = c->own_stream;
@@ -228,8 +236,9 @@ extern "C" int crf_ctx_destroy(crf_ctx *c) {
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->copy_done);
-    for (auto &ev : c->ev)
-        if (ev) cudaEventDestroy(ev);
+    for (auto &set : c->ev)
+        for (auto &ev : set)
+            if (ev) cudaEventDestroy(ev);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     delete c;
     return CRF_OK;
@@ -289,6 +298,9 @@ static void free_seq(crf_seq *s) {
     delete s;
 }
 
+#ifndef CRF_DEFAULT_WARP_NS
+#define CRF_DEFAULT_WARP_NS 0          // scan kernel used when neither a flag nor CRF_SCAN_KERNEL says otherwise
+#endif
 static const uint32_t EX_CAP = 1u << 22;       // exotic symbols kept per load
 static const uint32_t TILE_WORDS_MAX = 4096;   // THREADS * 16
 static const uint32_t MAX_K = 65535;
@@ -316,8 +328,12 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
     s->ctx = c;
     s->n_records = n_records;
     s->cap = max_motif_cap;
-    s->ev = c->ev;
-    s->h_counters = c->h_counters;
+    {
+        std::lock_guard<std::mutex> lock(c->mu);
+        const int slot = c->next_slot++ % crf_ctx::SLOTS;
+        s->ev = c->ev[slot];
+        s->h_counters = c->h_counters + (size_t)slot * C_COUNT;
+    }
     CHECK(dev_alloc(&s->d_counters, C_COUNT));
     s->open_cap = OPEN_CAP_INITIAL;
     CHECK(dev_alloc(&s->d_open_rows, 5 * (size_t)s->open_cap));
@@ -644,6 +660,7 @@ extern "C" int crf_seq_destroy(crf_seq *s) {
     if (!s) return CRF_OK;
     g_ctx = s->ctx;
     cudaSetDevice(s->ctx->device);
+    if (s->side_done) cudaEventSynchronize(s->side_done);
     cudaStreamSynchronize(s->ctx->stream);
     free_seq(s);
     return CRF_OK;
@@ -773,6 +790,19 @@ static int launch_scan(const ScanParams &sp, uint32_t n_tiles, size_t smem, cuda
     return CRF_OK;
 }
 
+// default scan kernel of this process: CRF_SCAN_KERNEL=block|warp1|warp2 (tuning / A-B runs), else the library default
+static int default_warp_ns() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CRF_SCAN_KERNEL");
+        if (e && !strcmp(e, "block")) v = 0;
+        else if (e && !strcmp(e, "warp1")) v = 1;
+        else if (e && !strcmp(e, "warp2")) v = 2;
+        else v = CRF_DEFAULT_WARP_NS;
+    }
+    return v;
+}
+
 static int scan_validate(const crf_seq *s, const crf_scan_params *pr) {
     // the four checks of perfect_repeat_finder.py:23-30
     if (pr->min_motif_size < 1) { set_err("min_motif_size is set to %u. It must be at least 1.", pr->min_motif_size); return CRF_ERR_ARG; }
@@ -830,7 +860,13 @@ static int scan_prepare(crf_seq *s, const crf_scan_params *pr, ScanPlan &pl) {
         CU(cudaStreamSynchronize(st));  // tab / segs are locals
         s->ktab_for = *pr;
     }
-    const uint32_t TW = THREADS * pl.T;
+    // which kernel: the warp-tiled one (CRF_SCAN_WARP_TILES, two sub-tiles per warp) or the block-tiled one; T != 8 exists
+    // only block-tiled.  CRF_SCAN_KERNEL=block|warp1|warp2 overrides the default (tuning).
+    pl.warp_ns = default_warp_ns();
+    if (pr->flags & CRF_SCAN_BLOCK_TILES) pl.warp_ns = 0;
+    if (pr->flags & CRF_SCAN_WARP_TILES) pl.warp_ns = std::max(pl.warp_ns, 1);
+    if (pl.T != 8 || pr->max_motif_size > 1024) pl.warp_ns = 0;      // (a warp's halo must stay a small part of its tile)
+    const uint32_t TW = pl.warp_ns ? 32u * pl.T * pl.warp_ns : (uint32_t)THREADS * pl.T;
     pl.n_tiles = (s->n_words + TW - 1) / TW;
     if (s->tiles_cap < pl.n_tiles + 1) {
         dev_free(s->tile_cnt); dev_free(s->tile_base); dev_free(s->tile_off);
@@ -840,8 +876,25 @@ static int scan_prepare(crf_seq *s, const crf_scan_params *pr, ScanPlan &pl) {
         CHECK(dev_alloc(&s->tile_off, (size_t)pl.n_tiles + 1));
         s->tiles_cap = pl.n_tiles + 1;
     }
-    pl.outcap = pr->tile_out_cap ? pr->tile_out_cap : 1024;
-    pl.smem = scan_smem_bytes(pl.T, pr->max_motif_size, pl.outcap);
+    if (pl.warp_ns) {
+        pl.outcap = pr->tile_out_cap ? std::min<uint32_t>(pr->tile_out_cap, 256) : 48u * pl.warp_ns;
+        pl.smem = WARPS_PER_CTA * warp_smem_bytes(pl.T, pl.warp_ns, pr->max_motif_size, pl.outcap);
+        int per_sm = 0, n_sm = 0;
+        CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+        if (pl.warp_ns == 1) {
+            CU(cudaFuncSetAttribute(scan_warp_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_warp_kernel<8, 1>, 32 * WARPS_PER_CTA, pl.smem));
+        } else {
+            CU(cudaFuncSetAttribute(scan_warp_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_warp_kernel<8, 2>, 32 * WARPS_PER_CTA, pl.smem));
+        }
+        if (per_sm < 1) { set_err("crf_scan: the warp-tiled kernel does not fit an SM (%zu bytes of shared memory)", pl.smem); return CRF_ERR_UNSUPPORTED; }
+        pl.warp_grid = std::min<uint32_t>((uint32_t)per_sm * n_sm, (pl.n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+        pl.warp_grid = std::max(pl.warp_grid, 1u);
+    } else {
+        pl.outcap = pr->tile_out_cap ? pr->tile_out_cap : 1024;
+        pl.smem = scan_smem_bytes(pl.T, pr->max_motif_size, pl.outcap);
+    }
     pl.single_copy = pr->min_repeats == 1;    // see single_copy_filter_kernel
     return CRF_OK;
 }
@@ -882,11 +935,21 @@ static int scan_enqueue(crf_seq *s, ScanPlan &pl) {
     sp.counters = s->d_counters;
     pl.launches = 0;
 
+    if (s->side_done) {            // the previous push of this sequence's rows (on the exchange's own stream) comes first
+        CU(cudaStreamWaitEvent(st, s->side_done, 0));
+        s->side_done = nullptr;
+    }
     CU(cudaEventRecord(s->ev[0], st));
     CU(cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
     CU(cudaEventRecord(s->ev[1], st));
     const uint32_t n_tiles = pl.n_tiles;
-    if (pl.T == 1) CHECK(launch_scan<1>(sp, n_tiles, pl.smem, st));
+    if (pl.warp_ns == 1) {
+        scan_warp_kernel<8, 1><<<pl.warp_grid, 32 * WARPS_PER_CTA, pl.smem, st>>>(sp);
+        CU(cudaGetLastError());
+    } else if (pl.warp_ns == 2) {
+        scan_warp_kernel<8, 2><<<pl.warp_grid, 32 * WARPS_PER_CTA, pl.smem, st>>>(sp);
+        CU(cudaGetLastError());
+    } else if (pl.T == 1) CHECK(launch_scan<1>(sp, n_tiles, pl.smem, st));
     else if (pl.T == 2) CHECK(launch_scan<2>(sp, n_tiles, pl.smem, st));
     else if (pl.T == 4) CHECK(launch_scan<4>(sp, n_tiles, pl.smem, st));
     else if (pl.T == 8) CHECK(launch_scan<8>(sp, n_tiles, pl.smem, st));
@@ -900,7 +963,7 @@ static int scan_enqueue(crf_seq *s, ScanPlan &pl) {
     g.spill_key = s->spill_key; g.spill_k = s->spill_k;
     g.fin_key = s->fin_key; g.fin_k = s->fin_k;
     g.n_tiles = n_tiles; g.fin_cap = s->res_cap; g.stage_cap = s->res_cap; g.spill_cap = s->res_cap;
-    g.tile_words = THREADS * pl.T; g.spill_sorted = 0;
+    g.tile_words = pl.warp_ns ? 32u * pl.T * pl.warp_ns : (uint32_t)THREADS * pl.T; g.spill_sorted = 0;
     g.counters = s->d_counters;
     pl.ggrid = (n_tiles * 32 + 255) / 256;
     gather_kernel<<<pl.ggrid, 256, 0, st>>>(g);
@@ -1099,8 +1162,11 @@ struct crf_xchg {
     uint32_t step = 0, first_unchecked = 1;      // steps are numbered from 1
     unsigned long long *h_ring = nullptr;        // page-locked: XCHG_RING x XCHG_RESULT_WORDS
     unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
-    crf_seq *pending_seq = nullptr;              // sequence whose asynchronous scan feeds the step in flight
-    uint32_t pending_reruns = 0;
+    std::vector<crf_seq *> pending;              // sequences whose asynchronous scans feed the steps in flight
+    // the exchange kernels run on their own stream behind the scan that feeds them, so the next phase's scan (another
+    // sequence, the context's stream) overlaps the push of this one
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
 };
 
 extern "C" int crf_xchg_create(crf_ctx *c, uint32_t rank, uint32_t world, uint64_t row_cap, crf_xchg **out) {
@@ -1120,7 +1186,14 @@ extern "C" int crf_xchg_create(crf_ctx *c, uint32_t rank, uint32_t world, uint64
     cudaError_t e = cudaMalloc(&x->base, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->base, 0, XCHG_ROWS_OFFSET);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&x->h_ring, (size_t)XCHG_RING * XCHG_RESULT_WORDS * 8);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->xstream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_main, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_side, cudaEventDisableTiming);
     if (e != cudaSuccess) {
+        if (x->xstream) cudaStreamDestroy(x->xstream);
+        if (x->ev_main) cudaEventDestroy(x->ev_main);
+        if (x->ev_side) cudaEventDestroy(x->ev_side);
+        if (x->h_ring) cudaFreeHost(x->h_ring);
         if (x->base) cudaFree(x->base);
         delete x;
         set_err("crf_xchg_create: %s", cudaGetErrorString(e));
@@ -1181,6 +1254,11 @@ extern "C" int crf_xchg_destroy(crf_xchg *x) {
     if (!x) return CRF_OK;
     cudaSetDevice(x->ctx->device);
     cudaStreamSynchronize(x->ctx->stream);
+    cudaStreamSynchronize(x->xstream);
+    for (crf_seq *s : x->pending) s->side_done = nullptr;
+    cudaStreamDestroy(x->xstream);
+    cudaEventDestroy(x->ev_main);
+    cudaEventDestroy(x->ev_side);
     for (uint32_t r = 0; r < x->world; ++r)
         if (x->peer_ipc[r] && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
     if (x->base) cudaFree(x->base);
@@ -1196,14 +1274,16 @@ extern "C" int crf_xchg_set_timeout(crf_xchg *x, double seconds) {
 }
 
 // push + settle of the rows the sequence holds (results of the scan queued before it on the stream)
-static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted) {
+static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted, bool append) {
     for (uint32_t r = 0; r < x->world; ++r)
         if (!x->connected[r]) { set_err("crf_xchg: rank %u is not connected", r); return CRF_ERR_ARG; }
     if (x->step + 1 - x->first_unchecked >= XCHG_RING) {
         set_err("crf_xchg: %u steps in flight without crf_xchg_wait (at most %u)", XCHG_RING, XCHG_RING);
         return CRF_ERR_ARG;
     }
-    cudaStream_t st = x->ctx->stream;
+    cudaStream_t xs = x->xstream;
+    CU(cudaEventRecord(x->ev_main, x->ctx->stream));          // the scan + assembly queued so far
+    CU(cudaStreamWaitEvent(xs, x->ev_main, 0));
     ++x->step;
     PushParams pp = {};
     pp.self = (XchgBlock *)x->base;
@@ -1215,20 +1295,24 @@ static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted) {
     pp.counters = s->d_counters;
     pp.res_cap = s->res_cap; pp.open_cap = s->open_cap;
     pp.trusted = trusted ? 1u : 0u;
+    pp.append = append ? 1u : 0u;
     pp.timeout_ns = x->timeout_ns;
-    publish_kernel<<<1, 32, 0, st>>>(pp);
-    push_kernel<<<148 * 2, 256, 0, st>>>(pp);
+    publish_kernel<<<1, 32, 0, xs>>>(pp);
+    push_kernel<<<148 * 2, 256, 0, xs>>>(pp);
     SettleParams sp = {};
     sp.self = (XchgBlock *)x->base;
-    sp.row_cap = x->row_cap; sp.rank = x->rank; sp.world = x->world; sp.step = x->step; sp.timeout_ns = x->timeout_ns;
-    settle_kernel<<<1, 32, 0, st>>>(sp);
+    sp.row_cap = x->row_cap; sp.rank = x->rank; sp.world = x->world; sp.step = x->step; sp.append = pp.append;
+    sp.timeout_ns = x->timeout_ns;
+    settle_kernel<<<1, 32, 0, xs>>>(sp);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(x->h_ring + (size_t)(x->step % XCHG_RING) * XCHG_RESULT_WORDS, ((XchgBlock *)x->base)->result,
-                       XCHG_RESULT_WORDS * 8, cudaMemcpyDeviceToHost, st));
+                       XCHG_RESULT_WORDS * 8, cudaMemcpyDeviceToHost, xs));
+    CU(cudaEventRecord(x->ev_side, xs));
+    s->side_done = x->ev_side;                                // the next scan of this sequence waits for its rows to be gone
     return CRF_OK;
 }
 
-extern "C" int crf_scan_gather(crf_seq *s, const crf_scan_params *pr, crf_xchg *x) {
+extern "C" int crf_scan_gather(crf_seq *s, const crf_scan_params *pr, crf_xchg *x, int append) {
     if (!s || !pr || !x) { set_err("crf_scan_gather: null argument"); return CRF_ERR_ARG; }
     if (s->ctx != x->ctx) { set_err("crf_scan_gather: sequence and exchange belong to different contexts"); return CRF_ERR_ARG; }
     CHECK(scan_validate(s, pr));
@@ -1242,19 +1326,18 @@ extern "C" int crf_scan_gather(crf_seq *s, const crf_scan_params *pr, crf_xchg *
     CHECK(ensure_result_buffers(s, default_result_cap(s, pr)));
     CHECK(scan_enqueue(s, *s->plan));
     CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    CHECK(xchg_enqueue(s, x, false));
-    x->pending_seq = s;
+    CHECK(xchg_enqueue(s, x, false, append != 0));
+    if (std::find(x->pending.begin(), x->pending.end(), s) == x->pending.end()) x->pending.push_back(s);
     s->plan->launches += 3;
     return CRF_OK;
 }
 
-extern "C" int crf_xchg_push(crf_seq *s, crf_xchg *x) {
+extern "C" int crf_xchg_push(crf_seq *s, crf_xchg *x, int append) {
     if (!s || !x) { set_err("crf_xchg_push: null argument"); return CRF_ERR_ARG; }
     if (s->ctx != x->ctx) { set_err("crf_xchg_push: sequence and exchange belong to different contexts"); return CRF_ERR_ARG; }
     if (!s->have_results) { set_err("crf_xchg_push: no scan results"); return CRF_ERR_ARG; }
     CU(cudaSetDevice(s->ctx->device));
-    CHECK(xchg_enqueue(s, x, true));
-    x->pending_seq = nullptr;
+    CHECK(xchg_enqueue(s, x, true, append != 0));
     return CRF_OK;
 }
 
@@ -1262,7 +1345,7 @@ extern "C" int crf_xchg_wait(crf_xchg *x, crf_xchg_result_t *res) {
     if (!x || !res) { set_err("crf_xchg_wait: null argument"); return CRF_ERR_ARG; }
     if (x->step == 0) { set_err("crf_xchg_wait: nothing was pushed"); return CRF_ERR_ARG; }
     CU(cudaSetDevice(x->ctx->device));
-    CU(cudaStreamSynchronize(x->ctx->stream));
+    CU(cudaStreamSynchronize(x->xstream));                    // (behind everything the context's stream had queued)
     uint32_t worst = XCHG_OK;
     for (uint32_t st = x->first_unchecked; st <= x->step; ++st)
         worst = std::max<uint32_t>(worst, (uint32_t)x->h_ring[(size_t)(st % XCHG_RING) * XCHG_RESULT_WORDS]);
@@ -1275,17 +1358,38 @@ extern "C" int crf_xchg_wait(crf_xchg *x, crf_xchg_result_t *res) {
     res->total_open = r[2];
     res->my_offset = r[3];
     res->any_open = (uint32_t)r[4];
+    res->base_rows = r[5];
     res->step = x->step;
     for (uint32_t q = 0; q < XCHG_MAX_WORLD; ++q) res->rows_of_rank[q] = q < x->world ? r[8 + q] : 0;
     if (res->status == XCHG_TIMEOUT) {
         set_err("crf_xchg_wait: a peer rank did not arrive within %.1f s", x->timeout_ns * 1e-9);
         return CRF_ERR_CUDA;
     }
-    if (x->pending_seq && res->status == XCHG_OK) {   // the asynchronous scan behind this step: its counters are on the host now
-        crf_seq *s = x->pending_seq;
-        CHECK(scan_fill_stats(s, *s->plan, 0));
+    for (crf_seq *s : x->pending) {                           // the asynchronous scans behind these steps: their counters
+        s->side_done = nullptr;                               // are on the host now
+        if (worst == XCHG_OK) CHECK(scan_fill_stats(s, *s->plan, 0));
     }
-    x->pending_seq = nullptr;
+    x->pending.clear();
+    return CRF_OK;
+}
+
+extern "C" int crf_xchg_step_result(crf_xchg *x, uint32_t step, crf_xchg_result_t *res) {
+    if (!x || !res) { set_err("crf_xchg_step_result: null argument"); return CRF_ERR_ARG; }
+    if (step == 0 || step >= x->first_unchecked || step + XCHG_RING <= x->step) {
+        set_err("crf_xchg_step_result: step %u is not among the last %u completed steps", step, XCHG_RING);
+        return CRF_ERR_ARG;
+    }
+    const unsigned long long *r = x->h_ring + (size_t)(step % XCHG_RING) * XCHG_RESULT_WORDS;
+    memset(res, 0, sizeof(*res));
+    res->status = res->worst_status = (uint32_t)r[0];
+    res->steps_checked = 1;
+    res->step = step;
+    res->total_rows = r[1];
+    res->total_open = r[2];
+    res->my_offset = r[3];
+    res->any_open = (uint32_t)r[4];
+    res->base_rows = r[5];
+    for (uint32_t q = 0; q < XCHG_MAX_WORLD; ++q) res->rows_of_rank[q] = q < x->world ? r[8 + q] : 0;
     return CRF_OK;
 }
 
@@ -1336,6 +1440,8 @@ extern "C" int crf_xchg_patch_end(crf_xchg *x, const uint64_t *rows, const uint3
 
 static cudaError_t preload_kernels() {
     cudaError_t e = preload(scan_kernel<1>);
+    if (e == cudaSuccess) e = preload(scan_warp_kernel<8, 1>);
+    if (e == cudaSuccess) e = preload(scan_warp_kernel<8, 2>);
     if (e == cudaSuccess) e = preload(scan_kernel<2>);
     if (e == cudaSuccess) e = preload(scan_kernel<4>);
     if (e == cudaSuccess) e = preload(scan_kernel<8>);

@@ -46,6 +46,7 @@ struct TileCtx {
     uint32_t cap;
     uint2 *startq;                 // run starts found by stage A of the exact phase
     uint32_t *nstart;
+    uint32_t longcap, startcap;    // capacities of longq / startq
 };
 
 // Exact M_k word w: from the staged tile when everything needed is there, else from global memory.
@@ -131,7 +132,7 @@ __device__ inline void handle_start(const ScanParams &p, const TileCtx &t, const
         return;
     }
     const uint32_t slot = atomicAdd(t.nlong, 1u);
-    if (slot < LONGCAP) {
+    if (slot < t.longcap) {
         t.longq[3 * slot] = st;
         t.longq[3 * slot + 1] = k;
         t.longq[3 * slot + 2] = i0 >> 5;
@@ -200,7 +201,7 @@ __device__ inline void exact_item(const ScanParams &p, const TileCtx &t, uint32_
             else if (st1 == NOPOS) st1 = st;
             else {
                 const uint32_t slot = atomicAdd(t.nstart, 1u);
-                if (slot < STARTQ_CAP) t.startq[slot] = make_uint2(st, k | (re << 16));
+                if (slot < t.startcap) t.startq[slot] = make_uint2(st, k | (re << 16));
                 else handle_start(p, t, p.ktab[k], k, st, re);
             }
         }
@@ -214,6 +215,12 @@ __device__ inline void exact_item(const ScanParams &p, const TileCtx &t, uint32_
     }
 }
 
+// mask |= bit, predicated on the filter's verdict: one ISETP + one predicated LOP3 instead of SEL + SHF.L + LOP3 behind the
+// compare (the bit itself lives in the uniform datapath: it only depends on the motif size)
+__device__ __forceinline__ void set_bit_if(uint32_t &mask, bool hit, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(mask) : "r"((uint32_t)hit), "r"(bit));
+}
+
 // ---- fast-phase filters (T+1 words: the strip plus one look-ahead word) ------------------------
 template <int T>
 __device__ __forceinline__ bool filter_word(const uint32_t (&NH)[T + 1], const uint32_t (&FH)[T + 2], uint32_t s) {
@@ -222,15 +229,20 @@ __device__ __forceinline__ bool filter_word(const uint32_t (&NH)[T + 1], const u
     for (int i = 0; i <= T; ++i) hit |= (NH[i] == __funnelshift_r(FH[i], FH[i + 1], s));
     return hit;
 }
+// "some aligned half-word of the compare is zero" = the minimum over all half-words is zero: one packed three-input
+// minimum (VIMNMX3.U16x2, ALU rate on sm_100a -- profiles/microbench/dpx_min.cu) per TWO words instead of a
+// subtract + LOP3 per word
 template <int T>
 __device__ __forceinline__ bool filter_half(const uint32_t (&NH)[T + 1], const uint32_t (&FH)[T + 2], uint32_t s) {
-    uint32_t acc = 0;
+    uint32_t acc = 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i <= T; ++i) {
-        const uint32_t x = NH[i] ^ __funnelshift_r(FH[i], FH[i + 1], s);
-        acc |= (x - 0x00010001u) & ~x;
+    for (int i = 0; i + 1 <= T; i += 2) {
+        const uint32_t x0 = NH[i] ^ __funnelshift_r(FH[i], FH[i + 1], s);
+        const uint32_t x1 = NH[i + 1] ^ __funnelshift_r(FH[i + 1], FH[i + 2], s);
+        acc = __vimin3_u16x2(acc, x0, x1);
     }
-    return (acc & 0x80008000u) != 0;
+    if (((T + 1) & 1) != 0) acc = __vminu2(acc, NH[T] ^ __funnelshift_r(FH[T], FH[T + 1], s));
+    return ((acc - 0x00010001u) & ~acc & 0x80008000u) != 0;
 }
 // SUP: positions that start a stretch of > k equal bases (HD = dilated mismatch word of M'_1, ~HD = such
 // positions) are treated as mismatches.  A primitive motif of size k cannot contain k+1 equal consecutive
@@ -335,6 +347,7 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
     tc.sH = sH; tc.sL = sL; tc.sN = sN; tc.wbase = w0; tc.nsm = nsm;
     tc.key = s_key; tc.kk = s_k; tc.nout = &s_misc[8]; tc.nlong = &s_misc[9]; tc.longq = s_long; tc.cap = p.outcap;
     tc.startq = s_startq; tc.nstart = &s_misc[10];
+    tc.longcap = LONGCAP; tc.startcap = STARTQ_CAP;
 
     uint32_t NH[T + 1], NL[T + 1];
 #pragma unroll
@@ -386,10 +399,10 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
                 const uint32_t sh0 = sg.sh0, sh1 = sg.sh1, sh2 = sg.sh2;
                 if ((sg.mode & 15u) == MODE_WORD) {
 #pragma unroll 1
-                    for (uint32_t s = s_lo; s <= s_hi; ++s) hitmask |= (filter_word<T>(NH, FH, s) ? 1u : 0u) << s;
+                    for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1) set_bit_if(hitmask, filter_word<T>(NH, FH, s), bit);
                 } else if ((sg.mode & 15u) == MODE_HALF) {
 #pragma unroll 1
-                    for (uint32_t s = s_lo; s <= s_hi; ++s) hitmask |= (filter_half<T>(NH, FH, s) ? 1u : 0u) << s;
+                    for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1) set_bit_if(hitmask, filter_half<T>(NH, FH, s), bit);
                 } else {
                     const uint32_t sup = sg.mode >> 4;  // 0: none, 1: stretches of > 8 equal bases, 2: > 16
                     if (sup == 2 && hd_level == 1) {    // widen the homopolymer mask from 8 to 16 matches
@@ -402,45 +415,45 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
                     if (sup) {
                         if (mode == MODE_BYTE) {
 #pragma unroll 1
-                            for (uint32_t s = s_lo; s <= s_hi; ++s)
-                                hitmask |= (filter_byte<T, true>(NH, NL, FH, FL, s, HD) ? 1u : 0u) << s;
+                            for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                                set_bit_if(hitmask, filter_byte<T, true>(NH, NL, FH, FL, s, HD), bit);
                         } else if (sh2) {
 #pragma unroll 1
-                            for (uint32_t s = s_lo; s <= s_hi; ++s)
-                                hitmask |= (filter_erode<T, 3, true>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD) ? 1u : 0u) << s;
+                            for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                                set_bit_if(hitmask, filter_erode<T, 3, true>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD), bit);
                         } else if (sh1) {
 #pragma unroll 1
-                            for (uint32_t s = s_lo; s <= s_hi; ++s)
-                                hitmask |= (filter_erode<T, 2, true>(NH, NL, FH, FL, s, sh0, sh1, 0, HD) ? 1u : 0u) << s;
+                            for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                                set_bit_if(hitmask, filter_erode<T, 2, true>(NH, NL, FH, FL, s, sh0, sh1, 0, HD), bit);
                         } else if (sh0) {
 #pragma unroll 1
-                            for (uint32_t s = s_lo; s <= s_hi; ++s)
-                                hitmask |= (filter_erode<T, 1, true>(NH, NL, FH, FL, s, sh0, 0, 0, HD) ? 1u : 0u) << s;
+                            for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                                set_bit_if(hitmask, filter_erode<T, 1, true>(NH, NL, FH, FL, s, sh0, 0, 0, HD), bit);
                         } else {
 #pragma unroll 1
-                            for (uint32_t s = s_lo; s <= s_hi; ++s)
-                                hitmask |= (filter_erode<T, 0, true>(NH, NL, FH, FL, s, 0, 0, 0, HD) ? 1u : 0u) << s;
+                            for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                                set_bit_if(hitmask, filter_erode<T, 0, true>(NH, NL, FH, FL, s, 0, 0, 0, HD), bit);
                         }
                     } else if (mode == MODE_BYTE) {
 #pragma unroll 1
-                        for (uint32_t s = s_lo; s <= s_hi; ++s)
-                            hitmask |= (filter_byte<T, false>(NH, NL, FH, FL, s, HD) ? 1u : 0u) << s;
+                        for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                            set_bit_if(hitmask, filter_byte<T, false>(NH, NL, FH, FL, s, HD), bit);
                     } else if (sh2) {
 #pragma unroll 1
-                        for (uint32_t s = s_lo; s <= s_hi; ++s)
-                            hitmask |= (filter_erode<T, 3, false>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD) ? 1u : 0u) << s;
+                        for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                            set_bit_if(hitmask, filter_erode<T, 3, false>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD), bit);
                     } else if (sh1) {
 #pragma unroll 1
-                        for (uint32_t s = s_lo; s <= s_hi; ++s)
-                            hitmask |= (filter_erode<T, 2, false>(NH, NL, FH, FL, s, sh0, sh1, 0, HD) ? 1u : 0u) << s;
+                        for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                            set_bit_if(hitmask, filter_erode<T, 2, false>(NH, NL, FH, FL, s, sh0, sh1, 0, HD), bit);
                     } else if (sh0) {
 #pragma unroll 1
-                        for (uint32_t s = s_lo; s <= s_hi; ++s)
-                            hitmask |= (filter_erode<T, 1, false>(NH, NL, FH, FL, s, sh0, 0, 0, HD) ? 1u : 0u) << s;
+                        for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                            set_bit_if(hitmask, filter_erode<T, 1, false>(NH, NL, FH, FL, s, sh0, 0, 0, HD), bit);
                     } else {
 #pragma unroll 1
-                        for (uint32_t s = s_lo; s <= s_hi; ++s)
-                            hitmask |= (filter_erode<T, 0, false>(NH, NL, FH, FL, s, 0, 0, 0, HD) ? 1u : 0u) << s;
+                        for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
+                            set_bit_if(hitmask, filter_erode<T, 0, false>(NH, NL, FH, FL, s, 0, 0, 0, HD), bit);
                     }
                 }
             }

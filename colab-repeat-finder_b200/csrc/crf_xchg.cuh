@@ -39,10 +39,12 @@ struct XchgBlock {
     unsigned long long count_slot[2][XCHG_MAX_WORLD];  // [step parity][rank]: written by that rank's push_kernel
     unsigned long long done_slot[2][XCHG_MAX_WORLD];   // root only: rows of [rank] have landed (value = its open-ended rows)
     unsigned long long my_offset;                      // where this rank's rows start in the root buffer (last push)
+    unsigned long long base_rows;                      // rows gathered by the earlier phases of the job in progress
     unsigned int blocks_done;                          // last-block counter of push_kernel
     unsigned int push_ok;                              // publish_kernel: this rank may push (nothing void, everything fits)
     unsigned long long result[XCHG_RESULT_WORDS];      // settle_kernel: [0] status [1] total rows [2] total open
                                                        // [3] my offset [4] some rank has open-ended rows
+                                                       // [5] rows of the job's earlier phases (before this step)
                                                        // [8 + r] rows of rank r
 };
 
@@ -94,6 +96,7 @@ struct PushParams {
     const unsigned long long *counters;
     uint32_t res_cap, open_cap;
     uint32_t trusted;                    // the host has already checked (and fixed up) the scan these rows come from
+    uint32_t append;                     // this step's rows go after those of the job's earlier phases (base_rows)
     unsigned long long timeout_ns;
 };
 
@@ -122,8 +125,9 @@ __global__ void __launch_bounds__(32) publish_kernel(const PushParams p) {
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
     const bool any_bad = __any_sync(0xFFFFFFFFu, bad);
     if (lane == 0) {
-        const bool ok = valid && !any_bad && mine + n_total <= p.row_cap;
-        p.self->my_offset = mine;
+        const unsigned long long base = p.append ? p.self->base_rows : 0ull;   // (left by this rank's previous settle_kernel)
+        const bool ok = valid && !any_bad && base + mine + n_total <= p.row_cap;
+        p.self->my_offset = base + mine;
         p.self->push_ok = ok ? 1u : 0u;
     }
 }
@@ -136,13 +140,26 @@ __global__ void __launch_bounds__(256) push_kernel(const PushParams p) {
     const bool ok = p.self->push_ok != 0;
     const unsigned long long n_total = p.counters[C_TOTAL], n_open = p.counters[C_OPEN];
     if (ok) {
-        uint32_t *d_rec = p.root_rows + off, *d_start = d_rec + p.row_cap, *d_end = d_start + p.row_cap, *d_k = d_end + p.row_cap;
-        const uint32_t n = (uint32_t)n_total, stride = gridDim.x * blockDim.x;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-            d_rec[i] = p.o_rec[i];
-            d_start[i] = p.o_start[i];
-            d_end[i] = p.o_end[i];
-            d_k[i] = p.o_k[i];
+        // four columns, each copied with 16-byte peer stores: the destination starts at an arbitrary row, so every column
+        // has a scalar head up to the first 16-byte boundary of the DESTINATION, a vector body (four scalar loads from my
+        // own HBM feed one st.v4 over NVLink) and a scalar tail
+        const uint32_t n = (uint32_t)n_total;
+        const uint32_t *src[4] = {p.o_rec, p.o_start, p.o_end, p.o_k};
+        const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t *dst = p.root_rows + (size_t)c * p.row_cap + off;
+            const uint32_t *sp = src[c];
+            const uint32_t head = min(n, (uint32_t)((4u - (uint32_t)(((uintptr_t)dst >> 2) & 3u)) & 3u));
+            const uint32_t nvec = (n - head) >> 2;
+            if (gtid < head) dst[gtid] = sp[gtid];
+            uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+            for (uint32_t v = gtid; v < nvec; v += gsize) {
+                const uint32_t i = head + 4 * v;
+                dv[v] = make_uint4(sp[i], sp[i + 1], sp[i + 2], sp[i + 3]);
+            }
+            const uint32_t tail0 = head + 4 * nvec;
+            if (gtid < n - tail0) dst[tail0 + gtid] = sp[tail0 + gtid];
         }
     }
     __threadfence_system();                               // my rows are visible on the root before the done word can be
@@ -160,7 +177,7 @@ __global__ void __launch_bounds__(256) push_kernel(const PushParams p) {
 struct SettleParams {
     XchgBlock *self;
     uint64_t row_cap;
-    uint32_t rank, world, step;
+    uint32_t rank, world, step, append;
     unsigned long long timeout_ns;
 };
 
@@ -191,10 +208,14 @@ __global__ void __launch_bounds__(32) settle_kernel(const SettleParams p) {
     const bool any_open = __any_sync(0xFFFFFFFFu, has_open);
     if (lane < p.world) p.self->result[8 + lane] = n;
     if (lane == 0) {
+        const unsigned long long base = p.append ? p.self->base_rows : 0ull;
+        total += base;                                     // cumulative over the phases of this job
         uint32_t status = XCHG_OK;
         if (any_timeout) status = XCHG_TIMEOUT;
         else if (total > p.row_cap) status = XCHG_ROOT_FULL;
         else if (any_void) status = XCHG_VOID_STEP;
+        p.self->base_rows = total;                         // every rank computes the same value from the same counts
+        p.self->result[5] = base;
         p.self->result[0] = status;
         p.self->result[1] = total;
         p.self->result[2] = open_total;

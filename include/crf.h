@@ -121,6 +121,10 @@ int crf_seq_info(const crf_seq *seq, crf_seq_info_t *info);
 /* keep runs whose motif is not primitive too (used to find where the reference's interval-mode
  * loop stops, prf:70-74: is_in_middle_of_repeat() does not look at the motif) */
 #define CRF_SCAN_NO_PRIMITIVITY 1u
+/* which scan kernel (same results, different scheduling; default = the library's choice): tiles owned by warps, no
+ * block-wide barrier (csrc/crf_scan_warp.cuh), or tiles owned by 256-thread blocks (csrc/crf_scan.cuh) */
+#define CRF_SCAN_WARP_TILES 2u
+#define CRF_SCAN_BLOCK_TILES 4u
 /* bits 16..31: profiling switches (results are NOT valid when set): 1<<16 = fast phase only */
 #define CRF_SCAN_DEBUG_FAST_ONLY (1u << 16)
 #define CRF_SCAN_DEBUG_NO_SUP (1u << 17)   /* tuning: no homopolymer suppression in the filters (results stay valid) */
@@ -198,10 +202,13 @@ int crf_xchg_set_timeout(crf_xchg *xchg, double seconds); /* how long a kernel w
 
 /* crf_scan + push in one go, fully asynchronous: nothing is copied back and the host does not wait.  If the scan
  * outgrows a buffer, has a long spill list or more open-ended rows than their list holds, the step is void on
- * every rank (status 1): repeat it with crf_scan (which grows what was too small) followed by crf_xchg_push. */
-int crf_scan_gather(crf_seq *seq, const crf_scan_params *params, crf_xchg *xchg);
+ * every rank (status 1): repeat it with crf_scan (which grows what was too small) followed by crf_xchg_push.
+ * A job may be gathered in several PHASES (a rank holds one sequence per phase; genome order = phase-major, rank-minor):
+ * append != 0 puts this step's rows after those of the job's earlier steps.  The exchange kernels run on a stream of
+ * their own behind the scan that feeds them, so the push of phase p overlaps the scan of phase p + 1. */
+int crf_scan_gather(crf_seq *seq, const crf_scan_params *params, crf_xchg *xchg, int append);
 /* Push the rows of the last completed crf_scan (asynchronous). */
-int crf_xchg_push(crf_seq *seq, crf_xchg *xchg);
+int crf_xchg_push(crf_seq *seq, crf_xchg *xchg, int append);
 
 typedef struct {
     uint32_t status;        /* of the last step: 0 ok, 1 void (repeat the slow way), 2 rank 0's buffer too small, 3 timeout */
@@ -210,13 +217,16 @@ typedef struct {
     uint32_t step;          /* number of the last step (from 1) */
     uint32_t any_open;      /* some rank has open-ended rows (same answer on every rank): stitch before using the rows */
     uint32_t reserved;
-    uint64_t total_rows;    /* rows of all ranks (they are on rank 0, in rank order = genome order) */
+    uint64_t total_rows;    /* rows of all ranks so far in this job (they are on rank 0, in genome order) */
+    uint64_t base_rows;     /* of which gathered by the job's earlier phases (0 unless the step appended) */
     uint64_t total_open;    /* rank 0 only: open-ended rows of all ranks (runs that left their unit's data) */
     uint64_t my_offset;     /* first row of this rank inside rank 0's buffer */
     uint64_t rows_of_rank[CRF_XCHG_MAX_WORLD];
 } crf_xchg_result_t;
 /* Wait until this rank's part of every queued step is complete (on rank 0: until all rows have landed). */
 int crf_xchg_wait(crf_xchg *xchg, crf_xchg_result_t *result);
+/* The result of one of the last 64 steps that crf_xchg_wait has already checked (phased jobs: one per phase). */
+int crf_xchg_step_result(crf_xchg *xchg, uint32_t step, crf_xchg_result_t *result);
 /* Rank 0: copy gathered rows [first_row, first_row + n_rows) out (see crf_fetch for the columns). */
 int crf_xchg_fetch(crf_xchg *xchg, uint32_t *record, uint32_t *start, uint32_t *end, uint32_t *motif_size,
                    uint64_t first_row, uint64_t n_rows, int dst_on_device);

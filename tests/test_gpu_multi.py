@@ -35,14 +35,15 @@ def _whole(mods, bases, offsets, kmax=50):
         return seq.fetch(n)
 
 
-@pytest.mark.parametrize("world", [2, 3, 8])
-def test_loopback_ranks_gather_equals_single_scan(mods, world):
-    """24 ragged records over `world` ranks (threads on device 0): rank 0's gathered rows == the one-load scan."""
+@pytest.mark.parametrize("world,phases", [(2, 1), (2, 2), (3, 3), (8, 2)])
+def test_loopback_ranks_gather_equals_single_scan(mods, world, phases):
+    """24 ragged records over `world` ranks (threads on device 0), each step in `phases` phases whose pushes overlap the
+    next phase's scan: rank 0's gathered rows == the one-load scan."""
     bases, offsets, _ = mods.synth.s38(device=None, scale=0.002)            # ~6 Mbp, 24 records
     want = _whole(mods, bases, offsets)
     lengths = np.diff(offsets.astype(np.int64))
     got = mods.multi.scan_on_devices([0] * world, bases, offsets[:-1], lengths, 1, 50, 3, 9, chunk=1 << 17, halo=1 << 12,
-                                     timeout_s=30)
+                                     timeout_s=30, phases=phases)
     assert len(want[0]) > 5000
     for a, b in zip(want, got):
         assert np.array_equal(a, b)
@@ -97,7 +98,7 @@ def test_many_steps_in_flight_then_one_wait(mods):
 
     def work(rank):
         rs = mods.multi.RankScan(mods.cabi.Context(0), comms[rank], bases, offsets[:-1], lengths, 1, 50, 3, 9,
-                                 chunk=1 << 18, halo=1 << 12, timeout_s=30)
+                                 chunk=1 << 18, halo=1 << 12, timeout_s=30, phases=2)
         rs.step_async()
         rs.finish()                                   # sizes the buffers
         for _ in range(20):
@@ -112,7 +113,7 @@ def test_many_steps_in_flight_then_one_wait(mods):
     for t in threads:
         t.join()
     assert out[0][0] == out[1][0] == len(want[0])
-    assert out[0][1] == 20 and out[0][2] == 0
+    assert out[0][1] == 40 and out[0][2] == 0          # 20 jobs x 2 phases, every status word checked
     for a, b in zip(want, out[0][3]):
         assert np.array_equal(a, b)
 
