@@ -337,11 +337,11 @@ def main():
     if world == 1:
         for _ in range(args.steps):                  # one synchronous crf_scan per step (its counters come back every time)
             rs.step_async()
-            total_results = rs.finish()
-            st_ = rs.stats()
-            kernel_ms.append(st_["kernel_ms"])
-            scan_ms.append(st_["scan_ms"])
-            launches += st_["launches"]
+        total_results = rs.finish()
+        st_ = rs.stats()                             # events / counters of the last step (the steps are identical)
+        kernel_ms.append(st_["kernel_ms"])
+        scan_ms.append(st_["scan_ms"])
+        launches = st_["launches"] * args.steps
     else:
         # N ranks: every step is kernel launches only -- counts and rows travel GPU to GPU -- so the K steps are queued back
         # to back and the host waits once; finish() then checks the status word of every one of the K steps

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("CRF_LIB_PATH") or os.path.join(_HERE, "libcrf.so")   
 SCAN_NO_PRIMITIVITY = 1
 SCAN_WARP_TILES = 2
 SCAN_BLOCK_TILES = 4
+SCAN_TWO_STRIPS = 8
 
 CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_CAPACITY = range(6)
 

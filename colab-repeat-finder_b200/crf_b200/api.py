@@ -108,7 +108,7 @@ def _interval_stop_position(ctx, s, end_position, kmin, kmax, knobs):
         hi_t = min(L - 1, E + window)                   # last t examined
         we = min(L, hi_t + 1 + kmax)
         with ctx.load(s[ws:we], max_motif_cap=kmax) as seq:
-            n = seq.scan(kmin, kmax, 2, 1, flags=_cabi.SCAN_NO_PRIMITIVITY, **knobs)
+            n = seq.scan(kmin, kmax, 2, 1, **{**knobs, "flags": int(knobs.get("flags", 0)) | _cabi.SCAN_NO_PRIMITIVITY})
             _, st, en, kk = seq.fetch(n)
         st = st.astype(np.int64) + ws
         i0 = en.astype(np.int64) + ws - kk

@@ -68,6 +68,7 @@ struct crf_ctx {
     cudaEvent_t ev[SLOTS][5] = {};
     unsigned long long *h_counters = nullptr;           // SLOTS x C_COUNT
     int next_slot = 0;
+    int n_xchg = 0;                                     // exchange blocks alive on this context (a rank of a multi-GPU job)
 };
 static const size_t CACHE_LIMIT_BYTES = 24ull << 30;
 static thread_local crf_ctx *g_ctx = nullptr;          // context of the API call in progress
@@ -128,6 +129,7 @@ struct ScanPlan {
     crf_scan_params pr;
     int T;
     int warp_ns;                       // 0: block-tiled scan_kernel; 1 / 2: scan_warp_kernel with that many sub-tiles per warp
+    int block_ns;                      // block-tiled kernel: strips per thread (1 or 2)
     uint32_t warp_grid;
     uint32_t n_tiles, outcap, ggrid, tgrid, launches;
     size_t smem;
@@ -163,6 +165,9 @@ struct crf_seq {
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;   // h_counters: the context's page-locked block
     cudaEvent_t *ev = nullptr;                                         // the context's events
     uint32_t open_cap = 0;                                             // rows d_open_rows holds
+    cudaGraphExec_t graph_exec = nullptr;                              // the whole scan of a small input, captured once
+    struct ScanLaunch *graph_key = nullptr;
+    uint32_t graph_launches = 0;
     cudaEvent_t side_done = nullptr;                                   // an exchange stream still reads this sequence's rows
     ScanPlan *plan = nullptr;                                          // launch parameters of the scan in flight / last run
     crf_scan_stats_t stats = {};
@@ -283,6 +288,7 @@ static int bitonic_sort(cudaStream_t st, uint64_t *key, uint16_t *val, uint32_t 
 }
 
 // ---- sequence upload ------------------------------------------------------------------------
+static void free_graph_key(struct ScanLaunch *k);
 static void free_seq(crf_seq *s) {
     if (!s) return;
     if (s->ctx) { cudaSetDevice(s->ctx->device); g_ctx = s->ctx; }
@@ -294,13 +300,15 @@ static void free_seq(crf_seq *s) {
     dev_free(s->o_rec); dev_free(s->o_start); dev_free(s->o_end); dev_free(s->o_k);
     dev_free(s->tile_cnt); dev_free(s->tile_base); dev_free(s->tile_off);
     dev_free(s->d_counters);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    free_graph_key(s->graph_key);
     delete s->plan;
     delete s;
 }
 
-#ifndef CRF_DEFAULT_WARP_NS
-#define CRF_DEFAULT_WARP_NS 0          // scan kernel used when neither a flag nor CRF_SCAN_KERNEL says otherwise
-#endif
+#ifndef CRF_DEFAULT_KERNEL
+#define CRF_DEFAULT_KERNEL 0           // scan kernel used when neither a flag nor CRF_SCAN_KERNEL says otherwise:
+#endif                                 // 0 block-tiled, 1 / 2 warp-tiled (1 / 2 sub-tiles), 3 block-tiled with 2 strips per thread
 static const uint32_t EX_CAP = 1u << 22;       // exotic symbols kept per load
 static const uint32_t TILE_WORDS_MAX = 4096;   // THREADS * 16
 static const uint32_t MAX_K = 65535;
@@ -782,14 +790,6 @@ static int ensure_result_buffers(crf_seq *s, uint32_t cap) {
     return CRF_OK;
 }
 
-template <int T>
-static int launch_scan(const ScanParams &sp, uint32_t n_tiles, size_t smem, cudaStream_t st) {
-    CU(cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    scan_kernel<T><<<n_tiles, THREADS, smem, st>>>(sp);
-    CU(cudaGetLastError());
-    return CRF_OK;
-}
-
 // default scan kernel of this process: CRF_SCAN_KERNEL=block|warp1|warp2 (tuning / A-B runs), else the library default
 static int default_warp_ns() {
     static int v = -1;
@@ -798,7 +798,8 @@ static int default_warp_ns() {
         if (e && !strcmp(e, "block")) v = 0;
         else if (e && !strcmp(e, "warp1")) v = 1;
         else if (e && !strcmp(e, "warp2")) v = 2;
-        else v = CRF_DEFAULT_WARP_NS;
+        else if (e && !strcmp(e, "block2")) v = 3;
+        else v = CRF_DEFAULT_KERNEL;
     }
     return v;
 }
@@ -863,10 +864,13 @@ static int scan_prepare(crf_seq *s, const crf_scan_params *pr, ScanPlan &pl) {
     // which kernel: the warp-tiled one (CRF_SCAN_WARP_TILES, two sub-tiles per warp) or the block-tiled one; T != 8 exists
     // only block-tiled.  CRF_SCAN_KERNEL=block|warp1|warp2 overrides the default (tuning).
     pl.warp_ns = default_warp_ns();
+    pl.block_ns = 1;
+    if (pl.warp_ns == 3) { pl.warp_ns = 0; pl.block_ns = 2; }
     if (pr->flags & CRF_SCAN_BLOCK_TILES) pl.warp_ns = 0;
     if (pr->flags & CRF_SCAN_WARP_TILES) pl.warp_ns = std::max(pl.warp_ns, 1);
-    if (pl.T != 8 || pr->max_motif_size > 1024) pl.warp_ns = 0;      // (a warp's halo must stay a small part of its tile)
-    const uint32_t TW = pl.warp_ns ? 32u * pl.T * pl.warp_ns : (uint32_t)THREADS * pl.T;
+    if (pr->flags & CRF_SCAN_TWO_STRIPS) { pl.warp_ns = 0; pl.block_ns = 2; }
+    if (pl.T != 8 || pr->max_motif_size > 1024) { pl.warp_ns = 0; pl.block_ns = 1; }   // (other shapes: the plain block kernel)
+    const uint32_t TW = pl.warp_ns ? 32u * pl.T * pl.warp_ns : (uint32_t)THREADS * pl.T * pl.block_ns;
     pl.n_tiles = (s->n_words + TW - 1) / TW;
     if (s->tiles_cap < pl.n_tiles + 1) {
         dev_free(s->tile_cnt); dev_free(s->tile_base); dev_free(s->tile_off);
@@ -893,7 +897,14 @@ static int scan_prepare(crf_seq *s, const crf_scan_params *pr, ScanPlan &pl) {
         pl.warp_grid = std::max(pl.warp_grid, 1u);
     } else {
         pl.outcap = pr->tile_out_cap ? pr->tile_out_cap : 1024;
-        pl.smem = scan_smem_bytes(pl.T, pr->max_motif_size, pl.outcap);
+        pl.smem = scan_smem_bytes(pl.T, pr->max_motif_size, pl.outcap, pl.block_ns);
+        const int smem = (int)pl.smem;
+        if (pl.block_ns == 2) CU(cudaFuncSetAttribute(scan_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else if (pl.T == 1) CU(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else if (pl.T == 2) CU(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else if (pl.T == 4) CU(cudaFuncSetAttribute(scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else if (pl.T == 8) CU(cudaFuncSetAttribute(scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else CU(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     pl.single_copy = pr->min_repeats == 1;    // see single_copy_filter_kernel
     return CRF_OK;
@@ -913,12 +924,63 @@ static int launch_translate(crf_seq *s, ScanPlan &pl, cudaStream_t st) {
     return CRF_OK;
 }
 
-// memset -> scan -> tile offsets -> spill sort -> gather -> (single-copy filter) -> translate, all asynchronous on the
-// context's stream, result buffers of s->res_cap rows.  ev[0] .. ev[3] bracket the whole / the scan kernel.
-static int scan_enqueue(crf_seq *s, ScanPlan &pl) {
+// Everything the kernels of one scan are launched with; doubles as the key of the captured CUDA graph.
+struct ScanLaunch {
+    ScanParams sp;
+    GatherParams g;
+    TranslateParams tp;
+    uint32_t T, warp_ns, block_ns, warp_grid, n_tiles, ggrid, tgrid, single_copy;
+    unsigned long long smem;
+    uint32_t *tile_off;
+    uint32_t n_words_alloc, res_cap;
+};
+
+// memset -> scan -> tile offsets -> spill sort -> gather -> (single-copy filter) -> translate on `st`; ev[0] .. ev[3] bracket
+// the whole / the scan kernel (ev_flags = cudaEventRecordExternal while the stream is being captured into a graph).
+static int scan_launch_all(crf_seq *s, const ScanLaunch &L, cudaStream_t st, unsigned ev_flags, uint32_t *launches) {
+    CU(cudaEventRecordWithFlags(s->ev[0], st, ev_flags));
+    CU(cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
+    CU(cudaEventRecordWithFlags(s->ev[1], st, ev_flags));
+    const uint32_t n_tiles = L.n_tiles;
+    const size_t smem = (size_t)L.smem;
+    if (L.warp_ns == 1) scan_warp_kernel<8, 1><<<L.warp_grid, 32 * WARPS_PER_CTA, smem, st>>>(L.sp);
+    else if (L.warp_ns == 2) scan_warp_kernel<8, 2><<<L.warp_grid, 32 * WARPS_PER_CTA, smem, st>>>(L.sp);
+    else if (L.block_ns == 2) scan_kernel<8, 2><<<n_tiles, THREADS, smem, st>>>(L.sp);
+    else if (L.T == 1) scan_kernel<1><<<n_tiles, THREADS, smem, st>>>(L.sp);
+    else if (L.T == 2) scan_kernel<2><<<n_tiles, THREADS, smem, st>>>(L.sp);
+    else if (L.T == 4) scan_kernel<4><<<n_tiles, THREADS, smem, st>>>(L.sp);
+    else if (L.T == 8) scan_kernel<8><<<n_tiles, THREADS, smem, st>>>(L.sp);
+    else scan_kernel<16><<<n_tiles, THREADS, smem, st>>>(L.sp);
+    CU(cudaGetLastError());
+    CU(cudaEventRecordWithFlags(s->ev[2], st, ev_flags));
+    tile_offsets_kernel<<<1, 1024, 0, st>>>(s->tile_cnt, L.tile_off, n_tiles, s->d_counters);
+    spill_sort_small_kernel<<<1, 1024, 0, st>>>(L.sp.spill_key, L.sp.spill_k, L.res_cap, s->d_counters);
+    gather_kernel<<<L.ggrid, 256, 0, st>>>(L.g);
+    *launches = 4;
+    if (L.single_copy) {
+        single_copy_filter_kernel<<<1, 1024, 0, st>>>(L.g.fin_key, L.g.fin_k, L.sp.NM, L.sp.X, L.n_words_alloc, L.res_cap,
+                                                      s->d_counters);
+        ++*launches;
+    }
+    translate_kernel<<<L.tgrid, 256, 0, st>>>(L.tp);
+    ++*launches;
+    CU(cudaGetLastError());
+    CU(cudaEventRecordWithFlags(s->ev[3], st, ev_flags));
+    return CRF_OK;
+}
+
+// A scan of a small input (a chromosome, a batch of reads) is a handful of short kernels: launching them as one captured
+// graph takes the per-launch gaps out of a step that is otherwise ~100 us.  The graph is re-captured whenever anything it
+// was built from changes (buffers grown, other filters, another output map).
+static const uint32_t GRAPH_MAX_TILES = 8192;
+static void free_graph_key(ScanLaunch *k) { delete k; }
+
+static int scan_enqueue(crf_seq *s, ScanPlan &pl, bool allow_graph = true) {
     cudaStream_t st = s->ctx->stream;
     const crf_scan_params *pr = &pl.pr;
-    ScanParams sp;
+    ScanLaunch L;
+    memset(&L, 0, sizeof(L));                      // (the struct is compared byte-wise: padding must be defined)
+    ScanParams &sp = L.sp;
     sp.H = s->H; sp.L = s->L; sp.NM = s->NM; sp.X = s->X;
     sp.ktab = s->d_ktab; sp.segs = s->d_segs; sp.n_segs = s->n_segs;
     sp.ex_key = s->ex_key; sp.n_exotic = s->n_exotic;
@@ -933,55 +995,55 @@ static int scan_enqueue(crf_seq *s, ScanPlan &pl) {
     sp.tile_cnt = s->tile_cnt; sp.tile_base = s->tile_base;
     sp.spill_key = s->spill_key; sp.spill_k = s->spill_k; sp.spill_cap = s->res_cap;
     sp.counters = s->d_counters;
-    pl.launches = 0;
-
-    if (s->side_done) {            // the previous push of this sequence's rows (on the exchange's own stream) comes first
-        CU(cudaStreamWaitEvent(st, s->side_done, 0));
-        s->side_done = nullptr;
-    }
-    CU(cudaEventRecord(s->ev[0], st));
-    CU(cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
-    CU(cudaEventRecord(s->ev[1], st));
     const uint32_t n_tiles = pl.n_tiles;
-    if (pl.warp_ns == 1) {
-        scan_warp_kernel<8, 1><<<pl.warp_grid, 32 * WARPS_PER_CTA, pl.smem, st>>>(sp);
-        CU(cudaGetLastError());
-    } else if (pl.warp_ns == 2) {
-        scan_warp_kernel<8, 2><<<pl.warp_grid, 32 * WARPS_PER_CTA, pl.smem, st>>>(sp);
-        CU(cudaGetLastError());
-    } else if (pl.T == 1) CHECK(launch_scan<1>(sp, n_tiles, pl.smem, st));
-    else if (pl.T == 2) CHECK(launch_scan<2>(sp, n_tiles, pl.smem, st));
-    else if (pl.T == 4) CHECK(launch_scan<4>(sp, n_tiles, pl.smem, st));
-    else if (pl.T == 8) CHECK(launch_scan<8>(sp, n_tiles, pl.smem, st));
-    else CHECK(launch_scan<16>(sp, n_tiles, pl.smem, st));
-    CU(cudaEventRecord(s->ev[2], st));
-    tile_offsets_kernel<<<1, 1024, 0, st>>>(s->tile_cnt, s->tile_off, n_tiles, s->d_counters);
-    spill_sort_small_kernel<<<1, 1024, 0, st>>>(s->spill_key, s->spill_k, s->res_cap, s->d_counters);
-    GatherParams &g = pl.g;
+    GatherParams &g = L.g;
     g.stage_key = s->stage_key; g.stage_k = s->stage_k;
     g.tile_cnt = s->tile_cnt; g.tile_base = s->tile_base; g.tile_off = s->tile_off;
     g.spill_key = s->spill_key; g.spill_k = s->spill_k;
     g.fin_key = s->fin_key; g.fin_k = s->fin_k;
     g.n_tiles = n_tiles; g.fin_cap = s->res_cap; g.stage_cap = s->res_cap; g.spill_cap = s->res_cap;
-    g.tile_words = pl.warp_ns ? 32u * pl.T * pl.warp_ns : (uint32_t)THREADS * pl.T; g.spill_sorted = 0;
+    g.tile_words = pl.warp_ns ? 32u * pl.T * pl.warp_ns : (uint32_t)THREADS * pl.T * pl.block_ns; g.spill_sorted = 0;
     g.counters = s->d_counters;
     pl.ggrid = (n_tiles * 32 + 255) / 256;
-    gather_kernel<<<pl.ggrid, 256, 0, st>>>(g);
-    pl.launches += 4;
-    if (pl.single_copy) {
-        single_copy_filter_kernel<<<1, 1024, 0, st>>>(s->fin_key, s->fin_k, s->NM, s->X, s->n_words_alloc, s->res_cap,
-                                                      s->d_counters);
-        ++pl.launches;
-    }
     pl.tgrid = std::min<uint32_t>(148 * 8, (s->res_cap + 255) / 256);
-    TranslateParams &tp = pl.tp;
+    TranslateParams &tp = L.tp;
     tp.fin_key = s->fin_key; tp.fin_k = s->fin_k; tp.rec_dev_off = s->d_rec_dev_off; tp.rec_len = s->d_rec_len;
     tp.map_rec = s->d_map_rec; tp.map_shift = s->d_map_shift; tp.map_open = s->d_map_open;
     tp.n_records = s->n_records; tp.fin_cap = s->res_cap; tp.counters = s->d_counters;
     tp.o_rec = s->o_rec; tp.o_start = s->o_start; tp.o_end = s->o_end; tp.o_k = s->o_k;
-    CHECK(launch_translate(s, pl, st));
-    CU(cudaEventRecord(s->ev[3], st));
-    return CRF_OK;
+    tp.open_rows = s->d_open_rows; tp.open_cap = s->open_cap;
+    pl.g = g;
+    pl.tp = tp;
+    L.T = (uint32_t)pl.T; L.warp_ns = (uint32_t)pl.warp_ns; L.block_ns = (uint32_t)pl.block_ns; L.warp_grid = pl.warp_grid;
+    L.n_tiles = n_tiles; L.ggrid = pl.ggrid; L.tgrid = pl.tgrid; L.single_copy = pl.single_copy ? 1u : 0u;
+    L.smem = pl.smem; L.tile_off = s->tile_off; L.n_words_alloc = s->n_words_alloc; L.res_cap = s->res_cap;
+
+    if (s->side_done) {            // the previous push of this sequence's rows (on the exchange's own stream) comes first
+        CU(cudaStreamWaitEvent(st, s->side_done, 0));
+        s->side_done = nullptr;
+    }
+    static const bool graphs_off = getenv("CRF_NO_GRAPH") != nullptr;
+    // (not on a rank of a multi-GPU job: instantiating a graph may wait for kernels that are themselves waiting for peers)
+    if (allow_graph && s->ctx->n_xchg == 0 && n_tiles <= GRAPH_MAX_TILES && !graphs_off) {
+        if (!s->graph_exec || !s->graph_key || memcmp(s->graph_key, &L, sizeof(L)) != 0) {
+            if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+            if (!s->graph_key) s->graph_key = new (std::nothrow) ScanLaunch;
+            if (!s->graph_key) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = scan_launch_all(s, L, st, cudaEventRecordExternal, &s->graph_launches);
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { s->graph_exec = nullptr; set_err("crf_scan: graph capture failed: %s", cudaGetErrorString(e)); return CRF_ERR_CUDA; }
+            memcpy(s->graph_key, &L, sizeof(L));
+        }
+        CU(cudaGraphLaunch(s->graph_exec, st));
+        pl.launches = s->graph_launches;
+        return CRF_OK;
+    }
+    return scan_launch_all(s, L, st, cudaEventRecordDefault, &pl.launches);
 }
 
 // after the counters of a completed scan are on the host
@@ -1202,6 +1264,7 @@ extern "C" int crf_xchg_create(crf_ctx *c, uint32_t rank, uint32_t world, uint64
     memset(x->h_ring, 0, (size_t)XCHG_RING * XCHG_RESULT_WORDS * 8);
     x->peer_base[rank] = x->base;
     x->connected[rank] = true;
+    ++c->n_xchg;
     *out = x;
     return CRF_OK;
 }
@@ -1263,6 +1326,7 @@ extern "C" int crf_xchg_destroy(crf_xchg *x) {
         if (x->peer_ipc[r] && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
     if (x->base) cudaFree(x->base);
     if (x->h_ring) cudaFreeHost(x->h_ring);
+    --x->ctx->n_xchg;
     delete x;
     return CRF_OK;
 }
@@ -1324,7 +1388,7 @@ extern "C" int crf_scan_gather(crf_seq *s, const crf_scan_params *pr, crf_xchg *
     if (!s->plan) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
     CHECK(scan_prepare(s, pr, *s->plan));
     CHECK(ensure_result_buffers(s, default_result_cap(s, pr)));
-    CHECK(scan_enqueue(s, *s->plan));
+    CHECK(scan_enqueue(s, *s->plan, false));      // (no graph: instantiating one may wait for kernels that wait for peers)
     CU(cudaMemcpyAsync(s->h_counters, s->d_counters, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CHECK(xchg_enqueue(s, x, false, append != 0));
     if (std::find(x->pending.begin(), x->pending.end(), s) == x->pending.end()) x->pending.push_back(s);
@@ -1440,6 +1504,7 @@ extern "C" int crf_xchg_patch_end(crf_xchg *x, const uint64_t *rows, const uint3
 
 static cudaError_t preload_kernels() {
     cudaError_t e = preload(scan_kernel<1>);
+    if (e == cudaSuccess) e = preload(scan_kernel<8, 2>);
     if (e == cudaSuccess) e = preload(scan_warp_kernel<8, 1>);
     if (e == cudaSuccess) e = preload(scan_warp_kernel<8, 2>);
     if (e == cudaSuccess) e = preload(scan_kernel<2>);

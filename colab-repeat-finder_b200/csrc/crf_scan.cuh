@@ -294,33 +294,38 @@ __device__ __forceinline__ bool filter_erode(const uint32_t (&NH)[T + 1], const 
     return all != 0xFFFFFFFFu;
 }
 
-// dynamic shared memory a scan block needs
-__host__ __device__ inline uint32_t scan_tile_words(int T, uint32_t kmax) {
-    return (uint32_t)THREADS * T + (kmax >> 5) + 5;  // 1 word of left context + tile + halo (q+4)
+// dynamic shared memory a scan block needs (NS = strips per thread: the tile is THREADS * T * NS words)
+__host__ __device__ inline uint32_t scan_tile_words(int T, uint32_t kmax, int NS = 1) {
+    return (uint32_t)THREADS * T * NS + (kmax >> 5) + 5;  // 1 word of left context + tile + halo (q+4)
 }
-__host__ __device__ inline size_t scan_smem_bytes(int T, uint32_t kmax, uint32_t outcap) {
-    const size_t plane = pad_idx(scan_tile_words(T, kmax)) + 1;
-    size_t words = 3 * plane + (NBATCH + 1) * THREADS + 16 + 3 * LONGCAP;
+__host__ __device__ inline size_t scan_smem_bytes(int T, uint32_t kmax, uint32_t outcap, int NS = 1) {
+    const size_t plane = pad_idx(scan_tile_words(T, kmax, NS)) + 1;
+    size_t words = 3 * plane + (NBATCH + 1) * THREADS * NS + 32 + 3 * LONGCAP;
     words = (words + 1) & ~(size_t)1;
     return words * 4 + (size_t)STARTQ_CAP * 8 + (size_t)outcap * 8 + (((size_t)outcap * 2 + 7) & ~(size_t)7);
 }
 
-template <int T>
-__global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
-    constexpr int TW = THREADS * T;
+// NS strips per thread: with NS = 2 a tile holds twice the (strip, k) hits, so the exact phase runs in ~3 rounds of which
+// only the last is partly filled -- the warps that have no item in the last round wait 1/3 as long at the barrier that
+// closes the phase as with NS = 1 (2 rounds, the second ~40 % filled); registers are unchanged (the strips of a thread are
+// processed one after the other), shared memory grows by the second set of plane words.
+template <int T, int NS = 1>
+__global__ void __launch_bounds__(THREADS, (T <= 8 && NS == 1) ? 4 : (T <= 8 ? 3 : 1)) scan_kernel(const ScanParams p) {
+    constexpr int TW = THREADS * T * NS;
+    constexpr uint32_t STRIPS = THREADS * NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nsm = scan_tile_words(T, p.kmax);
+    const uint32_t nsm = scan_tile_words(T, p.kmax, NS);
     const uint32_t plane = pad_idx(nsm) + 1;
 
     uint32_t *sH = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *sL = sH + plane;
     uint32_t *sN = sL + plane;
-    uint32_t *s_hit = sN + plane;               // NBATCH x THREADS hit masks (later: strip histogram)
-    uint32_t *s_pre = s_hit + NBATCH * THREADS;
-    uint32_t *s_misc = s_pre + THREADS;  // [0..7] warp sums [8] nout [9] nlong [10] nstart/minpos [11] base [12..15] q
-    uint32_t *s_long = s_misc + 16;
-    size_t off_words = 3 * (size_t)plane + (NBATCH + 1) * THREADS + 16 + 3 * LONGCAP;
+    uint32_t *s_hit = sN + plane;               // NBATCH x STRIPS hit masks (later: strip histogram)
+    uint32_t *s_pre = s_hit + NBATCH * STRIPS;
+    uint32_t *s_misc = s_pre + STRIPS;  // [0..7] warp sums [8] nout [9] nlong [10] nstart/minpos [11] base [12..15] q [16..23] warp sums (2nd strip set)
+    uint32_t *s_long = s_misc + 32;
+    size_t off_words = 3 * (size_t)plane + (NBATCH + 1) * STRIPS + 32 + 3 * LONGCAP;
     off_words = (off_words + 1) & ~(size_t)1;
     uint2 *s_startq = reinterpret_cast<uint2 *>(smem_raw + off_words * 4);
     uint64_t *s_key = reinterpret_cast<uint64_t *>(s_startq + STARTQ_CAP);
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
         sN[a] = nmw;
         any_mask |= nmw;
     }
-    if (tid < 16) s_misc[tid] = 0;
+    if (tid < 32) s_misc[tid] = 0;
     const bool tile_has_n = __syncthreads_or(any_mask != 0);  // masked positions anywhere in the staged words
 
     TileCtx tc;
@@ -349,33 +354,36 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
     tc.startq = s_startq; tc.nstart = &s_misc[10];
     tc.longcap = LONGCAP; tc.startcap = STARTQ_CAP;
 
-    uint32_t NH[T + 1], NL[T + 1];
-#pragma unroll
-    for (int i = 0; i <= T; ++i) {
-        NH[i] = sH[pad_idx(1 + tid * T + i)];
-        NL[i] = sL[pad_idx(1 + tid * T + i)];
-    }
-
     unsigned long long ncand = 0;
     uint32_t si = 0;
     while (si < p.n_segs) {
-        // ---- fast phase: up to NBATCH groups of <= 32 motif sizes (one group per k >> 5)
+        // ---- fast phase: up to NBATCH groups of <= 32 motif sizes (one group per k >> 5), every strip of this thread
+        const uint32_t si0 = si;
         uint32_t nb = 0;
-        uint32_t cnt = 0;
-        for (; nb < NBATCH && si < p.n_segs; ++nb) {
+#pragma unroll 1
+        for (int sub = 0; sub < NS; ++sub) {
+        const uint32_t sbase = 1 + (sub * THREADS + tid) * T;   // smem index of the strip's first word
+        uint32_t NH[T + 1], NL[T + 1];
+#pragma unroll
+        for (int i = 0; i <= T; ++i) {
+            NH[i] = sH[pad_idx(sbase + i)];
+            NL[i] = sL[pad_idx(sbase + i)];
+        }
+        si = si0;
+        for (nb = 0; nb < NBATCH && si < p.n_segs; ++nb) {
             const uint32_t qb = (uint32_t)p.segs[si].k_lo >> 5;
             uint32_t FH[T + 2], FL[T + 2];
 #pragma unroll
             for (int i = 0; i <= T + 1; ++i) {
-                FH[i] = sH[pad_idx(1 + tid * T + qb + i)];
-                FL[i] = sL[pad_idx(1 + tid * T + qb + i)];
+                FH[i] = sH[pad_idx(sbase + qb + i)];
+                FL[i] = sL[pad_idx(sbase + qb + i)];
             }
             // homopolymer mask for this strip (only k <= 16, i.e. the first group): HD bit j = some mismatch of
             // M'_1 in [j, j+8): ~HD = nine equal bases from j on; the word after the window is filled with mismatches
             uint32_t HD[T + 2];
             uint32_t hd_level = 0;
             if (qb == 0 && p.sup_enabled) {
-                const uint32_t hx = sH[pad_idx(1 + tid * T + T + 2)], lx = sL[pad_idx(1 + tid * T + T + 2)];
+                const uint32_t hx = sH[pad_idx(sbase + T + 2)], lx = sL[pad_idx(sbase + T + 2)];
 #pragma unroll
                 for (int i = 0; i <= T; ++i)
                     HD[i] = (FH[i] ^ __funnelshift_r(FH[i], FH[i + 1], 1)) | (FL[i] ^ __funnelshift_r(FL[i], FL[i + 1], 1));
@@ -457,42 +465,55 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
                     }
                 }
             }
-            s_hit[nb * THREADS + tid] = hitmask;
+            s_hit[nb * STRIPS + sub * THREADS + tid] = hitmask;
             if (tid == 0) s_misc[12 + nb] = qb;
-            cnt += __popc(hitmask);
+        }
         }
 
         // ---- exact phase over the hits of these groups: compact (prefix sum, no atomics) ...
-        uint32_t incl = cnt;
+        uint32_t cnt[NS], incl[NS];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= (uint32_t)o) incl += v;
+        for (int sub = 0; sub < NS; ++sub) {
+            uint32_t c = 0;                       // hits of my strip `sub` (my own stores, read back)
+            for (uint32_t b = 0; b < nb; ++b) c += __popc(s_hit[b * STRIPS + sub * THREADS + tid]);
+            cnt[sub] = c;
+            uint32_t in = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, in, o);
+                if (lane >= (uint32_t)o) in += v;
+            }
+            incl[sub] = in;
+            if (lane == 31) s_misc[16 * sub + warp] = in;
         }
-        if (lane == 31) s_misc[warp] = incl;
         if (tid == 0) s_misc[10] = 0;  // start-queue fill
         __syncthreads();
-        uint32_t woff = 0, total = 0;
+        uint32_t total = 0;
 #pragma unroll
-        for (uint32_t i = 0; i < THREADS / 32; ++i) {
-            const uint32_t v = s_misc[i];
-            if (i < warp) woff += v;
-            total += v;
+        for (int sub = 0; sub < NS; ++sub) {
+            uint32_t woff = 0, tsub = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < THREADS / 32; ++i) {
+                const uint32_t v = s_misc[16 * sub + i];
+                if (i < warp) woff += v;
+                tsub += v;
+            }
+            s_pre[sub * THREADS + tid] = total + woff + incl[sub] - cnt[sub];
+            total += tsub;
         }
-        s_pre[tid] = woff + incl - cnt;
         __syncthreads();
         if (tid == 0) ncand += total;
         if (p.debug_flags & 1u) total = 0;  // profiling only: fast phase alone
         // ... one thread per (strip, k) hit: find the run starts, follow each run, emit
         for (uint32_t item = tid; item < total; item += THREADS) {
-            uint32_t lo = 0, hi = THREADS - 1;  // last strip whose exclusive prefix is <= item
+            uint32_t lo = 0, hi = STRIPS - 1;  // last strip whose exclusive prefix is <= item
             while (lo < hi) {
                 const uint32_t mid = (lo + hi + 1) >> 1;
                 if (s_pre[mid] <= item) lo = mid; else hi = mid - 1;
             }
             uint32_t n = item - s_pre[lo], k = 0;
             for (uint32_t b = 0; b < nb; ++b) {
-                const uint32_t mask = s_hit[b * THREADS + lo];
+                const uint32_t mask = s_hit[b * STRIPS + lo];
                 const uint32_t c = __popc(mask);
                 if (n < c) { k = s_misc[12 + b] * 32 + __fns(mask, 0, n + 1); break; }
                 n -= c;
@@ -536,7 +557,8 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
     // ---- order the tile's results by (start, end): counting sort over strips, then each strip's
     //      few results are put in order by one thread; written as one segment of the staging list
     const uint32_t n = min(s_misc[8], p.outcap);
-    s_hit[tid] = 0;
+#pragma unroll
+    for (int sub = 0; sub < NS; ++sub) s_hit[sub * THREADS + tid] = 0;
     if (tid == 0) {
         const unsigned long long base = atomicAdd(p.counters + C_STAGE, (unsigned long long)n);
         s_misc[11] = (base + n <= p.stage_cap) ? (uint32_t)base : NOPOS;
@@ -554,20 +576,33 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
     }
     __syncthreads();
     {
-        const uint32_t c = s_hit[tid];
-        uint32_t incl = c;
+        uint32_t c[NS], in[NS];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= (uint32_t)o) incl += v;
+        for (int sub = 0; sub < NS; ++sub) {
+            c[sub] = s_hit[sub * THREADS + tid];
+            uint32_t v = c[sub];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                if (lane >= (uint32_t)o) v += t;
+            }
+            in[sub] = v;
+            if (lane == 31) s_misc[16 * sub + warp] = v;
         }
-        if (lane == 31) s_misc[warp] = incl;
         __syncthreads();
-        uint32_t woff = 0;
+        uint32_t run = 0;
 #pragma unroll
-        for (uint32_t i = 0; i < THREADS / 32; ++i)
-            if (i < warp) woff += s_misc[i];
-        s_pre[tid] = woff + incl - c;  // cursor: start of this strip's slots
+        for (int sub = 0; sub < NS; ++sub) {
+            uint32_t woff = 0, tsub = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < THREADS / 32; ++i) {
+                const uint32_t v = s_misc[16 * sub + i];
+                if (i < warp) woff += v;
+                tsub += v;
+            }
+            s_pre[sub * THREADS + tid] = run + woff + in[sub] - c[sub];  // cursor: start of this strip's slots
+            run += tsub;
+        }
     }
     __syncthreads();
     for (uint32_t i = tid; i < n; i += THREADS) {
@@ -578,10 +613,11 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams p) {
         p.stage_k[base + pos] = s_k[i];
     }
     __syncthreads();  // block-wide visibility of the staged rows
-    {
-        const uint32_t c = s_hit[tid];
+#pragma unroll 1
+    for (int sub = 0; sub < NS; ++sub) {
+        const uint32_t c = s_hit[sub * THREADS + tid];
         if (c > 1) {  // insertion sort of this strip's rows (in place, by (key, k))
-            const uint32_t first = base + s_pre[tid] - c;
+            const uint32_t first = base + s_pre[sub * THREADS + tid] - c;
             for (uint32_t a = 1; a < c; ++a) {
                 const uint64_t key = p.stage_key[first + a];
                 const uint16_t kk = p.stage_k[first + a];

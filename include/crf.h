@@ -125,6 +125,7 @@ int crf_seq_info(const crf_seq *seq, crf_seq_info_t *info);
  * block-wide barrier (csrc/crf_scan_warp.cuh), or tiles owned by 256-thread blocks (csrc/crf_scan.cuh) */
 #define CRF_SCAN_WARP_TILES 2u
 #define CRF_SCAN_BLOCK_TILES 4u
+#define CRF_SCAN_TWO_STRIPS 8u   /* block tiles with two strips per thread (131 kbp tiles) */
 /* bits 16..31: profiling switches (results are NOT valid when set): 1<<16 = fast phase only */
 #define CRF_SCAN_DEBUG_FAST_ONLY (1u << 16)
 #define CRF_SCAN_DEBUG_NO_SUP (1u << 17)   /* tuning: no homopolymer suppression in the filters (results stay valid) */

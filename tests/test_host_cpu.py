@@ -336,7 +336,7 @@ def test_cli_groups_records_by_layout_positions_not_bases():
 
 def test_tracker_module_compat():
     """utils.perfect_repeat_tracker stays importable: the string helper answers like the reference's (vectors generated
-    from trk:108-142 by tests/golden/make_golden.py, also used by api._is_primitive), the CPU tracker class refuses."""
+    from trk:108-142 by tests/golden/make_golden.py, also used by api._is_primitive), the tracker class keeps the reference's constructor (its scan is covered by the -m gpu tests)."""
     from crf_b200 import api
     from tests.helpers import load_golden
     from utils.perfect_repeat_tracker import PerfectRepeatTracker, consists_of_perfect_repeats
@@ -346,7 +346,9 @@ def test_tracker_module_compat():
         assert consists_of_perfect_repeats(c["seq"]) == c["unit"], c
         assert api._is_primitive(c["seq"].encode()) == (c["unit"] is None), c
     with pytest.raises(NotImplementedError, match="detect_repeats"):
-        PerfectRepeatTracker(3, 3, 9, "ACGT", {})
+        PerfectRepeatTracker(3, 1, 9, "ACGT", {})           # the single-copy corner is detect_repeats()'s
+    t = PerfectRepeatTracker(3, 3, 9, "ACGT", {})            # (the GPU scan behind it only runs on first use)
+    assert t.current_position == 0 and t.motif_size == 3
 
 
 # ---- interval mode: the host half (N-trim, probe scan -> stop position, cut, selection, AssertionError / IndexError) with

@@ -103,3 +103,41 @@ def test_gpu_equals_python_reference_live_fuzz():
         else:
             n_rows += len(want)
     assert n_rows > 1000
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_tracker_compat_class_replays_the_reference_tracker():
+    """utils.perfect_repeat_tracker.PerfectRepeatTracker (GPU-backed facade) driven in lock-step exactly as the reference's
+    detect_repeats drives its trackers (prf:51-79), against the reference's own class doing the same: same dict, same
+    is_in_middle_of_repeat() at every position, same current_position; done() called mid-sequence too."""
+    import importlib
+    ref_prf, _ = ref.load()
+    RefTracker = ref_prf.PerfectRepeatTracker
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    mine = importlib.import_module("utils.perfect_repeat_tracker")
+    assert os.path.dirname(os.path.dirname(os.path.abspath(mine.__file__))) == ROOT
+    rng = random.Random(5)
+    checked = 0
+    for it in range(40):
+        seq = random_seq(rng, rng.choice([50, 400, 3000]), exotic=rng.random() < 0.3)
+        if rng.random() < 0.5:
+            seq = seq.upper()
+        mr, ms = rng.choice([2, 3, 3, 4]), rng.choice([1, 6, 9, 20])
+        ks = sorted(rng.sample(range(1, 30), 4))
+        out_ref, out_mine = {}, {}
+        a = [RefTracker(k, mr, ms, seq, out_ref) for k in ks]
+        b = [mine.PerfectRepeatTracker(k, mr, ms, seq, out_mine) for k in ks]
+        stop = rng.randint(0, len(seq)) if rng.random() < 0.4 else len(seq)
+        for _pos in range(stop):
+            for x, y in zip(a, b):
+                assert x.advance() == y.advance()
+                assert x.is_in_middle_of_repeat() == y.is_in_middle_of_repeat()
+                assert x.current_position == y.current_position
+        for x, y in zip(a, b):
+            x.done()
+            y.done()
+        assert out_mine == out_ref, (seq, ks, mr, ms, stop)
+        checked += len(out_ref)
+    assert checked > 100
