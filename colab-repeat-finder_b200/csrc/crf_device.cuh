@@ -84,34 +84,43 @@ __device__ __forceinline__ uint32_t plane_at(const uint32_t *__restrict__ P, uin
 }
 
 // letter of the exotic symbol at layout position pos (0 if none)
-__device__ inline uint32_t exotic_letter(const ScanParams &p, uint32_t pos) {
-    uint32_t lo = 0, hi = p.n_exotic;
+__device__ inline uint32_t exotic_letter(const uint64_t *__restrict__ ex_key, uint32_t n_exotic, uint32_t pos) {
+    uint32_t lo = 0, hi = n_exotic;
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
-        if ((uint32_t)(p.ex_key[mid] >> 8) < pos) lo = mid + 1; else hi = mid;
+        if ((uint32_t)(ex_key[mid] >> 8) < pos) lo = mid + 1; else hi = mid;
     }
-    if (lo < p.n_exotic && (uint32_t)(p.ex_key[lo] >> 8) == pos) return (uint32_t)(p.ex_key[lo] & 0xFF);
+    if (lo < n_exotic && (uint32_t)(ex_key[lo] >> 8) == pos) return (uint32_t)(ex_key[lo] & 0xFF);
     return 0;
 }
 
-// Exact M_k for the 32 positions of word w.
-__device__ inline uint32_t exact_mask(const ScanParams &p, uint32_t k, uint32_t w) {
+// Exact M_k for the 32 positions of word w, from global memory.  Out of line on purpose (plain arguments, so that the
+// kernel's parameter block need not be copied to local memory): the scan kernel reaches it only where a run leaves the
+// staged tile or the load has exotic symbols, but it is referenced from every walk / primitivity site of the exact phase --
+// inlined, its copies (exotic look-up included) were 40 % of the kernel's code, and the kernel is sensitive to its
+// instruction footprint (profiles/r02_kernel_iterations.md).
+__device__ __noinline__ uint32_t exact_mask_global(const uint32_t *__restrict__ H, const uint32_t *__restrict__ L,
+                                                   const uint32_t *__restrict__ NM, const uint32_t *__restrict__ X,
+                                                   const uint64_t *__restrict__ ex_key, uint32_t n_exotic, uint32_t k, uint32_t w) {
     const uint32_t q = k >> 5, s = k & 31;
-    const uint32_t dh = __ldg(p.H + w) ^ plane_at(p.H, w, q, s);
-    const uint32_t dl = __ldg(p.L + w) ^ plane_at(p.L, w, q, s);
-    const uint32_t nm = __ldg(p.NM + w) | plane_at(p.NM, w, q, s);
+    const uint32_t dh = __ldg(H + w) ^ plane_at(H, w, q, s);
+    const uint32_t dl = __ldg(L + w) ^ plane_at(L, w, q, s);
+    const uint32_t nm = __ldg(NM + w) | plane_at(NM, w, q, s);
     const uint32_t eq = ~(dh | dl);
     uint32_t m = eq & ~nm;
-    if (p.n_exotic) {  // equal exotic letters match too (only "N" is special, trk:53)
-        uint32_t x = __ldg(p.X + w) & plane_at(p.X, w, q, s) & eq;
+    if (n_exotic) {  // equal exotic letters match too (only "N" is special, trk:53)
+        uint32_t x = __ldg(X + w) & plane_at(X, w, q, s) & eq;
         while (x) {
             const uint32_t b = __ffs(x) - 1;
             x &= x - 1;
             const uint32_t pos = (w << 5) + b;
-            if (exotic_letter(p, pos) == exotic_letter(p, pos + k)) m |= 1u << b;
+            if (exotic_letter(ex_key, n_exotic, pos) == exotic_letter(ex_key, n_exotic, pos + k)) m |= 1u << b;
         }
     }
     return m;
+}
+__device__ __forceinline__ uint32_t exact_mask(const ScanParams &p, uint32_t k, uint32_t w) {
+    return exact_mask_global(p.H, p.L, p.NM, p.X, p.ex_key, p.n_exotic, k, w);
 }
 
 // First position >= from with M_k == 0, looking at no more than `limit` further words.

@@ -112,25 +112,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, NS == 1 ? 8 : 6) scan_warp
                         FH[i] = sH[pad_idx(sbase + qb + i)];
                         FL[i] = sL[pad_idx(sbase + qb + i)];
                     }
+                    // HD: all ones = no suppression.  It becomes the homopolymer mask when the first segment that wants one comes up
+                    // (2 <= k <= 16 of the ERODE / BYTE filters) and goes back to all ones for a later segment without suppression.
                     uint32_t HD[T + 2];
                     uint32_t hd_level = 0;
-                    if (qb == 0 && p.sup_enabled) {                   // homopolymer mask, see scan_kernel
-                        const uint32_t hx = sH[pad_idx(sbase + T + 2)], lx = sL[pad_idx(sbase + T + 2)];
 #pragma unroll
-                        for (int i = 0; i <= T; ++i)
-                            HD[i] = (FH[i] ^ __funnelshift_r(FH[i], FH[i + 1], 1)) | (FL[i] ^ __funnelshift_r(FL[i], FL[i + 1], 1));
-                        HD[T + 1] = (FH[T + 1] ^ __funnelshift_r(FH[T + 1], hx, 1)) | (FL[T + 1] ^ __funnelshift_r(FL[T + 1], lx, 1));
-#pragma unroll
-                        for (int sh = 1; sh <= 4; sh <<= 1) {
-#pragma unroll
-                            for (int i = 0; i <= T; ++i) HD[i] |= __funnelshift_r(HD[i], HD[i + 1], sh);
-                            HD[T + 1] |= __funnelshift_r(HD[T + 1], 0xFFFFFFFFu, sh);
-                        }
-                        hd_level = 1;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i <= T + 1; ++i) HD[i] = 0xFFFFFFFFu;
-                    }
+                    for (int i = 0; i <= T + 1; ++i) HD[i] = 0xFFFFFFFFu;
                     uint32_t hitmask = 0;
                     for (; si < p.n_segs; ++si) {
                         const Seg sg = p.segs[si];
@@ -144,56 +131,44 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, NS == 1 ? 8 : 6) scan_warp
 #pragma unroll 1
                             for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1) set_bit_if(hitmask, filter_half<T>(NH, FH, s), bit);
                         } else {
-                            const uint32_t sup = sg.mode >> 4;
-                            if (sup == 2 && hd_level == 1) {
+                            const uint32_t sup = (sg.mode >> 4) & 3u;  // 0: none, 1: stretches of > 8 equal bases, 2: > 16
+                            if (sup && hd_level == 0) {          // HD bit j = some mismatch of M'_1 in [j, j+8): ~HD = nine equal bases from j on;
+                                const uint32_t hx = sH[pad_idx(sbase + T + 2)], lx = sL[pad_idx(sbase + T + 2)];   // (only k <= 16: group 0, FH = the strip itself)
+#pragma unroll
+                                for (int i = 0; i <= T; ++i)
+                                    HD[i] = (FH[i] ^ __funnelshift_r(FH[i], FH[i + 1], 1)) | (FL[i] ^ __funnelshift_r(FL[i], FL[i + 1], 1));
+                                HD[T + 1] = (FH[T + 1] ^ __funnelshift_r(FH[T + 1], hx, 1)) | (FL[T + 1] ^ __funnelshift_r(FL[T + 1], lx, 1));
+#pragma unroll
+                                for (int sh = 1; sh <= 4; sh <<= 1) {
+#pragma unroll
+                                    for (int i = 0; i <= T; ++i) HD[i] |= __funnelshift_r(HD[i], HD[i + 1], sh);
+                                    HD[T + 1] |= __funnelshift_r(HD[T + 1], 0xFFFFFFFFu, sh);
+                                }
+                                hd_level = 1;
+                            }
+                            if (sup == 2 && hd_level == 1) {    // widen the homopolymer mask from 8 to 16 matches
 #pragma unroll
                                 for (int i = 0; i <= T; ++i) HD[i] |= __funnelshift_r(HD[i], HD[i + 1], 8);
                                 HD[T + 1] |= __funnelshift_r(HD[T + 1], 0xFFFFFFFFu, 8);
                                 hd_level = 2;
                             }
+                            if (sup == 0 && hd_level != 0) {    // (only with unusual filter settings: a BYTE / ERODE segment beyond k = 16)
+#pragma unroll
+                                for (int i = 0; i <= T + 1; ++i) HD[i] = 0xFFFFFFFFu;
+                                hd_level = 0;
+                            }
                             const uint32_t mode = sg.mode & 15u;
-                            if (sup) {
-                                if (mode == MODE_BYTE) {
-#pragma unroll 1
-                                    for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                        set_bit_if(hitmask, filter_byte<T, true>(NH, NL, FH, FL, s, HD), bit);
-                                } else if (sh2) {
-#pragma unroll 1
-                                    for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                        set_bit_if(hitmask, filter_erode<T, 3, true>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD), bit);
-                                } else if (sh1) {
-#pragma unroll 1
-                                    for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                        set_bit_if(hitmask, filter_erode<T, 2, true>(NH, NL, FH, FL, s, sh0, sh1, 0, HD), bit);
-                                } else if (sh0) {
-#pragma unroll 1
-                                    for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                        set_bit_if(hitmask, filter_erode<T, 1, true>(NH, NL, FH, FL, s, sh0, 0, 0, HD), bit);
-                                } else {
-#pragma unroll 1
-                                    for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                        set_bit_if(hitmask, filter_erode<T, 0, true>(NH, NL, FH, FL, s, 0, 0, 0, HD), bit);
-                                }
-                            } else if (mode == MODE_BYTE) {
+                            // (one loop per filter: without suppression HD is all ones, which the 3-input LOP3 of the compare absorbs for free, and
+                            // an unused dilation step has shift 0 -- every extra specialisation of these loops costs more in instruction fetch
+                            // than it saves in arithmetic, profiles/r02_kernel_iterations.md)
+                            if (mode == MODE_BYTE) {
 #pragma unroll 1
                                 for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                    set_bit_if(hitmask, filter_byte<T, false>(NH, NL, FH, FL, s, HD), bit);
-                            } else if (sh2) {
-#pragma unroll 1
-                                for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                    set_bit_if(hitmask, filter_erode<T, 3, false>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD), bit);
-                            } else if (sh1) {
-#pragma unroll 1
-                                for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                    set_bit_if(hitmask, filter_erode<T, 2, false>(NH, NL, FH, FL, s, sh0, sh1, 0, HD), bit);
-                            } else if (sh0) {
-#pragma unroll 1
-                                for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                    set_bit_if(hitmask, filter_erode<T, 1, false>(NH, NL, FH, FL, s, sh0, 0, 0, HD), bit);
+                                    set_bit_if(hitmask, filter_byte<T, true>(NH, NL, FH, FL, s, HD), bit);
                             } else {
 #pragma unroll 1
                                 for (uint32_t s = s_lo, bit = 1u << s_lo; s <= s_hi; ++s, bit <<= 1)
-                                    set_bit_if(hitmask, filter_erode<T, 0, false>(NH, NL, FH, FL, s, 0, 0, 0, HD), bit);
+                                    set_bit_if(hitmask, filter_erode<T, 3, true>(NH, NL, FH, FL, s, sh0, sh1, sh2, HD), bit);
                             }
                         }
                     }
