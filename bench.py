@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--words-per-thread", type=int, default=0)
     ap.add_argument("--trace", action="store_true", help="print per-stage device timings of one extra step (stderr)")
+    ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the shares balanced by base pairs")
     ap.add_argument("--phases", type=int, default=1,
                     help="N > 1: phases per step (the rows of one phase travel to rank 0 while the next one is scanned); "
                          "measured slower than one phase on S38 (profiles/r02_scaling_s38.md), kept for larger jobs")
@@ -315,12 +316,16 @@ def main():
     rs = multi.RankScan(ctx, comm, bases.data_ptr(), offsets[:-1], lengths, KMIN, KMAX, MIN_REPEATS, MIN_SPAN,
                         on_device=True, chunk=args_chunk(world), reads=(args.workload == "sr"), knobs=knobs,
                         phases=args.phases)
-    my_bp, n_units = rs.my_bp, rs.n_units
 
     # ---- device-resident timing ----
-    for _ in range(args.warmup):
+    rebalanced = []
+    for i in range(args.warmup):
         rs.step_async()
         rs.finish()
+        if world > 1 and i < 2 and not args.no_rebalance:
+            # shares by measured cost instead of by base pairs (RankScan.rebalance: the slowest rank sets the step); the
+            # remaining warm-up steps size the buffers of the new shares
+            rebalanced.append(round(rs.rebalance(), 4))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -496,6 +501,7 @@ def main():
     alu_peak_tops = ops.value / 1e12
     k_ms = float(np.mean(kernel_ms))
     n_k = KMAX - KMIN + 1
+    my_bp = rs.my_bp
     alg_bytes = (my_bp + 3) // 4 + (my_bp + 7) // 8 + 12 * int(stats.n_results)
     alg_ops = 6 * ((my_bp + 31) // 32) * n_k
     hbm_ach = alg_bytes / (k_ms * 1e-3) / 1e9
@@ -574,7 +580,7 @@ def main():
         "config": bench_config(meta["workload"], total_bp, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-        "results_per_step": int(total_results), "units": n_units,
+        "results_per_step": int(total_results), "units": rs.n_units, "rebalanced_gain": rebalanced,
         "scan_stats": {"scan_ms": float(np.mean(scan_ms)), "kernel_ms": k_ms, "candidates": int(stats.n_candidates),
                        "long_runs": int(stats.n_long), "spilled": int(stats.n_spilled), "tiles": int(stats.n_tiles)},
     }

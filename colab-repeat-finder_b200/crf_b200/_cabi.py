@@ -28,7 +28,7 @@ EXPORTS = [
     "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end", "crf_write_rows",
     "crf_fasta_open", "crf_fasta_info", "crf_fasta_data", "crf_fasta_close",
     "crf_xchg_create", "crf_xchg_destroy", "crf_xchg_export", "crf_xchg_connect_ipc", "crf_xchg_connect_local",
-    "crf_xchg_set_timeout", "crf_scan_gather", "crf_xchg_push", "crf_xchg_wait", "crf_xchg_step_result", "crf_xchg_fetch",
+    "crf_xchg_set_timeout", "crf_xchg_set_compact", "crf_scan_gather", "crf_xchg_push", "crf_xchg_wait", "crf_xchg_step_result", "crf_xchg_fetch",
     "crf_xchg_patch_end",
 ]
 
@@ -116,6 +116,7 @@ def lib():
         L.crf_xchg_connect_ipc.argtypes = [vp, u32, vp]
         L.crf_xchg_connect_local.argtypes = [vp, u32, vp]
         L.crf_xchg_set_timeout.argtypes = [vp, ctypes.c_double]
+        L.crf_xchg_set_compact.argtypes = [vp, i]
         L.crf_scan_gather.argtypes = [vp, P(ScanParams), vp, i]
         L.crf_xchg_push.argtypes = [vp, vp, i]
         L.crf_xchg_wait.argtypes = [vp, P(XchgResult)]
@@ -449,6 +450,9 @@ class Xchg:
 
     def set_timeout(self, seconds):
         _check(lib().crf_xchg_set_timeout(self._h, float(seconds)))
+
+    def set_compact(self, on=True):
+        _check(lib().crf_xchg_set_compact(self._h, int(bool(on))))
 
     def wait(self):
         res = XchgResult()

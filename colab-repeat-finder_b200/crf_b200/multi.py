@@ -94,7 +94,39 @@ class RankScan:
         lengths = [int(x) for x in lengths]
         self.total_bp = int(sum(lengths))
         self.reads = reads
-        self.phases = P = max(1, int(phases)) if self.world > 1 else 1
+        self.phases = max(1, int(phases)) if self.world > 1 else 1
+        self._lengths, self._record_starts = lengths, record_starts
+        self._plan_args = dict(chunk=chunk, halo=halo, kmax=kmax, min_repeats=min_repeats, min_span=min_span)
+        self._source = (bases, on_device, base_offset)
+        self.seqs = [None] * self.phases
+        self._make_shares(None)
+        self.reload(bases, on_device=on_device, base_offset=base_offset)
+        self.xchg = None
+        if self.world > 1:
+            self.xchg = _cabi.Xchg(ctx, self.rank, self.world, row_cap or default_row_cap(self.total_bp))
+            if timeout_s:
+                self.xchg.set_timeout(timeout_s)
+            if len(lengths) < 65536 and kmax < 65536:  # 12-byte rows over NVLink (record and motif size share a word)
+                self.xchg.set_compact(True)
+            if comm.same_process:
+                peers = comm.allgather_obj(self.xchg)
+                for r, other in enumerate(peers):
+                    if r != self.rank:
+                        self.xchg.connect_local(r, other)
+                comm.allgather_obj(None)               # every rank is connected before anyone pushes
+            else:
+                handles = comm.allgather_obj(self.xchg.export())
+                for r, h in enumerate(handles):
+                    if r != self.rank:
+                        self.xchg.connect_ipc(r, h)
+                comm.allgather_obj(None)
+        self.last = None
+        self.steps_repeated = 0
+
+    def _make_shares(self, density):
+        """Units and load arguments of this rank (all phases) for a cost density over the genome (None: by base pairs)."""
+        lengths, record_starts, reads = self._lengths, self._record_starts, self.reads
+        P = self.phases
         shares = P * self.world                       # "virtual ranks": share v = phase v // N of rank v % N
         self.load_args, self.units = [], []
         if reads:
@@ -111,9 +143,8 @@ class RankScan:
             self.my_bp = int(sum(int(a[1].sum()) for a in self.load_args))
             self.n_units = n_rec
         else:
-            whole = self.world == 1 and chunk >= max(lengths + [1])
-            self.plan = partition.Plan(lengths, shares, chunk=chunk, halo=halo, kmax=kmax, min_repeats=min_repeats,
-                                       min_span=min_span)
+            whole = self.world == 1 and self._plan_args["chunk"] >= max(lengths + [1])
+            self.plan = partition.Plan(lengths, shares, density=density, **self._plan_args)
             for p in range(P):
                 v = p * self.world + self.rank
                 starts, lens, own_lo, own_hi = self.plan.load_args(v, record_starts)
@@ -123,27 +154,28 @@ class RankScan:
                 self.units.append(self.plan.units_of(v))
             self.my_bp = int(sum(u.u1 - u.u0 for us in self.units for u in us))
             self.n_units = len(self.plan.units)
-        self.seqs = [None] * P
+
+    def rebalance(self, min_gain=0.02):
+        """Re-cut the shares by MEASURED cost: every rank reports the scan time of its last step and its range of the genome;
+        the new share boundaries equalise the time (cost per base pair taken as constant inside each old share) and this
+        rank's sequences are loaded again.  All ranks must call it together; returns the expected relative gain (0.0 when
+        the shares were left alone because less than `min_gain` was to be had)."""
+        if self.world == 1 or self.reads or self.phases != 1 or self.plan is None:
+            return 0.0
+        t = float(self.stats().get("scan_ms", 0.0))
+        lo, hi = self.plan.share_range(self.rank)
+        info = self.comm.allgather_obj((t, lo, hi))
+        times = [x[0] for x in info]
+        if min(times) <= 0 or any(x[2] <= x[1] for x in info):
+            return 0.0
+        gain = 1.0 - (sum(times) / len(times)) / max(times)
+        if gain < min_gain:
+            return 0.0
+        density = [(l, h, tt / (h - l)) for tt, l, h in info]
+        self._make_shares(density)
+        bases, on_device, base_offset = self._source
         self.reload(bases, on_device=on_device, base_offset=base_offset)
-        self.xchg = None
-        if self.world > 1:
-            self.xchg = _cabi.Xchg(ctx, self.rank, self.world, row_cap or default_row_cap(self.total_bp))
-            if timeout_s:
-                self.xchg.set_timeout(timeout_s)
-            if comm.same_process:
-                peers = comm.allgather_obj(self.xchg)
-                for r, other in enumerate(peers):
-                    if r != self.rank:
-                        self.xchg.connect_local(r, other)
-                comm.allgather_obj(None)               # every rank is connected before anyone pushes
-            else:
-                handles = comm.allgather_obj(self.xchg.export())
-                for r, h in enumerate(handles):
-                    if r != self.rank:
-                        self.xchg.connect_ipc(r, h)
-                comm.allgather_obj(None)
-        self.last = None
-        self.steps_repeated = 0
+        return gain
 
     @property
     def seq(self):

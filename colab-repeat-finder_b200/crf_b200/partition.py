@@ -27,8 +27,19 @@ DEFAULT_HALO = 1 << 20      # 1 Mbp (3 % of a unit): only a perfect repeat longe
                             # the halo is never scanned for starts, it is only read when a run is followed into it
 
 
+MIN_SPLIT = 1 << 20        # a share boundary closer than this to a chunk boundary moves onto it
+
+
 class Plan:
-    def __init__(self, lengths, n_ranks, chunk=DEFAULT_CHUNK, halo=DEFAULT_HALO, kmax=50, min_repeats=3, min_span=9):
+    """Records -> units (owned chunk + 1 base of left context + halo) -> contiguous shares, one per rank.
+
+    The shares are balanced by cost: `density` = [(lo, hi, cost_per_bp), ...] over the concatenated records (global base
+    pairs; default: uniform, i.e. balanced by base pairs).  A share boundary may fall anywhere, not only between chunks:
+    the chunk it falls into is cut in two units there, so a measured imbalance of a few percent can be corrected
+    (RankScan.rebalance) without making every unit -- and with it the share of halo that is scanned twice -- smaller."""
+
+    def __init__(self, lengths, n_ranks, chunk=DEFAULT_CHUNK, halo=DEFAULT_HALO, kmax=50, min_repeats=3, min_span=9,
+                 density=None):
         need = max(min_span, min_repeats * kmax) + kmax + 2
         if halo < need:
             raise ValueError(f"halo {halo} is shorter than one qualifying repeat of the largest motif ({need})")
@@ -37,30 +48,74 @@ class Plan:
         self.lengths = [int(x) for x in lengths]
         self.n_ranks = n_ranks
         self.chunk, self.halo = chunk, halo
-        units = []
+        rec_base = np.concatenate([[0], np.cumsum(np.asarray(self.lengths, dtype=np.int64))])
+        total = int(rec_base[-1])
+        self.total = total
+        # where the shares end, in global base pairs
+        cuts = self._cuts(total, n_ranks, density)
+        self.cuts = cuts
+        min_split = min(MIN_SPLIT, max(1, chunk // 8))
+        units, bounds, ci = [], [0], 1
         for r, length in enumerate(self.lengths):
             if length == 0:
                 continue
-            for u0 in range(0, length, chunk):
-                u1 = min(length, u0 + chunk)
+            g0 = int(rec_base[r])
+            edges = set(range(0, length, chunk)) | {length}
+            for c in cuts[1:-1]:                        # share boundaries inside this record
+                pos = c - g0
+                if 0 < pos < length:
+                    near = min(edges, key=lambda e: abs(e - pos))
+                    if abs(near - pos) >= min_split:
+                        edges.add(pos)
+            edges = sorted(edges)
+            for u0, u1 in zip(edges[:-1], edges[1:]):
                 units.append(Unit(len(units), r, u0, u1, max(0, u0 - 1), min(length, u1 + halo), length))
         self.units = units
-        # contiguous split balanced by owned base pairs
-        owned = np.array([u.u1 - u.u0 for u in units], dtype=np.int64)
-        csum = np.concatenate([[0], np.cumsum(owned)])
-        total = int(csum[-1])
-        bounds = [0]
+        # share i = the units whose owned range starts before cut i (and at or after cut i - 1)
+        starts = np.array([int(rec_base[u.record]) + u.u0 for u in units], dtype=np.int64)
+        ends = np.array([int(rec_base[u.record]) + u.u1 for u in units], dtype=np.int64)
+        mids = (starts + ends) // 2
         for i in range(1, n_ranks):
-            target = total * i / n_ranks
-            j = int(np.searchsorted(csum, target, side="left"))
-            if j > 0 and abs(csum[j - 1] - target) <= abs(csum[min(j, len(units))] - target):
-                j -= 1
+            j = int(np.searchsorted(mids, cuts[i], side="left"))
             bounds.append(min(max(j, bounds[-1]), len(units)))
         bounds.append(len(units))
         self.bounds = bounds
-        self._first_of_record = {}
+        self._rec_units = {}
         for u in units:
-            self._first_of_record.setdefault(u.record, u.index)
+            self._rec_units.setdefault(u.record, ([], []))
+            self._rec_units[u.record][0].append(u.u0)
+            self._rec_units[u.record][1].append(u.index)
+        del ci
+
+    @staticmethod
+    def _cuts(total, n_ranks, density):
+        if not density:
+            return [total * i // n_ranks for i in range(n_ranks + 1)]
+        segs = sorted((int(lo), int(hi), float(c)) for lo, hi, c in density if hi > lo)
+        # fill gaps / clip so that the segments tile [0, total)
+        tiled, pos = [], 0
+        mean = sum((hi - lo) * c for lo, hi, c in segs) / max(1, sum(hi - lo for lo, hi, c in segs))
+        for lo, hi, c in segs:
+            lo, hi = max(lo, pos), min(hi, total)
+            if lo > pos:
+                tiled.append((pos, lo, mean))
+            if hi > lo:
+                tiled.append((lo, hi, max(c, 1e-12)))
+                pos = hi
+        if pos < total:
+            tiled.append((pos, total, mean))
+        whole = sum((hi - lo) * c for lo, hi, c in tiled)
+        cuts, acc, k = [0], 0.0, 1
+        for lo, hi, c in tiled:
+            w = (hi - lo) * c
+            while k < n_ranks and acc + w >= whole * k / n_ranks:
+                cuts.append(int(lo + (whole * k / n_ranks - acc) / c))
+                k += 1
+            acc += w
+        while len(cuts) < n_ranks:
+            cuts.append(total)
+        cuts.append(total)
+        return cuts
 
     def units_of(self, rank):
         return self.units[self.bounds[rank]:self.bounds[rank + 1]]
@@ -69,8 +124,17 @@ class Plan:
         return int(np.searchsorted(np.array(self.bounds[1:]), index, side="right"))
 
     def unit_owning(self, record, pos):
-        first = self._first_of_record[record]
-        return self.units[first + pos // self.chunk]
+        import bisect
+        u0s, idx = self._rec_units[record]
+        return self.units[idx[bisect.bisect_right(u0s, pos) - 1]]
+
+    def share_range(self, rank):
+        """[lo, hi) in global base pairs (records concatenated) of the bases `rank` owns."""
+        us = self.units_of(rank)
+        if not us:
+            return 0, 0
+        rec_base = np.concatenate([[0], np.cumsum(np.asarray(self.lengths, dtype=np.int64))])
+        return int(rec_base[us[0].record]) + us[0].u0, int(rec_base[us[-1].record]) + us[-1].u1
 
     def load_args(self, rank, record_starts):
         """(starts, lengths, own_lo, own_hi) for Context.load_ranges; record_starts[r] = offset of

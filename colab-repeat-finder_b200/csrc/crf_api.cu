@@ -1229,6 +1229,7 @@ struct crf_xchg {
     // sequence, the context's stream) overlaps the push of this one
     cudaStream_t xstream = nullptr;
     cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    bool compact = false;                        // 12-byte rows over NVLink (crf_xchg_set_compact)
 };
 
 extern "C" int crf_xchg_create(crf_ctx *c, uint32_t rank, uint32_t world, uint64_t row_cap, crf_xchg **out) {
@@ -1331,6 +1332,12 @@ extern "C" int crf_xchg_destroy(crf_xchg *x) {
     return CRF_OK;
 }
 
+extern "C" int crf_xchg_set_compact(crf_xchg *x, int on) {
+    if (!x) { set_err("crf_xchg_set_compact: null exchange"); return CRF_ERR_ARG; }
+    x->compact = on != 0;
+    return CRF_OK;
+}
+
 extern "C" int crf_xchg_set_timeout(crf_xchg *x, double seconds) {
     if (!x || !(seconds > 0)) { set_err("crf_xchg_set_timeout: bad argument"); return CRF_ERR_ARG; }
     x->timeout_ns = (unsigned long long)(seconds * 1e9);
@@ -1360,6 +1367,7 @@ static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted, bool append) {
     pp.res_cap = s->res_cap; pp.open_cap = s->open_cap;
     pp.trusted = trusted ? 1u : 0u;
     pp.append = append ? 1u : 0u;
+    pp.compact = x->compact ? 1u : 0u;
     pp.timeout_ns = x->timeout_ns;
     publish_kernel<<<1, 32, 0, xs>>>(pp);
     push_kernel<<<148 * 2, 256, 0, xs>>>(pp);
@@ -1368,6 +1376,8 @@ static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted, bool append) {
     sp.row_cap = x->row_cap; sp.rank = x->rank; sp.world = x->world; sp.step = x->step; sp.append = pp.append;
     sp.timeout_ns = x->timeout_ns;
     settle_kernel<<<1, 32, 0, xs>>>(sp);
+    if (x->compact && x->rank == 0)
+        unpack_kernel<<<148 * 4, 256, 0, xs>>>((XchgBlock *)x->base, (uint32_t *)((char *)x->base + XCHG_ROWS_OFFSET), x->row_cap);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(x->h_ring + (size_t)(x->step % XCHG_RING) * XCHG_RESULT_WORDS, ((XchgBlock *)x->base)->result,
                        XCHG_RESULT_WORDS * 8, cudaMemcpyDeviceToHost, xs));
@@ -1526,6 +1536,7 @@ static cudaError_t preload_kernels() {
     if (e == cudaSuccess) e = preload(push_kernel);
     if (e == cudaSuccess) e = preload(settle_kernel);
     if (e == cudaSuccess) e = preload(patch_rows_kernel);
+    if (e == cudaSuccess) e = preload(unpack_kernel);
     return e;
 }
 

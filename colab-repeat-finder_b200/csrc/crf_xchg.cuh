@@ -97,6 +97,7 @@ struct PushParams {
     uint32_t res_cap, open_cap;
     uint32_t trusted;                    // the host has already checked (and fixed up) the scan these rows come from
     uint32_t append;                     // this step's rows go after those of the job's earlier phases (base_rows)
+    uint32_t compact;                    // 12 bytes per row over NVLink: record and motif size share one word (both < 65 536)
     unsigned long long timeout_ns;
 };
 
@@ -143,23 +144,30 @@ __global__ void __launch_bounds__(256) push_kernel(const PushParams p) {
         // four columns, each copied with 16-byte peer stores: the destination starts at an arbitrary row, so every column
         // has a scalar head up to the first 16-byte boundary of the DESTINATION, a vector body (four scalar loads from my
         // own HBM feed one st.v4 over NVLink) and a scalar tail
+        // compact rows: the record column is not sent; the motif-size column carries (record << 16 | k) and the root
+        // splits it again (unpack_kernel) -- rank 0's NVLink ingress is what bounds the gather, 12 bytes beat 16
         const uint32_t n = (uint32_t)n_total;
         const uint32_t *src[4] = {p.o_rec, p.o_start, p.o_end, p.o_k};
         const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+            if (c == 0 && p.compact) continue;
+            const bool fold = c == 3 && p.compact;
             uint32_t *dst = p.root_rows + (size_t)c * p.row_cap + off;
             const uint32_t *sp = src[c];
+            const uint32_t *rp = p.o_rec;
             const uint32_t head = min(n, (uint32_t)((4u - (uint32_t)(((uintptr_t)dst >> 2) & 3u)) & 3u));
             const uint32_t nvec = (n - head) >> 2;
-            if (gtid < head) dst[gtid] = sp[gtid];
+            if (gtid < head) dst[gtid] = fold ? (sp[gtid] | (rp[gtid] << 16)) : sp[gtid];
             uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
             for (uint32_t v = gtid; v < nvec; v += gsize) {
                 const uint32_t i = head + 4 * v;
-                dv[v] = make_uint4(sp[i], sp[i + 1], sp[i + 2], sp[i + 3]);
+                uint4 q = make_uint4(sp[i], sp[i + 1], sp[i + 2], sp[i + 3]);
+                if (fold) { q.x |= rp[i] << 16; q.y |= rp[i + 1] << 16; q.z |= rp[i + 2] << 16; q.w |= rp[i + 3] << 16; }
+                dv[v] = q;
             }
             const uint32_t tail0 = head + 4 * nvec;
-            if (gtid < n - tail0) dst[tail0 + gtid] = sp[tail0 + gtid];
+            if (gtid < n - tail0) dst[tail0 + gtid] = fold ? (sp[tail0 + gtid] | (rp[tail0 + gtid] << 16)) : sp[tail0 + gtid];
         }
     }
     __threadfence_system();                               // my rows are visible on the root before the done word can be
@@ -221,6 +229,18 @@ __global__ void __launch_bounds__(32) settle_kernel(const SettleParams p) {
         p.self->result[2] = open_total;
         p.self->result[3] = p.self->my_offset;
         p.self->result[4] = any_open ? 1ull : 0ull;
+    }
+}
+
+// root, compact rows: (record << 16 | k) of this step's rows -> the record and motif-size columns
+__global__ void __launch_bounds__(256) unpack_kernel(XchgBlock *self, uint32_t *root_rows, uint64_t row_cap) {
+    if (self->result[0] != XCHG_OK) return;
+    const unsigned long long lo = self->result[5], hi = self->result[1];      // this step's rows: [base, total)
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+        const uint32_t v = root_rows[3 * row_cap + i];
+        root_rows[i] = v >> 16;
+        root_rows[3 * row_cap + i] = v & 0xFFFFu;
     }
 }
 

@@ -200,6 +200,9 @@ int crf_xchg_connect_ipc(crf_xchg *xchg, uint32_t peer_rank, const uint8_t *hand
 /* Ranks of one process (one context per device, one thread per context). */
 int crf_xchg_connect_local(crf_xchg *xchg, uint32_t peer_rank, crf_xchg *peer);
 int crf_xchg_set_timeout(crf_xchg *xchg, double seconds); /* how long a kernel waits for a peer (default 20 s) */
+/* 12 instead of 16 bytes per row over NVLink (rank 0's ingress bounds the gather): allowed when every record number and every
+ * motif size of the job is below 65 536; all ranks must make the same choice.  Rank 0 still ends up with the four columns. */
+int crf_xchg_set_compact(crf_xchg *xchg, int on);
 
 /* crf_scan + push in one go, fully asynchronous: nothing is copied back and the host does not wait.  If the scan
  * outgrows a buffer, has a long spill list or more open-ended rows than their list holds, the step is void on

@@ -118,6 +118,46 @@ def test_many_steps_in_flight_then_one_wait(mods):
         assert np.array_equal(a, b)
 
 
+def test_rebalanced_shares_give_the_same_rows(mods):
+    """RankScan.rebalance(): shares re-cut by measured scan time (boundaries inside chunks), sequences reloaded; the rows
+    gathered on rank 0 stay the single-scan rows."""
+    import threading
+    bases, offsets, _ = mods.synth.s38(device=None, scale=0.004)
+    bases = bases.copy()
+    bases[: len(bases) // 3] = ord("N")                    # one third costs nothing: the first ranks' shares are cheap
+    want = _whole(mods, bases, offsets)
+    lengths = np.diff(offsets.astype(np.int64))
+    world = 3
+    comms = mods.multi.ThreadComm.split(world)
+    out = {}
+
+    def work(rank):
+        rs = mods.multi.RankScan(mods.cabi.Context(0), comms[rank], bases, offsets[:-1], lengths, 1, 50, 3, 9,
+                                 chunk=1 << 19, halo=1 << 12, timeout_s=30)
+        rs.step_async()
+        rs.finish()
+        before = rs.plan.share_range(rank)
+        gains = []
+        for _ in range(2):
+            gains.append(rs.rebalance(min_gain=0.0))
+            rs.step_async()
+            rs.finish()
+        out[rank] = (before, rs.plan.share_range(rank), gains, rs.fetch() if rank == 0 else None)
+        rs.close()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(out) == world
+    for a, b in zip(want, out[0][3]):
+        assert np.array_equal(a, b)
+    assert any(out[r][0] != out[r][1] for r in range(world))       # the boundaries did move
+    spans = sorted(out[r][1] for r in range(world))
+    assert spans[0][0] == 0 and spans[-1][1] == int(lengths.sum()) and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
 def test_cli_devices_writes_the_same_bed(mods, tmp_path, monkeypatch):
     """--devices: the BED of a multi-rank run equals the single-GPU BED byte for byte (loopback: both ranks on GPU 0;
     with 2+ GPUs also on distinct devices)."""

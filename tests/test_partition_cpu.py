@@ -62,6 +62,28 @@ def test_plan_covers_every_base_once_and_balances():
         partition.Plan(lengths, 2, chunk=256, halo=16, kmax=KMAX, min_repeats=MR, min_span=MS)
 
 
+def test_plan_balances_by_cost_density_with_cuts_inside_chunks():
+    lengths = [5000, 1, 0, 2300, 777, 40_000]
+    total = sum(lengths)
+    # the second half of the genome costs three times as much per base
+    density = [(0, total // 2, 1.0), (total // 2, total, 3.0)]
+    for world in (2, 3, 8):
+        plan = partition.Plan(lengths, world, chunk=4096, halo=64, kmax=KMAX, min_repeats=MR, min_span=MS, density=density)
+        seen, owned = [], [0] * len(lengths)
+        costs = []
+        for rank in range(world):
+            lo, hi = plan.share_range(rank)
+            costs.append(sum((min(hi, h) - max(lo, l)) * c for l, h, c in density if min(hi, h) > max(lo, l)))
+            for u in plan.units_of(rank):
+                owned[u.record] += u.u1 - u.u0
+                assert plan.rank_of_unit(u.index) == rank and plan.unit_owning(u.record, u.u0).index == u.index
+                assert plan.unit_owning(u.record, u.u1 - 1).index == u.index
+                seen.append(u.index)
+        assert owned == lengths and seen == list(range(len(plan.units)))
+        assert max(costs) - min(costs) <= 0.05 * sum(costs) / world + 3 * 600     # equal cost, up to the minimum split distance
+        assert max(u.u1 - u.u0 for u in plan.units) <= 4096
+
+
 @pytest.mark.parametrize("chunk,halo", [(256, 64), (500, 100), (4096, 64), (1 << 20, 64)])
 def test_single_rank_chunked_scan_equals_whole_record_scan(chunk, halo):
     records = make_records(3)
