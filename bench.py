@@ -322,7 +322,7 @@ def main():
     for i in range(args.warmup):
         rs.step_async()
         rs.finish()
-        if world > 1 and i < 2 and not args.no_rebalance:
+        if world > 1 and i < min(4, args.warmup - 1) and not args.no_rebalance:
             # shares by measured cost instead of by base pairs (RankScan.rebalance: the slowest rank sets the step); the
             # remaining warm-up steps size the buffers of the new shares
             rebalanced.append(round(rs.rebalance(), 4))
@@ -470,8 +470,32 @@ def main():
 
     e2e_dt, d2h = e2e_run(planes, args.e2e_steps)
     ascii_dt, _ = e2e_run(host_np, 1)
+
+    # where an end-to-end step goes (one more step, this rank's wall clock with a synchronisation after every stage)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tb0 = time.perf_counter()
+    rs.reload(planes, on_device=False, base_offset=span_lo)
+    torch.cuda.synchronize()
+    tb1 = time.perf_counter()
+    rs.step_async()
+    n2 = rs.finish()
+    torch.cuda.synchronize()
+    tb2 = time.perf_counter()
+    if rank == 0:
+        if world == 1:
+            rs.seq.fetch_host(*(pinned_out[j].data_ptr() for j in range(4)), pinned_out.shape[1])
+        else:
+            rs.xchg.fetch_to(*(pinned_out[j].data_ptr() for j in range(4)), n2)
+    torch.cuda.synchronize()
+    tb3 = time.perf_counter()
+    breakdown = {"upload_and_repack_ms": (tb1 - tb0) * 1e3, "scan_and_gather_ms": (tb2 - tb1) * 1e3,
+                 "rows_to_host_ms": (tb3 - tb2) * 1e3,
+                 "note": "rank 0, one extra step with a synchronisation after every stage; the upload shrinks with N, the "
+                         "rows of the whole job always leave through rank 0's PCIe link"}
     e2e = {"value": total_bp / e2e_dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": total_over_ranks(planes.nbytes),
-           "d2h_bytes_per_step": total_over_ranks(d2h), "ms_per_step": e2e_dt * 1e3,
+           "d2h_bytes_per_step": total_over_ranks(d2h), "ms_per_step": e2e_dt * 1e3, "breakdown": breakdown,
            "host_buffers": "2-bit planes + not-ACGT mask in page-locked memory, as the native FASTA reader packs them at "
                            "ingest (crf_pack_ascii: %.2f s for this rank's %d bp on the host, outside the timed region)"
                            % (pack_s, n_span),
