@@ -18,7 +18,7 @@ SCAN_WARP_TILES = 2
 SCAN_BLOCK_TILES = 4
 SCAN_TWO_STRIPS = 8
 
-CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_CAPACITY = range(6)
+CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_CAPACITY, CRF_ERR_IO = range(7)
 
 #: every symbol include/crf.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -142,6 +142,8 @@ def _check(rc):
         raise NotImplementedError(msg)
     if rc == CRF_ERR_NOMEM:
         raise MemoryError(msg)
+    if rc == CRF_ERR_IO:
+        raise OSError(msg)
     raise CrfError(f"libcrf error {rc}: {msg}")
 
 

@@ -1549,15 +1549,15 @@ static inline char *put_u32(char *p, uint32_t v) {
     return p;
 }
 
-extern "C" int crf_write_rows(const char *path, int append, int tsv, const char *names, const uint8_t *bases,
-                              const uint64_t *offsets, const uint32_t *record, const uint32_t *start,
-                              const uint32_t *end, const uint32_t *motif_size, uint64_t n_rows, uint64_t *bytes) {
-    if (!path || (n_rows && (!bases || !offsets || !record || !start || !end || !motif_size)) || (!tsv && !names)) {
-        set_err("crf_write_rows: null argument");
-        return CRF_ERR_ARG;
-    }
+static int write_rows_impl(const char *path, int append, int tsv, const char *names, const uint8_t *bases,
+                           const uint64_t *offsets, const uint32_t *record, const uint32_t *start,
+                           const uint32_t *end, const uint32_t *motif_size, uint64_t n_rows, uint64_t *bytes) {
     FILE *f = fopen(path, append ? "ab" : "wb");
     if (!f) { set_err("crf_write_rows: cannot open %s", path); return CRF_ERR_ARG; }
+    struct Closer {                                  // the file is closed on every way out (bad_alloc included)
+        FILE *f;
+        ~Closer() { if (f) fclose(f); }
+    } closer{f};
     std::vector<const char *> name_ptr;
     std::vector<size_t> name_len;
     if (!tsv) {
@@ -1571,14 +1571,22 @@ extern "C" int crf_write_rows(const char *path, int append, int tsv, const char 
         }
     }
     uint64_t total = 0;
-    if (tsv && !append) total += fwrite("start_0based\tend\tmotif\n", 1, 23, f);
+    bool ok = true;
+    auto put = [&](const char *p, size_t n) {        // a short write (disk full, I/O error) is an error, not a shorter file
+        if (n && ok) {
+            const size_t w = fwrite(p, 1, n, f);
+            total += w;
+            if (w != n) ok = false;
+        }
+    };
+    if (tsv && !append) put("start_0based\tend\tmotif\n", 23);
     std::vector<char> buf(1 << 22);
     size_t used = 0;
-    for (uint64_t i = 0; i < n_rows; ++i) {
+    for (uint64_t i = 0; i < n_rows && ok; ++i) {
         const uint32_t r = record[i], k = motif_size[i];
         const size_t need = (tsv ? 0 : name_len[r] + 1) + 24 + k + 1;
         if (used + need > buf.size()) {
-            total += fwrite(buf.data(), 1, used, f);
+            put(buf.data(), used);
             used = 0;
             if (need > buf.size()) buf.resize(need * 2);
         }
@@ -1595,11 +1603,28 @@ extern "C" int crf_write_rows(const char *path, int append, int tsv, const char 
         *p++ = '\n';
         used = (size_t)(p - buf.data());
     }
-    total += fwrite(buf.data(), 1, used, f);
-    const bool ok = fclose(f) == 0;
+    put(buf.data(), used);
+    if (ferror(f)) ok = false;
+    closer.f = nullptr;
+    if (fclose(f) != 0) ok = false;
     if (bytes) *bytes = total;
-    if (!ok) { set_err("crf_write_rows: write to %s failed", path); return CRF_ERR_ARG; }
+    if (!ok) { set_err("crf_write_rows: write to %s failed (after %llu bytes)", path, (unsigned long long)total); return CRF_ERR_IO; }
     return CRF_OK;
+}
+
+extern "C" int crf_write_rows(const char *path, int append, int tsv, const char *names, const uint8_t *bases,
+                              const uint64_t *offsets, const uint32_t *record, const uint32_t *start,
+                              const uint32_t *end, const uint32_t *motif_size, uint64_t n_rows, uint64_t *bytes) {
+    if (!path || (n_rows && (!bases || !offsets || !record || !start || !end || !motif_size)) || (!tsv && !names)) {
+        set_err("crf_write_rows: null argument");
+        return CRF_ERR_ARG;
+    }
+    try {                                            // no exception crosses the C boundary
+        return write_rows_impl(path, append, tsv, names, bases, offsets, record, start, end, motif_size, n_rows, bytes);
+    } catch (const std::bad_alloc &) {
+        set_err("crf_write_rows: out of host memory");
+        return CRF_ERR_NOMEM;
+    }
 }
 
 #include "crf_fasta.h"

@@ -29,6 +29,7 @@ extern "C" {
 #define CRF_ERR_NOMEM 3
 #define CRF_ERR_UNSUPPORTED 4 /* valid for the reference, not implemented here (loud)     */
 #define CRF_ERR_CAPACITY 5    /* caller-provided buffer too small                          */
+#define CRF_ERR_IO 6          /* a file could not be written in full                       */
 
 typedef struct crf_ctx crf_ctx; /* one CUDA device + stream + scratch                      */
 typedef struct crf_seq crf_seq; /* a set of records resident in HBM as packed bit-planes   */

@@ -407,3 +407,18 @@ def test_detect_repeats_host_logic_against_reference_vectors(monkeypatch, name):
             n_rows += len(got)
         n_exc += exc is not None
     assert n_rows > 30
+
+
+def test_write_rows_reports_a_short_write(tmp_path):
+    """crf_write_rows (host only): rows as text, and a device that takes no more bytes is an OSError, not a silently
+    truncated BED file."""
+    from crf_b200 import _cabi
+    bases = np.frombuffer(b"ACGTACGTACGTttttttttNN", dtype=np.uint8)
+    path = tmp_path / "w.bed"
+    n = _cabi.write_rows(str(path), ["chrA"], bases, [0, 22], [0, 0], [0, 12], [12, 20], [4, 1])
+    assert path.read_text() == "chrA\t0\t12\tACGT\nchrA\t12\t20\tT\n" and n == 28
+    n = _cabi.write_rows(str(path), None, bases, [0, 22], [0], [12], [20], [2], tsv=True)
+    assert path.read_text() == "start_0based\tend\tmotif\n12\t20\tTT\n" and n == 23 + 9
+    if os.path.exists("/dev/full"):
+        with pytest.raises(OSError, match="failed"):
+            _cabi.write_rows("/dev/full", ["chrA"], bases, [0, 22], [0] * 100_000, [0] * 100_000, [12] * 100_000, [4] * 100_000)

@@ -116,6 +116,85 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+# ---- crf_b200.multi.RankScan (the path bench.py and the CLI's --devices use) with the library replaced by CPU stand-ins:
+# ---- shares, phases, the offsets inside rank 0's buffer, the stitch of open-ended rows and their patching ----
+def _rankscan_rows(multi, comm, records, chunk, halo, phases, rebalance=False):
+    lengths = [len(r) for r in records]
+    starts = np.concatenate([[0], np.cumsum(lengths)])[:-1]
+    rs = multi.RankScan(FakeContext(), comm, np.frombuffer(b"".join(records), dtype=np.uint8), starts, lengths,
+                        KMIN, KMAX, MR, MS, chunk=chunk, halo=halo, phases=phases)
+    rs.step_async()
+    n = rs.finish()
+    if rebalance:
+        rs.rebalance(min_gain=-1.0)
+        rs.step_async()
+        n = rs.finish()
+    rows = None
+    if comm.rank == 0:
+        rec, st, en, k = rs.fetch()
+        rows = list(zip(rec.tolist(), st.tolist(), en.tolist(), k.tolist()))
+        assert len(rows) == n
+    rs.close()
+    return rows
+
+
+@pytest.mark.parametrize("world,phases,chunk,halo", [(1, 1, 300, 64), (2, 1, 300, 64), (3, 2, 256, 64), (4, 3, 500, 100)])
+def test_rankscan_with_thread_ranks(world, phases, chunk, halo, monkeypatch):
+    import threading
+    from crf_b200 import multi
+    from tests.fake_ctx import FakeXchg
+    monkeypatch.setattr(multi._cabi, "Xchg", FakeXchg)
+    monkeypatch.setattr(FakeXchg, "dist", None)
+    records = make_records(3)
+    comms = multi.ThreadComm.split(world)
+    out, errors = {}, []
+
+    def work(rank):
+        try:
+            out[rank] = _rankscan_rows(multi, comms[rank], records, chunk, halo, phases, rebalance=(phases == 1 and world > 1))
+        except BaseException as exc:      # noqa: BLE001
+            errors.append(exc)
+            comms[rank]._s.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert out[0] == expected(records)
+
+
+def _rankscan_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from crf_b200 import multi
+    from tests.fake_ctx import FakeXchg
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    multi._cabi.Xchg = FakeXchg
+    FakeXchg.dist = dist
+    rows = _rankscan_rows(multi, multi.DistComm(dist, rank, world), make_records(3), 300, 64, 2)
+    q.put((rank, rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rankscan_two_process_ranks_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + random.randint(2001, 4000)
+    procs = [ctx.Process(target=_rankscan_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0] == expected(make_records(3)) and results[1] is None
+
+
 def test_two_ranks_over_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
