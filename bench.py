@@ -127,8 +127,8 @@ def make_workload(name, device, scale):
     from crf_b200 import synth
     if name == "s38":
         return synth.s38(device=device, scale=scale)
-    if name == "s22":
-        return synth.s22(device=device, scale=scale)
+    if name == "s22":                                 # configs C1/C2: the real chr22 if this machine has it, else the stand-in
+        return synth.chr22(device=device, scale=scale)
     if name == "sr":                                  # config C5: 10 M reads x 150 bp, motif 1-20
         return synth.sr(int(10_000_000 * scale), device=device)
     raise SystemExit(f"unknown workload {name}")

@@ -190,6 +190,37 @@ def s22(device=None, scale=1.0, seed=22):
     return bases, offsets, meta
 
 
+CHR22_PATHS = ("/root/reference/benchmark/chr22.fa.gz", "benchmark/chr22.fa.gz")
+
+
+def chr22_path():
+    """The real chr22 FASTA of configs C1/C2 if this machine has it: $CRF_CHR22_FASTA, else the reference checkout's
+    benchmark/chr22.fa.gz (absent from it: .MISSING_LARGE_BLOBS:1), else None."""
+    import os
+    for path in (os.environ.get("CRF_CHR22_FASTA"),) + CHR22_PATHS:
+        if path and os.path.isfile(path):
+            return path
+    return None
+
+
+def chr22(device=None, scale=1.0):
+    """Configs C1/C2: the real chr22 when it can be found (read by the native FASTA reader), else the stand-in S22.
+    meta["workload"] says which."""
+    path = chr22_path()
+    if path is None or scale != 1.0:
+        return s22(device=device, scale=scale)
+    from . import _cabi
+    with _cabi.Fasta(path) as fa:
+        bases = fa.bases.copy()
+        offsets = fa.offsets.copy()
+        names = list(fa.names)
+    if device is not None:
+        import torch
+        bases = torch.from_numpy(bases).to(device)
+        torch.cuda.synchronize()
+    return bases, offsets, {"names": names, "workload": f"chr22 from {path}, {int(offsets[-1])} bp"}
+
+
 def sr(n_reads, read_len=150, device=None, seed=150):
     """n_reads x read_len reads (config C5): one planted STR per 512-base cell of the read
     stream (so roughly one read in three carries one), 0.1 % of bases N."""

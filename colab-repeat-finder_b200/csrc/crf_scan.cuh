@@ -32,6 +32,9 @@
 #pragma once
 #include "crf_device.cuh"
 
+#ifndef CRF_MIN_CTAS
+#define CRF_MIN_CTAS 4   // resident CTAs per SM the block-tiled kernel is compiled for (4 x 256 threads x 64 registers = the register file)
+#endif
 namespace crf {
 
 __host__ __device__ __forceinline__ uint32_t pad_idx(uint32_t v) { return v + (v >> 5); }
@@ -310,7 +313,7 @@ __host__ __device__ inline size_t scan_smem_bytes(int T, uint32_t kmax, uint32_t
 // closes the phase as with NS = 1 (2 rounds, the second ~40 % filled); registers are unchanged (the strips of a thread are
 // processed one after the other), shared memory grows by the second set of plane words.
 template <int T, int NS = 1>
-__global__ void __launch_bounds__(THREADS, (T <= 8 && NS == 1) ? 4 : (T <= 8 ? 3 : 1)) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(THREADS, (T <= 8 && NS == 1) ? CRF_MIN_CTAS : (T <= 8 ? 3 : 1)) scan_kernel(const ScanParams p) {
     constexpr int TW = THREADS * T * NS;
     constexpr uint32_t STRIPS = THREADS * NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];

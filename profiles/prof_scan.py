@@ -27,7 +27,7 @@ if not args.kmax:
 if args.workload == "s38":
     bases, offsets, meta = synth.s38(device="cuda:0", scale=args.scale)
 elif args.workload == "s22":
-    bases, offsets, meta = synth.s22(device="cuda:0", scale=args.scale)
+    bases, offsets, meta = synth.chr22(device="cuda:0", scale=args.scale)
 else:
     bases, offsets, meta = synth.sr(int(10_000_000 * args.scale), device="cuda:0")
 torch.cuda.synchronize()

@@ -422,3 +422,36 @@ def test_write_rows_reports_a_short_write(tmp_path):
     if os.path.exists("/dev/full"):
         with pytest.raises(OSError, match="failed"):
             _cabi.write_rows("/dev/full", ["chrA"], bases, [0, 22], [0] * 100_000, [0] * 100_000, [12] * 100_000, [4] * 100_000)
+
+
+GOLDEN_BED = "/root/reference/benchmark/repeat_finder/chr22_repeats.bed"
+
+
+@pytest.mark.skipif(not os.path.isfile(GOLDEN_BED), reason="the reference checkout is not on this machine")
+def test_reference_golden_bed_obeys_the_closed_form():
+    """The one full-size output the reference ships (benchmark/repeat_finder/chr22_repeats.bed: chr22, motif 1-6,
+    --min-repeats 3 --min-span 9; its input chr22.fa.gz is missing from the checkout).  Every row must satisfy what the
+    kernels compute: sorted by (start, end), unique keys, span >= max(min_span, min_repeats * k), a
+    primitive N-free motif, and the repeat really being periodic cannot be checked without the bases -- the rest pins our
+    reading of the BED format and the filters."""
+    from utils.perfect_repeat_tracker import consists_of_perfect_repeats
+    rows = [ln.rstrip("\n").split("\t") for ln in open(GOLDEN_BED)]
+    assert len(rows) == 67638 and all(len(r) == 4 and r[0] == "chr22" for r in rows)
+    keys = [(int(r[1]), int(r[2])) for r in rows]
+    assert keys == sorted(keys) and len(set(keys)) == len(keys)
+    for (s0, e0), r in zip(keys, rows):
+        motif = r[3]
+        k = len(motif)
+        assert 1 <= k <= 6 and set(motif) <= set("ACGT")
+        assert e0 - s0 >= max(9, 3 * k)
+        assert consists_of_perfect_repeats(motif) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(synth.chr22_path() is None or not os.path.isfile(GOLDEN_BED),
+                    reason="benchmark/chr22.fa.gz is not in the reference checkout (.MISSING_LARGE_BLOBS); set CRF_CHR22_FASTA")
+def test_config_c1_real_chr22_bed_equals_the_reference_golden(tmp_path, monkeypatch):
+    """Config C1 proper: the CLI on the real chr22 FASTA against the BED the reference produced from it."""
+    monkeypatch.chdir(tmp_path)
+    assert cli.main([synth.chr22_path(), "-min", "1", "-max", "6", "--min-repeats", "3", "--min-span", "9", "-o", "c1"]) == 0
+    assert open(tmp_path / "c1.bed").read() == open(GOLDEN_BED).read()
