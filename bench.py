@@ -425,8 +425,8 @@ def main():
     nw = (n_span + 31) // 32 + 1
     plane_buf = torch.zeros((3, nw), dtype=torch.int32, pin_memory=True)
     t0 = time.perf_counter()
-    planes = _cabi.pack_ascii(host_np, out=tuple(plane_buf[j].numpy().view(np.uint32) for j in range(3)))
-    pack_s = time.perf_counter() - t0
+    planes = _cabi.pack_ascii(host_np, out=tuple(plane_buf[j].numpy().view(np.uint32) for j in range(3))).with_runs()
+    pack_s = time.perf_counter() - t0                                    # (the mask goes up as runs of masked positions)
     pinned_out = None
 
     def e2e_run(source, n_steps):
@@ -496,9 +496,9 @@ def main():
                          "rows of the whole job always leave through rank 0's PCIe link"}
     e2e = {"value": total_bp / e2e_dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": total_over_ranks(planes.nbytes),
            "d2h_bytes_per_step": total_over_ranks(d2h), "ms_per_step": e2e_dt * 1e3, "breakdown": breakdown,
-           "host_buffers": "2-bit planes + not-ACGT mask in page-locked memory, as the native FASTA reader packs them at "
-                           "ingest (crf_pack_ascii: %.2f s for this rank's %d bp on the host, outside the timed region)"
-                           % (pack_s, n_span),
+           "host_buffers": "2-bit planes in page-locked memory + the not-ACGT mask as %d runs, as the native FASTA reader "
+                           "packs them at ingest (crf_pack_ascii + crf_mask_runs: %.2f s for this rank's %d bp on the host, "
+                           "outside the timed region)" % (planes.runs.shape[0], pack_s, n_span),
            "e2e_ascii": {"value": total_bp / ascii_dt / 1e9, "unit": "Gbp/s", "ms_per_step": ascii_dt * 1e3,
                          "h2d_bytes_per_step": total_over_ranks(n_span),
                          "host_buffers": "the ASCII text itself, page-locked (upper-casing + packing on the GPU)"}}

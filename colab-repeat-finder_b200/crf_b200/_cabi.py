@@ -24,6 +24,7 @@ CRF_OK, CRF_ERR_CUDA, CRF_ERR_ARG, CRF_ERR_NOMEM, CRF_ERR_UNSUPPORTED, CRF_ERR_C
 EXPORTS = [
     "crf_last_error", "crf_abi_version", "crf_ctx_create", "crf_ctx_destroy", "crf_ctx_set_stream",
     "crf_ctx_synchronize", "crf_load_limit", "crf_seq_load_packed", "crf_seq_load_packed_ranges", "crf_pack_ascii",
+    "crf_seq_load_packed_runs", "crf_seq_load_packed_runs_ranges", "crf_mask_runs",
     "crf_fasta_packed", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
     "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end", "crf_write_rows",
     "crf_fasta_open", "crf_fasta_info", "crf_fasta_data", "crf_fasta_close",
@@ -95,6 +96,9 @@ def lib():
         L.crf_seq_load_packed.argtypes = [vp, vp, vp, vp, vp, u64, vp, u32, u32, i, P(vp)]
         L.crf_seq_load_packed_ranges.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, u32, u32, i, P(vp)]
         L.crf_pack_ascii.argtypes = [vp, u64, u32, vp, vp, vp, vp, u64, P(u64)]
+        L.crf_seq_load_packed_runs.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, u32, u32, i, P(vp)]
+        L.crf_seq_load_packed_runs_ranges.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, vp, vp, vp, u32, u32, i, P(vp)]
+        L.crf_mask_runs.argtypes = [vp, u64, u32, vp, u64, P(u64)]
         L.crf_fasta_packed.argtypes = [vp, u32, P(vp), P(vp), P(vp), P(vp), P(u64)]
         L.crf_seq_set_output_map.argtypes = [vp, vp, vp, vp]
         L.crf_seq_destroy.argtypes = [vp]
@@ -218,6 +222,31 @@ class Sequence:
         if packed is not None:
             pk = packed
             ex_ptr = pk.exotic.ctypes.data if pk.exotic.size else 0
+            if pk.runs is not None:                       # the mask travels as runs: 0.25 B/bp over PCIe
+                runs_ptr = pk.runs.ctypes.data if pk.runs.size else 0
+                n_runs = pk.runs.shape[0]
+                if ranges is not None:
+                    starts, lengths, own_lo, own_hi = (None if a is None else np.ascontiguousarray(a, dtype=np.uint64)
+                                                       for a in ranges)
+                    self.n_records = starts.size
+                    self.lengths = lengths
+                    _check(lib().crf_seq_load_packed_runs_ranges(
+                        ctx._h, pk.H_ptr, pk.L_ptr, ctypes.c_void_p(runs_ptr), n_runs, ctypes.c_void_p(ex_ptr), pk.exotic.size,
+                        ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(lengths.ctypes.data),
+                        ctypes.c_void_p(own_lo.ctypes.data if own_lo is not None else 0),
+                        ctypes.c_void_p(own_hi.ctypes.data if own_hi is not None else 0),
+                        self.n_records, int(max_motif_cap), int(bool(pk.on_device)), ctypes.byref(self._h)))
+                    return
+                offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+                if offsets.ndim != 1 or offsets.size < 2:
+                    raise ValueError("offsets must hold n_records + 1 entries")
+                self.offsets = offsets
+                self.n_records = offsets.size - 1
+                _check(lib().crf_seq_load_packed_runs(ctx._h, pk.H_ptr, pk.L_ptr, ctypes.c_void_p(runs_ptr), n_runs,
+                                                      ctypes.c_void_p(ex_ptr), pk.exotic.size,
+                                                      ctypes.c_void_p(offsets.ctypes.data), self.n_records, int(max_motif_cap),
+                                                      int(bool(pk.on_device)), ctypes.byref(self._h)))
+                return
             if ranges is not None:
                 starts, lengths, own_lo, own_hi = (None if a is None else np.ascontiguousarray(a, dtype=np.uint64)
                                                    for a in ranges)
@@ -383,10 +412,12 @@ class PackedPlanes:
     """2-bit planes + not-ACGT mask of `n_bases` positions (what crf_seq_load_packed uploads): three uint32 arrays (or raw
     pointers) of ceil(n_bases / 32) words and the sorted exotic list (position << 8 | upper-cased byte)."""
 
-    def __init__(self, n_bases, H, L, NM, exotic, keep=None, on_device=False):
+    def __init__(self, n_bases, H, L, NM, exotic, keep=None, on_device=False, runs=None):
         self.n_bases = int(n_bases)
         self.H, self.L, self.NM = H, L, NM
         self.exotic = np.ascontiguousarray(exotic, dtype=np.uint64)
+        #: the mask as sorted runs of masked positions, shape (n, 2) -- when set, loads send these instead of the NM plane
+        self.runs = None if runs is None else np.ascontiguousarray(runs, dtype=np.uint64).reshape(-1, 2)
         self.on_device = on_device
         self._keep = keep
 
@@ -400,7 +431,30 @@ class PackedPlanes:
 
     @property
     def nbytes(self):
+        """Bytes a load of all of it sends to the device."""
+        if self.runs is not None:
+            return 8 * self.n_words + 8 * int(self.runs.size) + 8 * int(self.exotic.size)
         return 12 * self.n_words + 8 * int(self.exotic.size)
+
+    def with_runs(self, n_threads=0):
+        """The same planes with the mask as runs (crf_mask_runs; host only)."""
+        self.runs = mask_runs(self.NM_ptr, self.n_bases, n_threads)
+        return self
+
+
+def mask_runs(nm, n_bases, n_threads=0):
+    """(n, 2) uint64 array of the maximal runs [from, to) of masked positions of an NM plane (array or pointer)."""
+    ptr = nm if isinstance(nm, ctypes.c_void_p) else ctypes.c_void_p(nm.ctypes.data if isinstance(nm, np.ndarray) else int(nm))
+    cap = 4096
+    while True:
+        runs = np.empty((cap, 2), np.uint64)
+        n = ctypes.c_uint64()
+        rc = lib().crf_mask_runs(ptr, int(n_bases), int(n_threads), ctypes.c_void_p(runs.ctypes.data), cap, ctypes.byref(n))
+        if rc == CRF_ERR_CAPACITY:
+            cap = int(n.value) + 16
+            continue
+        _check(rc)
+        return runs[:n.value].copy()
 
 
 def pack_ascii(bases, n_threads=0, out=None):
@@ -533,7 +587,7 @@ class Fasta:
                                       ctypes.byref(ex), ctypes.byref(n_ex)))
         exotic = np.ctypeslib.as_array(ctypes.cast(ex, ctypes.POINTER(ctypes.c_uint64)), shape=(n_ex.value,)).copy() \
             if n_ex.value else np.zeros(0, np.uint64)
-        return PackedPlanes(self.total_bases, H.value, L.value, NM.value, exotic, keep=self)
+        return PackedPlanes(self.total_bases, H.value, L.value, NM.value, exotic, keep=self).with_runs(n_threads)
 
     def close(self):
         if self._h:

@@ -325,6 +325,9 @@ struct LoadSource {
     const uint32_t *pH = nullptr, *pL = nullptr, *pN = nullptr;   // packed: source position p = bit p & 31 of word p >> 5
     const uint64_t *exotic = nullptr;                   // packed: (source position << 8 | upper-cased byte), ascending
     uint64_t n_exotic = 0;
+    const uint64_t *nm_runs = nullptr;                  // packed, instead of pN: the masked positions as sorted runs
+    uint64_t n_runs = 0;                                //   [runs[2i], runs[2i+1]) -- 0.25 B/bp cross PCIe instead of 0.375
+    bool runs_mode = false;
     bool packed() const { return pH != nullptr; }
 };
 
@@ -389,8 +392,11 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
     uint64_t src_base = 0;                                               // source position of the device view's first element
     uint8_t *d_src_own = nullptr;
     uint32_t *d_planes_own = nullptr;                                    // 3 x (span / 32 + 1) words
+    uint32_t *d_mask_own = nullptr;                                      // runs mode with planes on the device: the mask plane
+    uint64_t *d_runs = nullptr;
     uint64_t *d_src_start = nullptr;
     const uint64_t span_words = span / 32 + 1;                           // + 1: repack_kernel reads word wi + 1
+    const bool runs_mode = packed && src.runs_mode;
     if (!on_device) {
         if (packed) {
             CHECK(dev_alloc(&d_planes_own, 3 * (size_t)span_words));
@@ -400,6 +406,21 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
             d_src = d_src_own;
         }
         src_base = src_lo;
+    } else if (runs_mode) {                                              // H, L stay where they are; the mask is built here
+        CHECK(dev_alloc(&d_mask_own, (size_t)((src_hi + 31) / 32 + 1)));
+        d_pN = d_mask_own;
+    }
+    // runs mode: the mask plane of the span is rebuilt on the device from the (few) runs that touch it
+    std::vector<uint64_t> runs_rel;
+    if (runs_mode) {
+        const uint64_t lo = on_device ? 0 : src_lo, hi = src_hi;
+        const uint64_t *rb = src.nm_runs, nr = src.n_runs;
+        uint64_t a = 0, b = nr;                                          // first run that ends after lo
+        while (a < b) { const uint64_t m = (a + b) / 2; if (rb[2 * m + 1] <= lo) a = m + 1; else b = m; }
+        for (uint64_t i = a; i < nr && rb[2 * i] < hi; ++i) {
+            runs_rel.push_back(std::max(rb[2 * i], lo) - lo);
+            runs_rel.push_back(std::min(rb[2 * i + 1], hi) - lo);
+        }
     }
     auto copy_span = [&](uint64_t lo, uint64_t n, cudaStream_t cs) -> cudaError_t {    // source positions [src_lo + lo, + n)
         if (!n) return cudaSuccess;
@@ -407,14 +428,17 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
         const uint64_t w0 = lo / 32, nw = (n + 31) / 32, h0 = src_lo / 32 + w0;
         cudaError_t e = cudaMemcpyAsync(d_planes_own + w0, src.pH + h0, nw * 4, cudaMemcpyHostToDevice, cs);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_planes_own + span_words + w0, src.pL + h0, nw * 4, cudaMemcpyHostToDevice, cs);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_planes_own + 2 * span_words + w0, src.pN + h0, nw * 4, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess && !runs_mode)
+            e = cudaMemcpyAsync(d_planes_own + 2 * span_words + w0, src.pN + h0, nw * 4, cudaMemcpyHostToDevice, cs);
         return e;
     };
     auto free_sources = [&]() {
         if (d_src_own) ctx_free(d_src_own);
         if (d_planes_own) ctx_free(d_planes_own);
+        if (d_mask_own) ctx_free(d_mask_own);
+        if (d_runs) ctx_free(d_runs);
         if (d_src_start) ctx_free(d_src_start);
-        d_src_own = nullptr; d_planes_own = nullptr; d_src_start = nullptr;
+        d_src_own = nullptr; d_planes_own = nullptr; d_mask_own = nullptr; d_runs = nullptr; d_src_start = nullptr;
     };
     std::vector<uint64_t> rel(n_records);                                // record starts relative to the device view
     for (uint32_t r = 0; r < n_records; ++r) rel[r] = s->h_rec_len[r] ? starts[r] - (packed ? 0 : src_base) : 0;
@@ -473,6 +497,19 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
         if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st);
         if (e == cudaSuccess && !ex_layout.empty())
             e = cudaMemcpyAsync(s->ex_key, ex_layout.data(), ex_layout.size() * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && runs_mode) {                             // mask plane of the span: zero, then the runs
+            const size_t mask_words = on_device ? (size_t)((src_hi + 31) / 32 + 1) : (size_t)span_words;
+            e = cudaMemsetAsync(const_cast<uint32_t *>(d_pN), 0, mask_words * 4, st);
+            const uint32_t nr = (uint32_t)(runs_rel.size() / 2);
+            if (e == cudaSuccess && nr) {
+                rc = dev_alloc(&d_runs, runs_rel.size());
+                if (!rc) e = cudaMemcpyAsync(d_runs, runs_rel.data(), runs_rel.size() * 8, cudaMemcpyHostToDevice, st);
+                if (!rc && e == cudaSuccess) {
+                    mask_runs_kernel<<<(nr + 7) / 8, 256, 0, st>>>(d_runs, nr, const_cast<uint32_t *>(d_pN));
+                    e = cudaGetLastError();
+                }
+            }
+        }
     }
     // one launch of the packer over layout words [w_lo, w_hi)
     auto launch_pack = [&](uint32_t w_lo, uint32_t w_hi) -> cudaError_t {
@@ -653,6 +690,34 @@ extern "C" int crf_seq_load_packed_ranges(crf_ctx *c, const uint32_t *H, const u
     LoadSource src;
     src.pH = H; src.pL = L; src.pN = NM; src.exotic = exotic; src.n_exotic = n_exotic;
     return load_checked(c, src, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, planes_on_device, out, "crf_seq_load_packed");
+}
+
+extern "C" int crf_seq_load_packed_runs_ranges(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint64_t *runs,
+                                               uint64_t n_runs, const uint64_t *exotic, uint64_t n_exotic,
+                                               const uint64_t *starts, const uint64_t *lengths, const uint64_t *own_lo,
+                                               const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
+                                               int planes_on_device, crf_seq **out) {
+    if (!H || !L) { set_err("crf_seq_load_packed_runs: null plane"); return CRF_ERR_ARG; }
+    if (n_runs && !runs) { set_err("crf_seq_load_packed_runs: null run list"); return CRF_ERR_ARG; }
+    for (uint64_t i = 0; i < n_runs; ++i)
+        if (runs[2 * i] >= runs[2 * i + 1] || (i && runs[2 * i] < runs[2 * i - 1])) {
+            set_err("crf_seq_load_packed_runs: runs must be non-empty, ascending and disjoint (run %llu)", (unsigned long long)i);
+            return CRF_ERR_ARG;
+        }
+    LoadSource src;
+    src.pH = H; src.pL = L; src.pN = H;      // (pN is not read in runs mode; non-null for the argument check)
+    src.exotic = exotic; src.n_exotic = n_exotic;
+    src.nm_runs = runs; src.n_runs = n_runs; src.runs_mode = true;
+    return load_checked(c, src, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, planes_on_device, out, "crf_seq_load_packed_runs");
+}
+
+extern "C" int crf_seq_load_packed_runs(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint64_t *runs, uint64_t n_runs,
+                                        const uint64_t *exotic, uint64_t n_exotic, const uint64_t *offsets, uint32_t n_records,
+                                        uint32_t max_motif_cap, int planes_on_device, crf_seq **out) {
+    std::vector<uint64_t> lengths;
+    CHECK(offsets_to_lengths(offsets, n_records, lengths, "crf_seq_load_packed_runs"));
+    return crf_seq_load_packed_runs_ranges(c, H, L, runs, n_runs, exotic, n_exotic, offsets, lengths.data(), nullptr, nullptr,
+                                           n_records, max_motif_cap, planes_on_device, out);
 }
 
 extern "C" int crf_seq_load_packed(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint32_t *NM,
@@ -1523,6 +1588,7 @@ static cudaError_t preload_kernels() {
     if (e == cudaSuccess) e = preload(scan_kernel<16>);
     if (e == cudaSuccess) e = preload(pack_kernel);
     if (e == cudaSuccess) e = preload(repack_kernel);
+    if (e == cudaSuccess) e = preload(mask_runs_kernel);
     if (e == cudaSuccess) e = preload(exotic_apply_kernel);
     if (e == cudaSuccess) e = preload(tile_offsets_kernel);
     if (e == cudaSuccess) e = preload(spill_sort_small_kernel);

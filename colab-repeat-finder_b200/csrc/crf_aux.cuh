@@ -139,6 +139,22 @@ __global__ void __launch_bounds__(256) repack_kernel(const RepackParams p) {
     p.X[w] = 0;
 }
 
+// runs mode of a packed load: the mask plane from the sorted runs of masked positions [runs[2i], runs[2i+1]); one warp per
+// run (its lanes stride over the run's words; a genome has a few hundred long N blocks, a read set millions of single N's)
+__global__ void __launch_bounds__(256) mask_runs_kernel(const uint64_t *runs, uint32_t n_runs, uint32_t *NM) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= n_runs) return;
+    const uint64_t a = runs[2 * r], b = runs[2 * r + 1];
+    const uint64_t w_first = a >> 5, w_last = (b - 1) >> 5;
+    for (uint64_t w = w_first + lane; w <= w_last; w += 32) {
+        uint32_t m = 0xFFFFFFFFu;
+        if (w == w_first) m &= 0xFFFFFFFFu << (uint32_t)(a & 31);
+        if (w == w_last && (b & 31)) m &= (1u << (uint32_t)(b & 31)) - 1u;
+        if (w == w_first || w == w_last) atomicOr(&NM[w], m);   // an edge word may be shared with the neighbouring run
+        else NM[w] = m;
+    }
+}
+
 // exotic symbols of a packed load: (layout position << 8 | letter), already sorted: mark them in X and give them the
 // letter's filler code (equal letters -> equal codes, pack_kernel)
 __global__ void __launch_bounds__(256) exotic_apply_kernel(const uint64_t *ex_key, uint32_t n, uint32_t *H, uint32_t *L, uint32_t *X) {

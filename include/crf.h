@@ -79,6 +79,19 @@ int crf_seq_load_packed_ranges(crf_ctx *ctx, const uint32_t *H, const uint32_t *
                                const uint64_t *exotic, uint64_t n_exotic, const uint64_t *starts, const uint64_t *lengths,
                                const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
                                int planes_on_device, crf_seq **seq);
+/* The same with the mask handed over as RUNS instead of a plane: runs[2i], runs[2i+1] = the i-th maximal block of masked
+ * positions [from, to), ascending and disjoint (crf_mask_runs makes them from an NM plane).  A genome's N's are a few hundred
+ * long blocks, so 0.25 bytes per base cross PCIe; the device rebuilds the plane (mask_runs_kernel). */
+int crf_seq_load_packed_runs(crf_ctx *ctx, const uint32_t *H, const uint32_t *L, const uint64_t *runs, uint64_t n_runs,
+                             const uint64_t *exotic, uint64_t n_exotic, const uint64_t *offsets, uint32_t n_records,
+                             uint32_t max_motif_cap, int planes_on_device, crf_seq **seq);
+int crf_seq_load_packed_runs_ranges(crf_ctx *ctx, const uint32_t *H, const uint32_t *L, const uint64_t *runs, uint64_t n_runs,
+                                    const uint64_t *exotic, uint64_t n_exotic, const uint64_t *starts,
+                                    const uint64_t *lengths, const uint64_t *own_lo, const uint64_t *own_hi,
+                                    uint32_t n_records, uint32_t max_motif_cap, int planes_on_device, crf_seq **seq);
+/* Host only: the maximal runs of set bits of an NM plane over [0, n_bases) (threaded).  *n_runs = how many there are
+ * (CRF_ERR_CAPACITY if more than cap pairs: call again with a longer list). */
+int crf_mask_runs(const uint32_t *NM, uint64_t n_bases, uint32_t n_threads, uint64_t *runs, uint64_t cap, uint64_t *n_runs);
 /* Host-only packer for the above (threaded; AVX2 when the CPU has it).  H, L, NM: ceil(n_bases / 32) words each, written
  * in full (positions beyond n_bases are masked).  exotic: room for exotic_cap entries; *n_exotic = how many there are
  * (CRF_ERR_CAPACITY if more than exotic_cap: call again with a longer list).  n_threads = 0: up to 16. */

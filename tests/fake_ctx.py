@@ -107,6 +107,11 @@ def unpack_planes(planes):
             (np.asarray(a)[:nw] if not isinstance(a, int) else np.ctypeslib.as_array((ctypes.c_uint32 * nw).from_address(a)))
         return ((a[:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8).reshape(-1)[:n]
     h, l, nm = bits(planes.H_ptr), bits(planes.L_ptr), bits(planes.NM_ptr)
+    if planes.runs is not None:                       # the runs must say what the plane says
+        from_runs = np.zeros(n, np.uint8)
+        for a, b in planes.runs.tolist():
+            from_runs[a:b] = 1
+        assert np.array_equal(from_runs, nm)
     out = np.frombuffer(b"ACGT", dtype=np.uint8)[(h << 1) | l].copy()
     out[nm == 1] = ord("N")
     for key in planes.exotic.tolist():

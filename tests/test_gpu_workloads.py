@@ -353,6 +353,8 @@ def test_packed_load_equals_ascii_load_equals_oracle(mods):
     a = rows(ctx.load(text, offsets, max_motif_cap=50))
     b = rows(ctx.load_packed(pk, offsets, max_motif_cap=50))
     assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 300
+    c = rows(ctx.load_packed(pk.with_runs(), offsets, max_motif_cap=50))      # the mask as runs instead of a plane
+    assert pk.runs.shape[0] > 20 and all(np.array_equal(x, y) for x, y in zip(a, c))
     want = []
     for r, rec in enumerate(recs):
         want += [(r, s, e, len(m)) for s, e, m in oracle.detect_repeats_by_k(rec, ns(**DEFAULTS))]
@@ -365,6 +367,8 @@ def test_packed_load_equals_ascii_load_equals_oracle(mods):
     a = rows(ctx.load(bases, r_off, max_motif_cap=20), 20)
     b = rows(ctx.load_packed(pk, r_off, max_motif_cap=20), 20)
     assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 2000
+    c = rows(ctx.load_packed(pk.with_runs(), r_off, max_motif_cap=20), 20)    # thousands of single-position runs
+    assert pk.runs.shape[0] > 5000 and all(np.array_equal(x, y) for x, y in zip(a, c))
 
     # 3. the pipelined upload (> 1 Gbp of planes' positions), records in order; then overlapping out-of-order ranges
     #    with owned sub-ranges and empty records
@@ -384,3 +388,9 @@ def test_packed_load_equals_ascii_load_equals_oracle(mods):
     a = rows(ctx.load_ranges(big.data_ptr(), starts, lens, own_lo, own_hi, max_motif_cap=50, on_device=True))
     b = rows(ctx.load_packed(pk, max_motif_cap=50, ranges=(starts, lens, own_lo, own_hi)))
     assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 500_000
+    pk.with_runs()                                                             # runs mode: pipelined, then ranges
+    c = rows(ctx.load_packed(pk, max_motif_cap=50, ranges=(starts, lens, own_lo, own_hi)))
+    assert all(np.array_equal(x, y) for x, y in zip(a, c))
+    d = rows(ctx.load_packed(pk, offs, max_motif_cap=50))
+    want_all = rows(ctx.load(big.data_ptr(), offs, max_motif_cap=50, on_device=True))
+    assert all(np.array_equal(x, y) for x, y in zip(want_all, d))

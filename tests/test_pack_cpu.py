@@ -61,6 +61,22 @@ def test_pack_ascii_matches_the_documented_format(scalar, monkeypatch):
             assert (~is_plain).sum() == pk.exotic.size
 
 
+def test_mask_runs_are_the_maximal_blocks_of_the_plane():
+    rng = np.random.default_rng(8)
+    for n in [0, 1, 31, 32, 33, 64, 1000, 100_003, 9_000_017]:
+        arr = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n, p=[.24, .24, .24, .24, .04]).astype(np.uint8)
+        if n > 5000:
+            arr[100:3000] = ord("N")                          # long blocks, one across the piece boundaries of the threads
+            arr[n // 2:n // 2 + 70_000] = ord("n")
+            arr[n - 777:] = ord("N")                          # ... and one up to the last base
+        pk = _cabi.pack_ascii(arr, n_threads=4).with_runs(4)
+        masked = np.isin(arr, [ord("N"), ord("n")])
+        d = np.diff(np.concatenate([[0], masked.astype(np.int8), [0]]))
+        want = np.stack([np.flatnonzero(d == 1), np.flatnonzero(d == -1)], 1).astype(np.uint64)
+        assert np.array_equal(pk.runs, want), n
+        assert pk.nbytes == 8 * ((n + 31) // 32) + 16 * len(want)
+
+
 def test_fasta_reader_hands_out_packed_planes(tmp_path):
     rng = np.random.default_rng(5)
     recs = [rng.choice(ALPHABET, size=n, p=WEIGHTS).astype(np.uint8) for n in (70_001, 0, 33, 120_000)]
