@@ -16,6 +16,33 @@ import perfect_repeat_finder as prf  # noqa: E402
 from tests.helpers import ns, random_seq  # noqa: E402
 
 
+def packed_vs_ascii(seq, kmin, kmax, min_repeats, min_span, rng):
+    """The same text split into random records, loaded as ASCII, as host-packed planes and as planes + mask runs
+    (crf_seq_load_ascii / crf_seq_load_packed / crf_seq_load_packed_runs): the raw rows of one scan must be identical."""
+    import numpy as np
+    from crf_b200 import _cabi, api
+    raw = np.frombuffer(seq.encode("latin-1"), dtype=np.uint8)
+    cuts = sorted({0, len(seq), *(rng.randint(0, len(seq)) for _ in range(rng.choice([0, 1, 3, 9])))})
+    offsets = np.array(cuts, dtype=np.uint64)
+    ctx = api.get_context()
+
+    def rows(s):
+        with s:
+            n = s.scan(kmin, kmax, min_repeats, min_span)
+            return [a.tolist() for a in s.fetch(n)]
+
+    a = rows(ctx.load(raw, offsets, max_motif_cap=kmax))
+    pk = _cabi.pack_ascii(raw)
+    b = rows(ctx.load_packed(pk, offsets, max_motif_cap=kmax))
+    c = rows(ctx.load_packed(pk.with_runs(), offsets, max_motif_cap=kmax))
+    if a != b or a != c:
+        path = f"/tmp/fuzz_fail_packed_{len(seq)}.txt"
+        with open(path, "w") as f:
+            f.write(repr((seq, cuts, kmin, kmax, min_repeats, min_span)))
+        print("MISMATCH packed vs ascii", len(seq), cuts, kmin, kmax, min_repeats, min_span, "saved", path)
+        sys.exit(1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120)
@@ -23,7 +50,7 @@ def main():
     args = ap.parse_args()
     rng = random.Random(args.seed)
     t_end = time.time() + args.seconds
-    n_cases = n_rows = 0
+    n_cases = n_rows = n_packed = 0
     while time.time() < t_end:
         n = rng.choice([rng.randint(0, 300), rng.randint(300, 5000), rng.randint(5000, 120000), rng.randint(60000, 400000)])
         seq = random_seq(rng, n, exotic=rng.random() < 0.3)
@@ -43,7 +70,8 @@ def main():
             fs.update(interval_start_0based=a, interval_end=rng.randint(a, len(seq)))
         knobs = rng.choice([{}, {}, {"words_per_thread": 1}, {"words_per_thread": 2}, {"words_per_thread": 4},
                             {"words_per_thread": 16}, {"words_per_thread": 1, "tile_out_cap": 3},
-                            {"walk_limit_words": 1}, {"tile_out_cap": 1, "walk_limit_words": 2}])
+                            {"walk_limit_words": 1}, {"tile_out_cap": 1, "walk_limit_words": 2},
+                            {"flags": 2}, {"flags": 8}, {"flags": 2, "tile_out_cap": 2, "walk_limit_words": 1}])
         try:
             by_k = not interval and fs["min_repeats"] > 1     # the by-k variant shares no dict: no keep-shorter rule
             want = (oracle.detect_repeats_by_k if by_k else oracle.detect_repeats)(seq, ns(**fs))
@@ -64,9 +92,12 @@ def main():
                 d = next((i for i, (x, y) in enumerate(zip(got + [None], want + [None])) if x != y), None)
                 print(" first difference at row", d, (got + [None])[d], (want + [None])[d], "saved", path)
             sys.exit(1)
+        if want is not None and not interval and len(seq) > kmax and rng.random() < 0.35:
+            packed_vs_ascii(seq, kmin, kmax, fs["min_repeats"], fs["min_span"], rng)
+            n_packed += 1
         n_cases += 1
         n_rows += len(want) if want else 0
-    print(f"fuzz ok: {n_cases} cases, {n_rows} rows compared, seed {args.seed}")
+    print(f"fuzz ok: {n_cases} cases ({n_packed} also through the packed loaders), {n_rows} rows compared, seed {args.seed}")
 
 
 if __name__ == "__main__":
