@@ -104,7 +104,10 @@ def _interval_stop_position(ctx, s, end_position, kmin, kmax, knobs):
         return None
     window = 256
     while True:
-        ws = max(0, E + 1 - kmax)
+        # tracker k at t has its last compare at j = min(t, L-k-1) and needs the k compares ending there: the window
+        # starts k before that -- before E+1 for most, but up to 2k before the END for a tracker that has already
+        # stopped (L-k-1 < E+1, i.e. the interval ends within kmax of the end of the sequence)
+        ws = max(0, min(E + 1 - kmax, L - 2 * kmax))
         hi_t = min(L - 1, E + window)                   # last t examined
         we = min(L, hi_t + 1 + kmax)
         with ctx.load(s[ws:we], max_motif_cap=kmax) as seq:

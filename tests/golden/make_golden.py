@@ -7,7 +7,7 @@ tests as a sanity check, then records detect_repeats() outputs for
 
   * kat.json   -- the 32 known-answer calls of perfect_repeat_finder_tests.py:31-143, restated
                   as data (inputs + the reference's outputs),
-  * fuzz_full.json, fuzz_interval.json, fuzz_minrep1.json, fuzz_interval_long.json -- seeded random cases,
+  * fuzz_full.json, fuzz_interval.json, fuzz_minrep1.json, fuzz_interval_long.json, fuzz_interval_tail.json -- seeded random cases,
   * primitivity.json -- consists_of_perfect_repeats() on seeded strings.
 
 The reference cannot travel to the GPU box, so these files are what pins the oracle
@@ -141,6 +141,28 @@ def fuzz_interval_long(ref, seed, count):
     return out
 
 
+def fuzz_interval_tail(ref, seed, count):
+    """Interval mode where interval_end lies within 2 * max_motif_size of the END of the sequence and the tail is periodic:
+    trackers of large motif sizes have already stopped (trk:50) while still "in the middle of a repeat", so the lock-step
+    loop runs on to the end (prf:70-74).  min_repeats 1 / 2 / 3."""
+    rng = random.Random(seed)
+    out = []
+    for _ in range(count):
+        seq = random_seq(rng, 400)
+        kmin = rng.choice([1, 2, 3, 7])
+        kmax = kmin + rng.choice([1, 5, 15, 30, 49])
+        unit = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, kmax)))
+        seq = seq + unit * rng.randint(2, 6) + unit[:rng.randint(0, len(unit))] + (random_seq(rng, 12) if rng.random() < 0.4 else "")
+        b = max(0, len(seq) - rng.randint(0, 2 * kmax + 2))
+        a = rng.randint(0, b)
+        min_repeats = rng.choice([1, 2, 2, 3])
+        min_span = rng.choice([2, 9, 9, 20])
+        kw = dict(min_motif_size=kmin, max_motif_size=kmax, min_repeats=min_repeats, min_span=min_span,
+                  interval_start_0based=a, interval_end=b)
+        out.append(run_case(ref, seq, kw))
+    return out
+
+
 def primitivity_cases(seed, count):
     """Inputs / outputs of the reference's consists_of_perfect_repeats (utils/perfect_repeat_tracker.py:108-142)."""
     sys.path.insert(0, REF)
@@ -176,6 +198,7 @@ def main():
     dump("fuzz_interval.json", fuzz(ref, 2002, 400, "interval"))
     dump("fuzz_minrep1.json", fuzz(ref, 3003, 300, "minrep1"))
     dump("fuzz_interval_long.json", fuzz_interval_long(ref, 4004, 40))
+    dump("fuzz_interval_tail.json", fuzz_interval_tail(ref, 6006, 240))
     dump("primitivity.json", primitivity_cases(5005, 600))
 
 

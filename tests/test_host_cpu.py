@@ -409,6 +409,48 @@ def test_detect_repeats_host_logic_against_reference_vectors(monkeypatch, name):
     assert n_rows > 30
 
 
+def test_interval_ending_near_the_end_of_the_sequence(monkeypatch):
+    """interval_end within 2 * max_motif_size of the END of a periodic tail: trackers of large motif sizes have stopped
+    (trk:50) but still count as mid-repeat, so prf:70-74 runs the loop to the end.  The probe window of
+    api._interval_stop_position must reach back 2k from the end for them; vectors from the reference, all three
+    min_repeats modes, then the stop position alone against the literal loop on seeded strings."""
+    import random
+    from crf_b200 import api
+    from tests.helpers import load_golden, ns
+    monkeypatch.setattr(api, "get_context", lambda device=None: _ClosedFormCtx())
+    closed_form_scan = api.scan_arrays
+
+    def scan_arrays(s, kmin, kmax, min_repeats, span, device=None, **kw):
+        if min_repeats == 1:
+            return _runs_single_copy(bytes(s), kmin, kmax, span)
+        return closed_form_scan(s, kmin, kmax, min_repeats, span, device=device, **kw)
+
+    monkeypatch.setattr(api, "scan_arrays", scan_arrays)
+    n_rows = n_single = 0
+    for i, case in enumerate(load_golden("fuzz_interval_tail.json")):
+        fs = ns(**case["settings"])
+        assert "raises" not in case
+        assert api.detect_repeats(case["seq"], fs) == [tuple(r) for r in case["result"]], (i, case["settings"])
+        n_rows += len(case["result"])
+        n_single += fs.min_repeats == 1
+    assert n_rows > 1000 and n_single > 40
+    rng = random.Random(5)
+    n_to_end = 0
+    for _ in range(1500):
+        s = "".join(rng.choice(rng.choice(["AC", "ACGT", "ACGTN"])) for _ in range(rng.randint(2, 300)))
+        if rng.random() < 0.7:
+            unit = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 40)))
+            pos = rng.randint(0, len(s))
+            s = s[:pos] + unit * rng.randint(2, 30) + ("" if rng.random() < 0.5 else s[pos:])
+        kmin = rng.choice([1, 2, 3, 7])
+        kmax = kmin + rng.choice([0, 1, 5, 15, 30, 49])
+        E = rng.choice([rng.randint(0, len(s)), max(0, len(s) - rng.randint(0, 2 * kmax + 2))])
+        want = _stop_literal(s.encode(), E, kmin, kmax)
+        assert api._interval_stop_position(_ClosedFormCtx(), s.encode(), E, kmin, kmax, {}) == want, (s, E, kmin, kmax)
+        n_to_end += want is None and E < len(s) - 1
+    assert n_to_end > 100
+
+
 def test_write_rows_reports_a_short_write(tmp_path):
     """crf_write_rows (host only): rows as text, and a device that takes no more bytes is an OSError, not a silently
     truncated BED file."""

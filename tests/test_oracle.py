@@ -14,7 +14,8 @@ def _run(case, fn=oracle.detect_repeats):
     return fn(case["seq"], ns(**case["settings"]))
 
 
-@pytest.mark.parametrize("name", ["kat.json", "fuzz_full.json", "fuzz_interval.json", "fuzz_minrep1.json", "fuzz_interval_long.json"])
+@pytest.mark.parametrize("name", ["kat.json", "fuzz_full.json", "fuzz_interval.json", "fuzz_minrep1.json", "fuzz_interval_long.json",
+                                  "fuzz_interval_tail.json"])
 def test_oracle_matches_reference_golden(name):
     cases = load_golden(name)
     assert cases
