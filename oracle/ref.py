@@ -93,3 +93,64 @@ def run_slices(pool, slices, fs):
     out = pool.map(_worker, [(s, fs) for s in slices], chunksize=1)
     wall = time.perf_counter() - t0
     return wall, [o[0] for o in out], [o[1] for o in out]
+
+
+# ---- the reference's command line (prf:83-179), for file-level parity of the CLI ------------------------------
+class _MiniFasta:
+    """What main() uses of pyfastx.Fasta (prf:117-137): iteration over records with .name / .seq, `name in fa`,
+    fa[name].seq.  pyfastx is not installed; this reads the file line by line (plain or gzip), names are the first
+    word of the header, sequence text is kept as written (case included)."""
+
+    def __init__(self, path):
+        import argparse
+        import gzip
+        with open(path, "rb") as f:
+            magic = f.read(2)
+        opener = gzip.open if magic == b"\x1f\x8b" else open
+        self._entries, name, parts = [], None, []
+        with opener(path, "rt") as f:
+            for line in f:
+                line = line.rstrip("\r\n")
+                if line.startswith(">"):
+                    if name is not None:
+                        self._entries.append(argparse.Namespace(name=name, seq="".join(parts)))
+                    name, parts = (line[1:].split() or [""])[0], []
+                elif name is not None:
+                    parts.append(line.strip())
+        if name is not None:
+            self._entries.append(argparse.Namespace(name=name, seq="".join(parts)))
+
+    def __iter__(self):
+        return iter(self._entries)
+
+    def __contains__(self, name):
+        return any(e.name == name for e in self._entries)
+
+    def __getitem__(self, name):
+        return next(e for e in self._entries if e.name == name)
+
+
+def run_main(argv, cwd):
+    """The reference's main() with sys.argv = argv, run in directory `cwd` (it writes <prefix>.bed / .tsv there).
+    Returns (exit status, stdout text); parser.error() exits with 2, an uncaught exception propagates."""
+    import argparse
+    import contextlib
+    import io
+    ref_prf, _ = load()
+    with _lock:
+        saved_argv, saved_cwd, saved_fastx = sys.argv, os.getcwd(), ref_prf.pyfastx
+        out, status = io.StringIO(), 0
+        try:
+            sys.argv = ["perfect_repeat_finder.py"] + [str(a) for a in argv]
+            os.chdir(cwd)
+            ref_prf.pyfastx = argparse.Namespace(Fasta=_MiniFasta)
+            with contextlib.redirect_stdout(out), contextlib.redirect_stderr(io.StringIO()):
+                try:
+                    ref_prf.main()
+                except SystemExit as e:
+                    status = e.code if isinstance(e.code, int) else 1
+        finally:
+            sys.argv = saved_argv
+            os.chdir(saved_cwd)
+            ref_prf.pyfastx = saved_fastx
+        return status, out.getvalue()

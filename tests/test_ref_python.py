@@ -141,3 +141,114 @@ def test_tracker_compat_class_replays_the_reference_tracker():
         assert out_mine == out_ref, (seq, ks, mr, ms, stop)
         checked += len(out_ref)
     assert checked > 100
+
+
+# ---- file-level parity of the command line: the reference's main() (prf:83-179) against crf_b200.cli.main -----------------
+def _cli_fasta(tmp_path, gz):
+    import gzip
+    rng = random.Random(31)
+    records = []
+    for name in ("chr1", "chrUn_gl000220 some description", "scaffold-3"):
+        seq = random_seq(rng, rng.randint(400, 3000), exotic=True)
+        unit = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 30)))
+        pos = rng.randint(0, len(seq))
+        seq = seq[:pos] + unit * rng.randint(3, 40) + seq[pos:]
+        seq = "".join(c.lower() if rng.random() < 0.2 else c for c in seq)
+        records.append((name, seq))
+    text = "".join(f">{n}\n" + "".join(s[i:i + 70] + "\n" for i in range(0, len(s), 70)) for n, s in records)
+    path = tmp_path / ("in.fa.gz" if gz else "in.fasta")
+    (gzip.open(path, "wt") if gz else open(path, "wt")).write(text)
+    return path, [(n.split()[0], s) for n, s in records]
+
+
+def _cli_argument_lists(path, records):
+    rng = random.Random(32)
+    out = []
+    for i in range(36):
+        name, seq = rng.choice(records)
+        a = rng.choice([0, rng.randint(0, len(seq)), max(0, len(seq) - rng.randint(0, 120))])
+        b = rng.choice([rng.randint(a, len(seq)), len(seq), len(seq) + 500, a])
+        argv = [str(path), "--interval", f"{name}:{a}-{b}"]
+        if rng.random() < 0.7:
+            kmin = rng.choice([1, 2, 3])
+            argv += ["-min", str(kmin), "-max", str(kmin + rng.choice([0, 5, 30, 49]))]
+        if rng.random() < 0.5:
+            argv += ["--min-repeats", str(rng.choice([1, 2, 3, 4])), "--min-span", str(rng.choice([2, 9, 12, 30]))]
+        if rng.random() < 0.5:
+            argv += ["-o", f"sub/dir/prefix{i}"]                     # the BED file still lands in the working directory
+        out.append(argv)
+    for raw in ("ACGTACGTACGTTTTTTTTTT", "cagcagcagcagNNNNNNcagcag" * 3, "A" * 40, "ACGT", "nnnnnnnn", "TTTTTTTTTNACACACAC"):
+        out.append([raw])
+        out.append([raw, "-o", "named", "-min", "2", "-max", "6", "--min-repeats", "2", "--min-span", "4"])
+    out += [[str(path), "--interval", "chr1:5"], [str(path), "--interval", "nope:1-50"], ["ACGT", "--interval", "chr1:1-5"],
+            ["ACGTXZ"], ["ACGT", "-min", "0"], ["ACGT", "-min", "5", "-max", "4"], ["ACGT", "--min-repeats", "0"],
+            ["ACGT", "--min-span", "0"]]
+    return out
+
+
+def _run_dropin_cli(cli_main, argv, cwd, capsys):
+    saved = os.getcwd()
+    os.chdir(cwd)
+    try:
+        capsys.readouterr()
+        try:
+            status = cli_main([str(a) for a in argv])
+        except SystemExit as e:
+            status = e.code
+        return status, capsys.readouterr().out
+    finally:
+        os.chdir(saved)
+
+
+def _compare_cli(cli_main, tmp_path, capsys, refusal=()):
+    n_files = n_errors = 0
+    for gz in (False, True):
+        path, records = _cli_fasta(tmp_path, gz)
+        for i, argv in enumerate(_cli_argument_lists(path, records)):
+            d_ref, d_mine = tmp_path / f"ref{int(gz)}_{i}", tmp_path / f"mine{int(gz)}_{i}"
+            d_ref.mkdir(), d_mine.mkdir()
+            try:
+                want = ref.run_main(argv, d_ref)
+            except (AssertionError, IndexError) as e:
+                want = type(e).__name__
+            try:
+                got = _run_dropin_cli(cli_main, argv, d_mine, capsys)
+            except (AssertionError, IndexError) as e:
+                got = type(e).__name__
+            except refusal:
+                continue
+            assert got == want, argv
+            files_ref = sorted(p.name for p in d_ref.iterdir())
+            assert sorted(p.name for p in d_mine.iterdir()) == files_ref, argv
+            for name in files_ref:
+                assert (d_mine / name).read_bytes() == (d_ref / name).read_bytes(), (argv, name)
+            n_files += len(files_ref)
+            n_errors += want == (2, "") or isinstance(want, str)
+    assert n_files >= 80 and n_errors >= 16
+
+
+@needs_ref
+def test_cli_files_and_stdout_equal_the_reference_cli_host_side(tmp_path, capsys, monkeypatch):
+    """The reference's own main() (with a line-by-line stand-in for pyfastx) and the drop-in CLI on the same argument lists:
+    same exit status, same stdout, same BED / TSV bytes -- --interval on plain and gzipped FASTA (mixed case, N blocks, IUPAC
+    letters, intervals clamped to the record, min_repeats 1..4), raw strings, every parser.error path.  Here the GPU scan is
+    the closed-form stand-in (host glue only); the -m gpu twin below runs the real thing."""
+    from crf_b200 import api, cli
+    from tests import test_host_cpu as stand_in
+    monkeypatch.setattr(api, "get_context", lambda device=None: stand_in._ClosedFormCtx())
+    closed_form = api.scan_arrays
+
+    def scan_arrays(s, kmin, kmax, min_repeats, span, device=None, **kw):
+        if min_repeats == 1:
+            return stand_in._runs_single_copy(bytes(s), kmin, kmax, span)
+        return closed_form(s, kmin, kmax, min_repeats, span, device=device, **kw)
+
+    monkeypatch.setattr(api, "scan_arrays", scan_arrays)
+    _compare_cli(cli.main, tmp_path, capsys, refusal=(NotImplementedError,))
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cli_files_and_stdout_equal_the_reference_cli(tmp_path, capsys):
+    from crf_b200 import cli
+    _compare_cli(cli.main, tmp_path, capsys, refusal=(NotImplementedError,))
