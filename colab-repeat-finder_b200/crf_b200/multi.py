@@ -201,13 +201,15 @@ class RankScan:
                 self.seqs[p].close()
                 self.seqs[p] = None
             if len(starts):
+                if base_offset:                                      # (a reads share has millions of starts: no copy without need)
+                    starts = starts - np.uint64(base_offset)
                 if isinstance(bases, _cabi.PackedPlanes):          # planes packed on the host: 0.375 B/bp over PCIe
                     if base_offset % 32:
                         raise ValueError("packed planes must start at a multiple of 32 positions")
                     seq = self.ctx.load_packed(bases, max_motif_cap=kmax,
-                                               ranges=(starts - np.uint64(base_offset), lens, own_lo, own_hi))
+                                               ranges=(starts, lens, own_lo, own_hi))
                 else:
-                    seq = self.ctx.load_ranges(bases, starts - np.uint64(base_offset), lens, own_lo, own_hi,
+                    seq = self.ctx.load_ranges(bases, starts, lens, own_lo, own_hi,
                                                max_motif_cap=kmax, on_device=on_device)
                 if self.reads:
                     if self.world > 1:

@@ -5,10 +5,13 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <utility>
 #include <new>
@@ -69,7 +72,30 @@ struct crf_ctx {
     unsigned long long *h_counters = nullptr;           // SLOTS x C_COUNT
     int next_slot = 0;
     int n_xchg = 0;                                     // exchange blocks alive on this context (a rank of a multi-GPU job)
+    // per-record tables of the load in progress (source start, length, layout offset, owned range): built in page-locked
+    // memory that grows and stays -- a reads file has 10^7 records, and fresh pageable vectors for them cost more in page
+    // faults and staged copies than the whole upload.  A load is done with it when it returns (it synchronises the stream).
+    void *h_tab = nullptr;
+    size_t h_tab_bytes = 0;
+    bool h_tab_pinned = false;
 };
+static void *ctx_tables(crf_ctx *c, size_t bytes) {
+    if (bytes <= c->h_tab_bytes) return c->h_tab;
+    if (c->h_tab) { if (c->h_tab_pinned) cudaFreeHost(c->h_tab); else free(c->h_tab); }
+    c->h_tab = nullptr; c->h_tab_bytes = 0;
+    size_t want = (size_t)1 << 16;
+    while (want < bytes) want <<= 1;
+    void *q = nullptr;
+    if (cudaHostAlloc(&q, want, cudaHostAllocDefault) == cudaSuccess) c->h_tab_pinned = true;
+    else {                                              // no page-locked memory left: pageable works too, only slower
+        cudaGetLastError();
+        q = malloc(want);
+        c->h_tab_pinned = false;
+    }
+    if (!q) return nullptr;
+    c->h_tab = q; c->h_tab_bytes = want;
+    return q;
+}
 static const size_t CACHE_LIMIT_BYTES = 24ull << 30;
 static thread_local crf_ctx *g_ctx = nullptr;          // context of the API call in progress
 
@@ -147,8 +173,7 @@ struct crf_seq {
     uint32_t *d_map_rec = nullptr, *d_map_shift = nullptr;
     uint8_t *d_map_open = nullptr;
     uint32_t *d_open_rows = nullptr;
-    std::vector<uint32_t> h_rec_dev_off;
-    std::vector<uint64_t> h_rec_len;
+    std::vector<uint32_t> h_rec_dev_off, h_rec_len;     // host copies of the two tables: see host_tables()
     uint64_t *ex_key = nullptr;
     uint32_t n_exotic = 0, ex_cap = 0;
     // scan scratch
@@ -245,6 +270,7 @@ extern "C" int crf_ctx_destroy(crf_ctx *c) {
         for (auto &ev : set)
             if (ev) cudaEventDestroy(ev);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_tab) { if (c->h_tab_pinned) cudaFreeHost(c->h_tab); else free(c->h_tab); }
     delete c;
     return CRF_OK;
 }
@@ -310,6 +336,7 @@ static void free_seq(crf_seq *s) {
 #define CRF_DEFAULT_KERNEL 0           // scan kernel used when neither a flag nor CRF_SCAN_KERNEL says otherwise:
 #endif                                 // 0 block-tiled, 1 / 2 warp-tiled (1 / 2 sub-tiles), 3 block-tiled with 2 strips per thread
 static const uint32_t EX_CAP = 1u << 22;       // exotic symbols kept per load
+static const uint32_t HOST_TABLES_EAGER = 1u << 16;   // record counts up to this keep host copies of their tables from the load on
 static const uint32_t TILE_WORDS_MAX = 4096;   // THREADS * 16
 static const uint32_t MAX_K = 65535;
 
@@ -331,10 +358,42 @@ struct LoadSource {
     bool packed() const { return pH != nullptr; }
 };
 
+// The two passes over the per-record arrays of a load run on a few threads when there are millions of records.
+static const uint32_t TABLE_SEGS = 8;
+template <class F>
+static void for_record_segments(uint32_t n_records, F fn) {               // fn(segment, first, last)
+    if (n_records < (1u << 20)) { fn(0u, 0u, n_records); return; }
+    std::thread th[TABLE_SEGS];
+    for (uint32_t g = 0; g < TABLE_SEGS; ++g) {
+        const uint32_t lo = (uint32_t)((uint64_t)n_records * g / TABLE_SEGS), hi = (uint32_t)((uint64_t)n_records * (g + 1) / TABLE_SEGS);
+        try {
+            th[g] = std::thread([=]() { fn(g, lo, hi); });
+        } catch (...) {                                                   // no thread to be had: do the segment here
+            fn(g, lo, hi);
+        }
+    }
+    for (auto &t : th)
+        if (t.joinable()) t.join();
+}
+
+// CRF_LOAD_TRACE=1: host-side stage times of a load on stderr (where does a 10 M-record load spend its time)
+struct LoadTrace {
+    bool on = getenv("CRF_LOAD_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[crf load] %-28s %8.3f ms (at %8.3f)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
+
 static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, const uint64_t *lengths,
                      const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
                      int on_device, crf_seq *s) {
     const char *who = src.packed() ? "crf_seq_load_packed" : "crf_seq_load_ascii";
+    LoadTrace trace;
     cudaStream_t st = c->stream;
     s->ctx = c;
     s->n_records = n_records;
@@ -348,25 +407,59 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
     CHECK(dev_alloc(&s->d_counters, C_COUNT));
     s->open_cap = OPEN_CAP_INITIAL;
     CHECK(dev_alloc(&s->d_open_rows, 5 * (size_t)s->open_cap));
+    trace.mark("slot + small allocs");
 
-    // layout: record r at dev_off[r], followed by a gap of max_motif_cap masked positions
-    s->h_rec_dev_off.resize(n_records);
-    s->h_rec_len.resize(n_records);
-    std::vector<uint32_t> len32(n_records);
-    uint64_t pos = 0, total = 0, src_lo = ~0ull, src_hi = 0;
+    // layout: record r at dev_off[r], followed by a gap of max_motif_cap masked positions.
+    // `lengths` may be null: `starts` is then n_records + 1 boundaries (record r = [starts[r], starts[r + 1])).
+    // Pass 1 reads the caller's arrays only: checks, the extent of the source, the size of the layout.
+    auto len_of = [&](uint32_t r) -> uint64_t { return lengths ? lengths[r] : starts[r + 1] - starts[r]; };
+    const bool owned = own_lo && own_hi;
     const uint64_t limit = layout_limit(max_motif_cap);
-    for (uint32_t r = 0; r < n_records; ++r) {
-        const uint64_t len = lengths[r];
-        if (pos > limit || len > limit) { pos = limit + 1; break; }
-        s->h_rec_dev_off[r] = (uint32_t)pos;
-        s->h_rec_len[r] = len;
-        len32[r] = (uint32_t)len;
-        pos += len + max_motif_cap;
-        total += len;
-        if (len) {
-            src_lo = std::min(src_lo, starts[r]);
-            src_hi = std::max(src_hi, starts[r] + len);
+    struct SegSum {
+        uint64_t pos = 0, total = 0, src_lo = ~0ull, src_hi = 0, first_end = 0, last_end = 0;
+        bool ends_sorted = true, too_long = false;
+        uint32_t bad_offsets = 0xFFFFFFFFu, bad_own = 0xFFFFFFFFu;           // first offending record, if any
+    } seg[TABLE_SEGS];
+    for_record_segments(n_records, [&](uint32_t g, uint32_t first, uint32_t last) {
+        SegSum q;
+        uint64_t prev_end = 0;
+        for (uint32_t r = first; r < last; ++r) {
+            if (!lengths && starts[r + 1] < starts[r]) { q.bad_offsets = std::min(q.bad_offsets, r); continue; }
+            const uint64_t len = len_of(r);
+            if (len > limit) { q.too_long = true; continue; }
+            if (owned && (own_lo[r] > own_hi[r] || own_hi[r] > len)) q.bad_own = std::min(q.bad_own, r);
+            q.pos += len + max_motif_cap;
+            q.total += len;
+            const uint64_t end = starts[r] + len;
+            if (r == first) q.first_end = end;
+            else q.ends_sorted &= end >= prev_end;
+            prev_end = end;
+            if (len) {
+                q.src_lo = std::min(q.src_lo, starts[r]);
+                q.src_hi = std::max(q.src_hi, end);
+            }
         }
+        q.last_end = prev_end;
+        seg[g] = q;
+    });
+    uint64_t pos = 0, total = 0, src_lo = ~0ull, src_hi = 0;
+    uint64_t seg_pos[TABLE_SEGS];                                        // layout position where each segment starts
+    bool ends_sorted = true, too_long = false;                           // starts[r] + len non-decreasing in r
+    uint32_t bad_offsets = 0xFFFFFFFFu, bad_own = 0xFFFFFFFFu;
+    const uint32_t n_segs_used = n_records < (1u << 20) ? 1 : TABLE_SEGS;
+    for (uint32_t g = 0; g < n_segs_used; ++g) {
+        seg_pos[g] = pos;
+        pos += seg[g].pos; total += seg[g].total;
+        src_lo = std::min(src_lo, seg[g].src_lo); src_hi = std::max(src_hi, seg[g].src_hi);
+        ends_sorted &= seg[g].ends_sorted && (g == 0 || seg[g].first_end >= seg[g - 1].last_end);
+        too_long |= seg[g].too_long;
+        bad_offsets = std::min(bad_offsets, seg[g].bad_offsets); bad_own = std::min(bad_own, seg[g].bad_own);
+    }
+    if (bad_offsets != 0xFFFFFFFFu) { set_err("%s: offsets must be non-decreasing", who); return CRF_ERR_ARG; }
+    if (too_long) pos = limit + 1;
+    if (pos <= limit && bad_own != 0xFFFFFFFFu) {
+        set_err("%s_ranges: own range of record %u is not inside the record", who, bad_own);
+        return CRF_ERR_ARG;
     }
     if (pos > limit) {
         set_err("%s: the records need more than %llu layout positions (per-load limit, crf_load_limit); split them "
@@ -374,6 +467,7 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
         return CRF_ERR_UNSUPPORTED;
     }
     if (src_lo > src_hi) src_lo = src_hi = 0;
+    trace.mark("layout loop");
     s->layout_len = (uint32_t)pos;
     s->n_words = (s->layout_len + 31) / 32;
     s->n_words_alloc = (s->n_words + TILE_WORDS_MAX - 1) / TILE_WORDS_MAX * TILE_WORDS_MAX + (max_motif_cap >> 5) + 16;
@@ -411,17 +505,19 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
         d_pN = d_mask_own;
     }
     // runs mode: the mask plane of the span is rebuilt on the device from the (few) runs that touch it
-    std::vector<uint64_t> runs_rel;
+    uint64_t run_first = 0, run_last = 0;                                // runs [run_first, run_last) of the caller's list
+    const uint64_t run_lo = on_device ? 0 : src_lo, run_hi = src_hi;
     if (runs_mode) {
-        const uint64_t lo = on_device ? 0 : src_lo, hi = src_hi;
         const uint64_t *rb = src.nm_runs, nr = src.n_runs;
-        uint64_t a = 0, b = nr;                                          // first run that ends after lo
-        while (a < b) { const uint64_t m = (a + b) / 2; if (rb[2 * m + 1] <= lo) a = m + 1; else b = m; }
-        for (uint64_t i = a; i < nr && rb[2 * i] < hi; ++i) {
-            runs_rel.push_back(std::max(rb[2 * i], lo) - lo);
-            runs_rel.push_back(std::min(rb[2 * i + 1], hi) - lo);
-        }
+        uint64_t a = 0, b = nr;                                          // first run that ends after run_lo
+        while (a < b) { const uint64_t m = (a + b) / 2; if (rb[2 * m + 1] <= run_lo) a = m + 1; else b = m; }
+        run_first = a;
+        b = nr;                                                          // first run that starts at or after run_hi
+        while (a < b) { const uint64_t m = (a + b) / 2; if (rb[2 * m] < run_hi) a = m + 1; else b = m; }
+        run_last = a;
     }
+    const uint64_t n_runs_rel = run_last - run_first;
+    trace.mark("source allocs + runs_rel");
     auto copy_span = [&](uint64_t lo, uint64_t n, cudaStream_t cs) -> cudaError_t {    // source positions [src_lo + lo, + n)
         if (!n) return cudaSuccess;
         if (!packed) return cudaMemcpyAsync(d_src_own + lo, src.bases + src_lo + lo, n, cudaMemcpyHostToDevice, cs);
@@ -440,22 +536,39 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
         if (d_src_start) ctx_free(d_src_start);
         d_src_own = nullptr; d_planes_own = nullptr; d_mask_own = nullptr; d_runs = nullptr; d_src_start = nullptr;
     };
-    std::vector<uint64_t> rel(n_records);                                // record starts relative to the device view
-    for (uint32_t r = 0; r < n_records; ++r) rel[r] = s->h_rec_len[r] ? starts[r] - (packed ? 0 : src_base) : 0;
-    std::vector<uint32_t> olo, ohi;
-    if (own_lo && own_hi) {
-        olo.resize(n_records);
-        ohi.resize(n_records);
-        for (uint32_t r = 0; r < n_records; ++r) {
-            if (own_lo[r] > own_hi[r] || own_hi[r] > lengths[r]) {
-                set_err("%s_ranges: own range of record %u is not inside the record", who, r);
-                free_sources();
-                return CRF_ERR_ARG;
-            }
-            olo[r] = s->h_rec_dev_off[r] + (uint32_t)own_lo[r];
-            ohi[r] = s->h_rec_dev_off[r] + (uint32_t)own_hi[r];
+    // Pass 2 fills the tables the kernels read, in the context's page-locked arena: source start relative to the device view,
+    // length, layout offset, owned range in layout positions
+    const size_t n8 = ((size_t)n_records * 4 + 7) & ~(size_t)7;           // bytes of one 32-bit table, 8-byte aligned
+    const size_t tab_bytes = (size_t)n_records * 8 + (owned ? 4 : 2) * n8;
+    uint8_t *tab = (uint8_t *)ctx_tables(c, tab_bytes + (size_t)n_runs_rel * 16);
+    if (!tab) { free_sources(); set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    uint64_t *rel = (uint64_t *)tab;
+    uint32_t *len32 = (uint32_t *)(tab + (size_t)n_records * 8), *dev_off = (uint32_t *)((uint8_t *)len32 + n8);
+    uint32_t *olo = owned ? (uint32_t *)((uint8_t *)dev_off + n8) : nullptr, *ohi = owned ? (uint32_t *)((uint8_t *)olo + n8) : nullptr;
+    uint64_t *runs_rel = (uint64_t *)(tab + tab_bytes);                  // the mask runs that touch the span, relative to it
+    for_record_segments(n_records, [&](uint32_t g, uint32_t first, uint32_t last) {
+        const uint64_t view = packed ? 0 : src_base;
+        uint64_t at = seg_pos[g];
+        for (uint32_t r = first; r < last; ++r) {
+            const uint64_t len = len_of(r);
+            rel[r] = len ? starts[r] - view : 0;
+            len32[r] = (uint32_t)len;
+            dev_off[r] = (uint32_t)at;
+            if (owned) { olo[r] = (uint32_t)(at + own_lo[r]); ohi[r] = (uint32_t)(at + own_hi[r]); }
+            at += len + max_motif_cap;
         }
+    });
+    for (uint64_t i = 0; i < n_runs_rel; ++i) {
+        const uint64_t *rb = src.nm_runs + 2 * (run_first + i);
+        runs_rel[2 * i] = std::max(rb[0], run_lo) - run_lo;
+        runs_rel[2 * i + 1] = std::min(rb[1], run_hi) - run_lo;
     }
+    // host copies for crf_run_end / crf_seq_set_output_map: now for an ordinary record count, on first use for millions
+    if (n_records <= HOST_TABLES_EAGER) {
+        s->h_rec_dev_off.assign(dev_off, dev_off + n_records);
+        s->h_rec_len.assign(len32, len32 + n_records);
+    }
+    trace.mark("rel + own tables");
     // exotic symbols of a packed source: source positions -> layout positions (a symbol in the halo two units share
     // appears once per unit); records in ascending source order are walked with one cursor
     std::vector<uint64_t> ex_layout;
@@ -463,22 +576,23 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
         const uint64_t *ex = src.exotic, ne = src.n_exotic;
         uint64_t cur = 0, prev_start = 0;
         for (uint32_t r = 0; r < n_records; ++r) {
-            const uint64_t a = starts[r], b = a + s->h_rec_len[r];
+            const uint64_t a = starts[r], b = a + len32[r];
             if (a == b) continue;
             if (a < prev_start || (cur < ne && a > (ex[cur] >> 8) + (1u << 16)))
                 cur = (uint64_t)(std::lower_bound(ex, ex + ne, a << 8) - ex);   // out of order, or far ahead: bisect
             while (cur < ne && (ex[cur] >> 8) < a) ++cur;
             prev_start = a;
             for (uint64_t i = cur; i < ne && (ex[i] >> 8) < b; ++i)
-                ex_layout.push_back((((ex[i] >> 8) - a + s->h_rec_dev_off[r]) << 8) | (ex[i] & 0xFF));
+                ex_layout.push_back((((ex[i] >> 8) - a + dev_off[r]) << 8) | (ex[i] & 0xFF));
         }
         std::sort(ex_layout.begin(), ex_layout.end());
     }
+    trace.mark("exotic layout");
     int rc = dev_alloc(&d_src_start, n_records);
     if (!rc) rc = dev_alloc(&s->d_rec_len, n_records);
     if (!rc) rc = dev_alloc(&s->d_rec_dev_off, n_records);
-    if (!rc && !olo.empty()) rc = dev_alloc(&s->d_own_lo, n_records);
-    if (!rc && !olo.empty()) rc = dev_alloc(&s->d_own_hi, n_records);
+    if (!rc && owned) rc = dev_alloc(&s->d_own_lo, n_records);
+    if (!rc && owned) rc = dev_alloc(&s->d_own_hi, n_records);
     if (!rc) rc = dev_alloc(&s->H, s->n_words_alloc);
     if (!rc) rc = dev_alloc(&s->L, s->n_words_alloc);
     if (!rc) rc = dev_alloc(&s->NM, s->n_words_alloc);
@@ -487,23 +601,24 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
     else s->ex_cap = std::min<uint32_t>(EX_CAP, next_pow2((uint32_t)std::min<uint64_t>(std::max<uint64_t>(total, 16), EX_CAP)));
     if (!rc) rc = dev_alloc(&s->ex_key, s->ex_cap);
     cudaError_t e = cudaSuccess;
+    trace.mark("device allocs");
     if (!rc) {
         const size_t n4 = (size_t)n_records * 4;
-        e = cudaMemcpyAsync(d_src_start, rel.data(), (size_t)n_records * 8, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_rec_len, len32.data(), n4, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_rec_dev_off, s->h_rec_dev_off.data(), n4, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess && !olo.empty()) e = cudaMemcpyAsync(s->d_own_lo, olo.data(), n4, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess && !olo.empty()) e = cudaMemcpyAsync(s->d_own_hi, ohi.data(), n4, cudaMemcpyHostToDevice, st);
+        e = cudaMemcpyAsync(d_src_start, rel, (size_t)n_records * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_rec_len, len32, n4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_rec_dev_off, dev_off, n4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && owned) e = cudaMemcpyAsync(s->d_own_lo, olo, n4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && owned) e = cudaMemcpyAsync(s->d_own_hi, ohi, n4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st);
         if (e == cudaSuccess && !ex_layout.empty())
             e = cudaMemcpyAsync(s->ex_key, ex_layout.data(), ex_layout.size() * 8, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess && runs_mode) {                             // mask plane of the span: zero, then the runs
             const size_t mask_words = on_device ? (size_t)((src_hi + 31) / 32 + 1) : (size_t)span_words;
             e = cudaMemsetAsync(const_cast<uint32_t *>(d_pN), 0, mask_words * 4, st);
-            const uint32_t nr = (uint32_t)(runs_rel.size() / 2);
+            const uint32_t nr = (uint32_t)n_runs_rel;
             if (e == cudaSuccess && nr) {
-                rc = dev_alloc(&d_runs, runs_rel.size());
-                if (!rc) e = cudaMemcpyAsync(d_runs, runs_rel.data(), runs_rel.size() * 8, cudaMemcpyHostToDevice, st);
+                rc = dev_alloc(&d_runs, (size_t)n_runs_rel * 2);
+                if (!rc) e = cudaMemcpyAsync(d_runs, runs_rel, (size_t)n_runs_rel * 16, cudaMemcpyHostToDevice, st);
                 if (!rc && e == cudaSuccess) {
                     mask_runs_kernel<<<(nr + 7) / 8, 256, 0, st>>>(d_runs, nr, const_cast<uint32_t *>(d_pN));
                     e = cudaGetLastError();
@@ -511,6 +626,7 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
             }
         }
     }
+    trace.mark("table uploads queued");
     // one launch of the packer over layout words [w_lo, w_hi)
     auto launch_pack = [&](uint32_t w_lo, uint32_t w_hi) -> cudaError_t {
         if (w_hi <= w_lo) return cudaSuccess;
@@ -537,14 +653,27 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
             if (!on_device) e = copy_span(0, span, st);
             if (e == cudaSuccess) e = launch_pack(0, s->n_words_alloc);
         } else {
-            // src_end[r]: running maximum of where records 0..r end in the source, so "the first record whose source is
-            // not all there" bounds the layout words that can be packed, whatever order the records come in
-            std::vector<uint64_t> src_end(n_records);
-            uint64_t run = 0;
-            for (uint32_t r = 0; r < n_records; ++r) {
-                if (s->h_rec_len[r]) run = std::max(run, starts[r] - src_lo + s->h_rec_len[r]);
-                src_end[r] = run;
+            // "The first record whose source is not all there" bounds the layout words that can be packed.  Records usually end
+            // in ascending source order (FASTA records, reads, units with halo): bisect their ends where they lie.  Otherwise
+            // src_end[r] = running maximum of where records 0..r end in the source, whatever order they come in.
+            std::vector<uint64_t> src_end;
+            if (!ends_sorted) {
+                src_end.resize(n_records);
+                uint64_t run = 0;
+                for (uint32_t r = 0; r < n_records; ++r) {
+                    if (len32[r]) run = std::max(run, starts[r] - src_lo + len32[r]);
+                    src_end[r] = run;
+                }
             }
+            auto first_incomplete = [&](uint64_t avail) -> uint32_t {     // first r whose source ends beyond src_lo + avail
+                if (!ends_sorted) return (uint32_t)(std::upper_bound(src_end.begin(), src_end.end(), avail) - src_end.begin());
+                uint32_t lo = 0, hi = n_records;
+                while (lo < hi) {
+                    const uint32_t mid = lo + (hi - lo) / 2;
+                    if (starts[mid] + len32[mid] > src_lo + avail) hi = mid; else lo = mid + 1;
+                }
+                return lo;
+            };
             e = cudaEventRecord(c->copy_done, st);                       // the copies start after what is queued on st
             if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->copy_done, 0);
             uint32_t w_done = 0;
@@ -556,11 +685,11 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
                 if (e != cudaSuccess) break;
                 uint32_t w_hi = s->n_words_alloc;
                 if (avail < span) {
-                    const uint32_t r = (uint32_t)(std::upper_bound(src_end.begin(), src_end.end(), avail) - src_end.begin());
+                    const uint32_t r = first_incomplete(avail);
                     if (r < n_records) {
                         const uint64_t r0 = starts[r] - src_lo;
-                        const uint64_t have = avail > r0 ? std::min<uint64_t>(avail - r0, s->h_rec_len[r]) : 0;
-                        w_hi = (uint32_t)((s->h_rec_dev_off[r] + have) >> 5);
+                        const uint64_t have = avail > r0 ? std::min<uint64_t>(avail - r0, len32[r]) : 0;
+                        w_hi = (uint32_t)((dev_off[r] + have) >> 5);
                     }
                 }
                 if (w_hi > w_done) {
@@ -575,8 +704,10 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
                                                                                           s->H, s->L, s->X);
             e = cudaGetLastError();
         }
+        trace.mark("copies + pack queued");
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // also keeps rel/len32/olo/ex_layout alive long enough
+        trace.mark("stream synchronised");
     }
     if (rc) { free_sources(); return rc; }
     if (e != cudaSuccess) { free_sources(); set_err("%s: %s", who, cudaGetErrorString(e)); return CRF_ERR_CUDA; }
@@ -614,13 +745,27 @@ static int load_impl(crf_ctx *c, const LoadSource &src, const uint64_t *starts, 
     s->info.n_exotic = s->n_exotic;
     s->info.max_motif_cap = max_motif_cap;
     s->info.load_ms = ms;
+    trace.mark("done");
+    return CRF_OK;
+}
+
+// Host copies of the layout offset and length tables (crf_run_end, crf_seq_set_output_map): filled by the load for an ordinary
+// record count, read back from the device on first use when there are millions of records.
+static int host_tables(crf_seq *s) {
+    if (s->h_rec_dev_off.size() == s->n_records && s->h_rec_len.size() == s->n_records) return CRF_OK;
+    try {
+        s->h_rec_dev_off.resize(s->n_records);
+        s->h_rec_len.resize(s->n_records);
+    } catch (const std::bad_alloc &) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
+    CU(cudaMemcpy(s->h_rec_dev_off.data(), s->d_rec_dev_off, (size_t)s->n_records * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(s->h_rec_len.data(), s->d_rec_len, (size_t)s->n_records * 4, cudaMemcpyDeviceToHost));
     return CRF_OK;
 }
 
 static int load_checked(crf_ctx *c, const LoadSource &src, const uint64_t *starts, const uint64_t *lengths,
                         const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
                         int on_device, crf_seq **out, const char *who) {
-    if (!c || !out || !starts || !lengths) { set_err("%s: null argument", who); return CRF_ERR_ARG; }
+    if (!c || !out || !starts) { set_err("%s: null argument", who); return CRF_ERR_ARG; }   // lengths == null: starts are boundaries
     *out = nullptr;
     if (n_records == 0) { set_err("%s: n_records must be >= 1", who); return CRF_ERR_ARG; }
     if ((own_lo == nullptr) != (own_hi == nullptr)) { set_err("%s_ranges: own_lo and own_hi go together", who); return CRF_ERR_ARG; }
@@ -631,7 +776,7 @@ static int load_checked(crf_ctx *c, const LoadSource &src, const uint64_t *start
     const bool have_src = src.packed() ? (src.pL && src.pN) : (src.bases != nullptr);
     if (!have_src) {
         for (uint32_t r = 0; r < n_records; ++r)
-            if (lengths[r]) { set_err("%s: null %s", who, src.packed() ? "plane" : "bases"); return CRF_ERR_ARG; }
+            if (lengths ? lengths[r] : starts[r + 1] - starts[r]) { set_err("%s: null %s", who, src.packed() ? "plane" : "bases"); return CRF_ERR_ARG; }
     }
     if (src.n_exotic && !src.exotic) { set_err("%s: null exotic list", who); return CRF_ERR_ARG; }
     CU(cudaSetDevice(c->device));
@@ -650,22 +795,18 @@ static int load_checked(crf_ctx *c, const LoadSource &src, const uint64_t *start
     return CRF_OK;
 }
 
-static int offsets_to_lengths(const uint64_t *offsets, uint32_t n_records, std::vector<uint64_t> &lengths, const char *who) {
+// The entry points that take n_records + 1 boundaries hand them to load_impl as they are (lengths == null): no per-record
+// array is built for them on the way.
+static int check_offsets(const uint64_t *offsets, uint32_t n_records, const char *who) {
     if (!offsets) { set_err("%s: null argument", who); return CRF_ERR_ARG; }
     if (n_records == 0) { set_err("%s: n_records must be >= 1", who); return CRF_ERR_ARG; }
-    try {
-        lengths.resize(n_records);
-    } catch (const std::bad_alloc &) { set_err("out of host memory"); return CRF_ERR_NOMEM; }
-    for (uint32_t r = 0; r < n_records; ++r) {
-        if (offsets[r + 1] < offsets[r]) { set_err("%s: offsets must be non-decreasing", who); return CRF_ERR_ARG; }
-        lengths[r] = offsets[r + 1] - offsets[r];
-    }
     return CRF_OK;
 }
 
 extern "C" int crf_seq_load_ascii_ranges(crf_ctx *c, const uint8_t *bases, const uint64_t *starts,
                                          const uint64_t *lengths, const uint64_t *own_lo, const uint64_t *own_hi,
                                          uint32_t n_records, uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
+    if (!lengths) { set_err("crf_seq_load_ascii_ranges: null argument"); return CRF_ERR_ARG; }
     LoadSource src;
     src.bases = bases;
     return load_checked(c, src, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, bases_on_device, out, "crf_seq_load_ascii");
@@ -673,16 +814,15 @@ extern "C" int crf_seq_load_ascii_ranges(crf_ctx *c, const uint8_t *bases, const
 
 extern "C" int crf_seq_load_ascii(crf_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint32_t n_records,
                                   uint32_t max_motif_cap, int bases_on_device, crf_seq **out) {
-    std::vector<uint64_t> lengths;
-    CHECK(offsets_to_lengths(offsets, n_records, lengths, "crf_seq_load_ascii"));
-    return crf_seq_load_ascii_ranges(c, bases, offsets, lengths.data(), nullptr, nullptr, n_records, max_motif_cap,
-                                     bases_on_device, out);
+    CHECK(check_offsets(offsets, n_records, "crf_seq_load_ascii"));
+    LoadSource src;
+    src.bases = bases;
+    return load_checked(c, src, offsets, nullptr, nullptr, nullptr, n_records, max_motif_cap, bases_on_device, out, "crf_seq_load_ascii");
 }
 
-extern "C" int crf_seq_load_packed_ranges(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint32_t *NM,
-                                          const uint64_t *exotic, uint64_t n_exotic, const uint64_t *starts,
-                                          const uint64_t *lengths, const uint64_t *own_lo, const uint64_t *own_hi,
-                                          uint32_t n_records, uint32_t max_motif_cap, int planes_on_device, crf_seq **out) {
+static int packed_load(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint32_t *NM, const uint64_t *exotic,
+                       uint64_t n_exotic, const uint64_t *starts, const uint64_t *lengths, const uint64_t *own_lo,
+                       const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap, int planes_on_device, crf_seq **out) {
     if (!H) {
         set_err("crf_seq_load_packed: null plane");
         return CRF_ERR_ARG;
@@ -692,11 +832,10 @@ extern "C" int crf_seq_load_packed_ranges(crf_ctx *c, const uint32_t *H, const u
     return load_checked(c, src, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, planes_on_device, out, "crf_seq_load_packed");
 }
 
-extern "C" int crf_seq_load_packed_runs_ranges(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint64_t *runs,
-                                               uint64_t n_runs, const uint64_t *exotic, uint64_t n_exotic,
-                                               const uint64_t *starts, const uint64_t *lengths, const uint64_t *own_lo,
-                                               const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
-                                               int planes_on_device, crf_seq **out) {
+static int packed_runs_load(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint64_t *runs, uint64_t n_runs,
+                            const uint64_t *exotic, uint64_t n_exotic, const uint64_t *starts, const uint64_t *lengths,
+                            const uint64_t *own_lo, const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
+                            int planes_on_device, crf_seq **out) {
     if (!H || !L) { set_err("crf_seq_load_packed_runs: null plane"); return CRF_ERR_ARG; }
     if (n_runs && !runs) { set_err("crf_seq_load_packed_runs: null run list"); return CRF_ERR_ARG; }
     for (uint64_t i = 0; i < n_runs; ++i)
@@ -711,22 +850,37 @@ extern "C" int crf_seq_load_packed_runs_ranges(crf_ctx *c, const uint32_t *H, co
     return load_checked(c, src, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, planes_on_device, out, "crf_seq_load_packed_runs");
 }
 
+extern "C" int crf_seq_load_packed_ranges(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint32_t *NM,
+                                          const uint64_t *exotic, uint64_t n_exotic, const uint64_t *starts,
+                                          const uint64_t *lengths, const uint64_t *own_lo, const uint64_t *own_hi,
+                                          uint32_t n_records, uint32_t max_motif_cap, int planes_on_device, crf_seq **out) {
+    if (!lengths) { set_err("crf_seq_load_packed_ranges: null argument"); return CRF_ERR_ARG; }
+    return packed_load(c, H, L, NM, exotic, n_exotic, starts, lengths, own_lo, own_hi, n_records, max_motif_cap, planes_on_device, out);
+}
+
+extern "C" int crf_seq_load_packed_runs_ranges(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint64_t *runs,
+                                               uint64_t n_runs, const uint64_t *exotic, uint64_t n_exotic,
+                                               const uint64_t *starts, const uint64_t *lengths, const uint64_t *own_lo,
+                                               const uint64_t *own_hi, uint32_t n_records, uint32_t max_motif_cap,
+                                               int planes_on_device, crf_seq **out) {
+    if (!lengths) { set_err("crf_seq_load_packed_runs_ranges: null argument"); return CRF_ERR_ARG; }
+    return packed_runs_load(c, H, L, runs, n_runs, exotic, n_exotic, starts, lengths, own_lo, own_hi, n_records, max_motif_cap,
+                            planes_on_device, out);
+}
+
 extern "C" int crf_seq_load_packed_runs(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint64_t *runs, uint64_t n_runs,
                                         const uint64_t *exotic, uint64_t n_exotic, const uint64_t *offsets, uint32_t n_records,
                                         uint32_t max_motif_cap, int planes_on_device, crf_seq **out) {
-    std::vector<uint64_t> lengths;
-    CHECK(offsets_to_lengths(offsets, n_records, lengths, "crf_seq_load_packed_runs"));
-    return crf_seq_load_packed_runs_ranges(c, H, L, runs, n_runs, exotic, n_exotic, offsets, lengths.data(), nullptr, nullptr,
-                                           n_records, max_motif_cap, planes_on_device, out);
+    CHECK(check_offsets(offsets, n_records, "crf_seq_load_packed_runs"));
+    return packed_runs_load(c, H, L, runs, n_runs, exotic, n_exotic, offsets, nullptr, nullptr, nullptr, n_records, max_motif_cap,
+                            planes_on_device, out);
 }
 
 extern "C" int crf_seq_load_packed(crf_ctx *c, const uint32_t *H, const uint32_t *L, const uint32_t *NM,
                                    const uint64_t *exotic, uint64_t n_exotic, const uint64_t *offsets, uint32_t n_records,
                                    uint32_t max_motif_cap, int planes_on_device, crf_seq **out) {
-    std::vector<uint64_t> lengths;
-    CHECK(offsets_to_lengths(offsets, n_records, lengths, "crf_seq_load_packed"));
-    return crf_seq_load_packed_ranges(c, H, L, NM, exotic, n_exotic, offsets, lengths.data(), nullptr, nullptr, n_records,
-                                      max_motif_cap, planes_on_device, out);
+    CHECK(check_offsets(offsets, n_records, "crf_seq_load_packed"));
+    return packed_load(c, H, L, NM, exotic, n_exotic, offsets, nullptr, nullptr, nullptr, n_records, max_motif_cap, planes_on_device, out);
 }
 
 extern "C" int crf_seq_destroy(crf_seq *s) {
@@ -753,6 +907,7 @@ extern "C" int crf_seq_set_output_map(crf_seq *s, const uint32_t *out_record, co
         CU(cudaMemcpy(s->d_map_rec, out_record, (size_t)n * 4, cudaMemcpyHostToDevice));
     }
     if (out_shift) {
+        CHECK(host_tables(s));
         std::vector<uint32_t> sh(n);
         for (uint32_t r = 0; r < n; ++r) {
             if (out_shift[r] > 0xFFFFFFFFull - s->h_rec_len[r]) { set_err("crf_seq_set_output_map: shifted coordinates exceed 32 bits"); return CRF_ERR_UNSUPPORTED; }
@@ -1256,9 +1411,10 @@ extern "C" int crf_patch_end(crf_seq *s, uint64_t row, uint32_t new_end) {
 
 extern "C" int crf_run_end(crf_seq *s, uint32_t record, uint32_t pos, uint32_t k, uint32_t *run_end) {
     if (!s || !run_end) { set_err("crf_run_end: null argument"); return CRF_ERR_ARG; }
+    CU(cudaSetDevice(s->ctx->device));
+    CHECK(host_tables(s));
     if (record >= s->n_records || pos >= s->h_rec_len[record]) { set_err("crf_run_end: position out of range"); return CRF_ERR_ARG; }
     if (k < 1 || k > s->cap) { set_err("crf_run_end: k %u not in [1, max_motif_cap %u]", k, s->cap); return CRF_ERR_ARG; }
-    CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
     ScanParams sp = {};
     sp.H = s->H; sp.L = s->L; sp.NM = s->NM; sp.X = s->X;
