@@ -18,6 +18,7 @@ ap.add_argument("--fast-only", action="store_true")
 ap.add_argument("--no-sup", action="store_true")
 ap.add_argument("--outcap", type=int, default=0)
 ap.add_argument("--wpt", type=int, default=0)
+ap.add_argument("--flags", type=int, default=0, help="crf_scan_params.flags (2: warp tiles, 8: two strips per thread)")
 ap.add_argument("--kmin", type=int, default=1)
 ap.add_argument("--kmax", type=int, default=0)
 ap.add_argument("--workload", default="s38", choices=["s38", "s22", "sr"])
@@ -33,7 +34,7 @@ else:
 torch.cuda.synchronize()
 ctx = _cabi.Context(0)
 seq = ctx.load(bases.data_ptr(), offsets, max_motif_cap=args.kmax, on_device=True)
-flags = ((1 << 16) if args.fast_only else 0) | ((1 << 17) if args.no_sup else 0)
+flags = ((1 << 16) if args.fast_only else 0) | ((1 << 17) if args.no_sup else 0) | args.flags
 for i in range(args.reps):
     n = seq.scan(args.kmin, args.kmax, 3, 9, flags=flags, words_per_thread=args.wpt, tile_out_cap=args.outcap)
     st = seq.stats()

@@ -247,6 +247,48 @@ def test_many_reads_path(mods):
         assert np.array_equal(st[sel], want[0]) and np.array_equal(en[sel], want[1])
 
 
+def test_millions_of_records_table_paths(mods):
+    """The per-record tables of a load with more than 2^20 records are built on several threads in the context's page-locked
+    arena, the host copies crf_run_end / crf_seq_set_output_map need are read back on first use, boundaries are taken as
+    they are and records that do not end in ascending source order fall back to the running-maximum table: 1.2 M reads
+    of 150 bp from the host, as boundaries, as (start, length) ranges in order and as ranges in REVERSE order (pipelined
+    upload, ends unsorted) -- all against the load of the same bytes already in HBM, plus run ends and shifted output."""
+    n_reads = 1_200_000
+    bases, offsets, _ = mods.synth.sr(n_reads, device="cuda:0")
+    host = bases.cpu().numpy()
+    ctx = mods.api.get_context()
+
+    def rows(seq):
+        n = seq.scan(1, 20, 3, 9)
+        return seq.fetch(n)
+
+    with ctx.load(bases.data_ptr(), offsets, max_motif_cap=20, on_device=True) as seq:
+        want = rows(seq)
+    assert want[0].size > 100_000
+    starts, lens = offsets[:-1].copy(), np.diff(offsets)
+    with ctx.load(host, offsets, max_motif_cap=20) as seq:                                   # boundaries, host text
+        got = rows(seq)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+        r = int(want[0][1000])                                                               # lazy host tables: a run end ...
+        st, k = int(want[1][1000]), int(want[3][1000])
+        assert seq.run_end(r, st, k) == int(want[2][1000]) - k                                # where the run of matches stops: end - k
+        with pytest.raises(ValueError):
+            seq.run_end(r, 150, k)
+        seq.set_output_map(out_shift=np.full(n_reads, 7, np.uint64))                         # ... and shifted coordinates
+        shifted = rows(seq)
+        assert np.array_equal(shifted[1], want[1] + 7) and np.array_equal(shifted[2], want[2] + 7)
+    with ctx.load_ranges(host, starts, lens, max_motif_cap=20) as seq:                       # ranges in source order
+        assert all(np.array_equal(a, b) for a, b in zip(rows(seq), want))
+    pk = mods.cabi.pack_ascii(host).with_runs()
+    with ctx.load_packed(pk, offsets, max_motif_cap=20) as seq:                              # planes + mask runs, boundaries
+        assert all(np.array_equal(a, b) for a, b in zip(rows(seq), want))
+    with ctx.load_ranges(host, starts[::-1].copy(), lens[::-1].copy(), max_motif_cap=20) as seq:   # reverse order
+        rec, st, en, k = rows(seq)
+    order = np.lexsort((en, st, n_reads - 1 - rec.astype(np.int64)))
+    assert np.array_equal(n_reads - 1 - rec[order].astype(np.int64), want[0].astype(np.int64))
+    assert np.array_equal(st[order], want[1]) and np.array_equal(en[order], want[2]) and np.array_equal(k[order], want[3])
+
+
 def test_pipelined_host_upload_equals_device_load(mods):
     """Host buffers above 128 MB go up in 64 MB chunks with the pack kernel running behind the copy; the packed
     planes must not depend on how the bytes arrived: same rows as a load of the same bytes already in HBM, for
