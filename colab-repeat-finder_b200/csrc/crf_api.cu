@@ -194,6 +194,7 @@ struct crf_seq {
     struct ScanLaunch *graph_key = nullptr;
     uint32_t graph_launches = 0;
     cudaEvent_t side_done = nullptr;                                   // an exchange stream still reads this sequence's rows
+    cudaEvent_t pub_done = nullptr;                                    // ... and this one says it is done with the scan counters
     ScanPlan *plan = nullptr;                                          // launch parameters of the scan in flight / last run
     crf_scan_stats_t stats = {};
     crf_seq_info_t info = {};
@@ -1157,7 +1158,8 @@ struct ScanLaunch {
 
 // memset -> scan -> tile offsets -> spill sort -> gather -> (single-copy filter) -> translate on `st`; ev[0] .. ev[3] bracket
 // the whole / the scan kernel (ev_flags = cudaEventRecordExternal while the stream is being captured into a graph).
-static int scan_launch_all(crf_seq *s, const ScanLaunch &L, cudaStream_t st, unsigned ev_flags, uint32_t *launches) {
+static int scan_launch_all(crf_seq *s, const ScanLaunch &L, cudaStream_t st, unsigned ev_flags, uint32_t *launches,
+                           cudaEvent_t rows_free = nullptr) {
     CU(cudaEventRecordWithFlags(s->ev[0], st, ev_flags));
     CU(cudaMemsetAsync(s->d_counters, 0, C_COUNT * sizeof(unsigned long long), st));
     CU(cudaEventRecordWithFlags(s->ev[1], st, ev_flags));
@@ -1182,6 +1184,7 @@ static int scan_launch_all(crf_seq *s, const ScanLaunch &L, cudaStream_t st, uns
                                                       s->d_counters);
         ++*launches;
     }
+    if (rows_free) CU(cudaStreamWaitEvent(st, rows_free, 0));   // the previous step's rows may still be travelling to rank 0
     translate_kernel<<<L.tgrid, 256, 0, st>>>(L.tp);
     ++*launches;
     CU(cudaGetLastError());
@@ -1238,13 +1241,24 @@ static int scan_enqueue(crf_seq *s, ScanPlan &pl, bool allow_graph = true) {
     L.n_tiles = n_tiles; L.ggrid = pl.ggrid; L.tgrid = pl.tgrid; L.single_copy = pl.single_copy ? 1u : 0u;
     L.smem = pl.smem; L.tile_off = s->tile_off; L.n_words_alloc = s->n_words_alloc; L.res_cap = s->res_cap;
 
-    if (s->side_done) {            // the previous push of this sequence's rows (on the exchange's own stream) comes first
-        CU(cudaStreamWaitEvent(st, s->side_done, 0));
-        s->side_done = nullptr;
+    // The previous push of this sequence's rows (on the exchange's own stream) comes first -- for the kernels that overwrite
+    // what it reads: the scan counters (read by its first kernel) and the rows (until its last).  With CRF_XCHG_OVERLAP=0 the
+    // whole scan waits for the whole push.
+    static const bool overlap_off = getenv("CRF_XCHG_OVERLAP") != nullptr && atoi(getenv("CRF_XCHG_OVERLAP")) == 0;
+    cudaEvent_t rows_free = nullptr;
+    if (s->side_done) {
+        if (s->pub_done && !overlap_off) {
+            CU(cudaStreamWaitEvent(st, s->pub_done, 0));
+            rows_free = s->side_done;
+        } else {
+            CU(cudaStreamWaitEvent(st, s->side_done, 0));
+        }
+        s->side_done = s->pub_done = nullptr;
     }
     static const bool graphs_off = getenv("CRF_NO_GRAPH") != nullptr;
     // (not on a rank of a multi-GPU job: instantiating a graph may wait for kernels that are themselves waiting for peers)
     if (allow_graph && s->ctx->n_xchg == 0 && n_tiles <= GRAPH_MAX_TILES && !graphs_off) {
+        if (rows_free) { CU(cudaStreamWaitEvent(st, rows_free, 0)); rows_free = nullptr; }   // (a captured scan waits as a whole)
         if (!s->graph_exec || !s->graph_key || memcmp(s->graph_key, &L, sizeof(L)) != 0) {
             if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
             if (!s->graph_key) s->graph_key = new (std::nothrow) ScanLaunch;
@@ -1263,7 +1277,7 @@ static int scan_enqueue(crf_seq *s, ScanPlan &pl, bool allow_graph = true) {
         pl.launches = s->graph_launches;
         return CRF_OK;
     }
-    return scan_launch_all(s, L, st, cudaEventRecordDefault, &pl.launches);
+    return scan_launch_all(s, L, st, cudaEventRecordDefault, &pl.launches, rows_free);
 }
 
 // after the counters of a completed scan are on the host
@@ -1449,7 +1463,7 @@ struct crf_xchg {
     // the exchange kernels run on their own stream behind the scan that feeds them, so the next phase's scan (another
     // sequence, the context's stream) overlaps the push of this one
     cudaStream_t xstream = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_pub = nullptr;
     bool compact = false;                        // 12-byte rows over NVLink (crf_xchg_set_compact)
 };
 
@@ -1470,13 +1484,19 @@ extern "C" int crf_xchg_create(crf_ctx *c, uint32_t rank, uint32_t world, uint64
     cudaError_t e = cudaMalloc(&x->base, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->base, 0, XCHG_ROWS_OFFSET);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&x->h_ring, (size_t)XCHG_RING * XCHG_RESULT_WORDS * 8);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->xstream, cudaStreamNonBlocking);
+    // (highest priority: when the rows of one step travel while the next step's scan runs, the copy blocks take the first
+    // SM slots that come free instead of queueing behind thousands of scan tiles)
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&x->xstream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_main, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_side, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_pub, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         if (x->xstream) cudaStreamDestroy(x->xstream);
         if (x->ev_main) cudaEventDestroy(x->ev_main);
         if (x->ev_side) cudaEventDestroy(x->ev_side);
+        if (x->ev_pub) cudaEventDestroy(x->ev_pub);
         if (x->h_ring) cudaFreeHost(x->h_ring);
         if (x->base) cudaFree(x->base);
         delete x;
@@ -1540,10 +1560,11 @@ extern "C" int crf_xchg_destroy(crf_xchg *x) {
     cudaSetDevice(x->ctx->device);
     cudaStreamSynchronize(x->ctx->stream);
     cudaStreamSynchronize(x->xstream);
-    for (crf_seq *s : x->pending) s->side_done = nullptr;
+    for (crf_seq *s : x->pending) s->side_done = s->pub_done = nullptr;
     cudaStreamDestroy(x->xstream);
     cudaEventDestroy(x->ev_main);
     cudaEventDestroy(x->ev_side);
+    cudaEventDestroy(x->ev_pub);
     for (uint32_t r = 0; r < x->world; ++r)
         if (x->peer_ipc[r] && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
     if (x->base) cudaFree(x->base);
@@ -1591,6 +1612,7 @@ static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted, bool append) {
     pp.compact = x->compact ? 1u : 0u;
     pp.timeout_ns = x->timeout_ns;
     publish_kernel<<<1, 32, 0, xs>>>(pp);
+    CU(cudaEventRecord(x->ev_pub, xs));                       // the scan counters have been read: the next scan may clear them
     push_kernel<<<148 * 2, 256, 0, xs>>>(pp);
     SettleParams sp = {};
     sp.self = (XchgBlock *)x->base;
@@ -1604,6 +1626,7 @@ static int xchg_enqueue(crf_seq *s, crf_xchg *x, bool trusted, bool append) {
                        XCHG_RESULT_WORDS * 8, cudaMemcpyDeviceToHost, xs));
     CU(cudaEventRecord(x->ev_side, xs));
     s->side_done = x->ev_side;                                // the next scan of this sequence waits for its rows to be gone
+    s->pub_done = x->ev_pub;                                  // (only before it overwrites them; its kernel starts after this one)
     return CRF_OK;
 }
 
@@ -1661,7 +1684,7 @@ extern "C" int crf_xchg_wait(crf_xchg *x, crf_xchg_result_t *res) {
         return CRF_ERR_CUDA;
     }
     for (crf_seq *s : x->pending) {                           // the asynchronous scans behind these steps: their counters
-        s->side_done = nullptr;                               // are on the host now
+        s->side_done = s->pub_done = nullptr;                 // are on the host now
         if (worst == XCHG_OK) CHECK(scan_fill_stats(s, *s->plan, 0));
     }
     x->pending.clear();

@@ -42,6 +42,8 @@ struct XchgBlock {
     unsigned long long base_rows;                      // rows gathered by the earlier phases of the job in progress
     unsigned int blocks_done;                          // last-block counter of push_kernel
     unsigned int push_ok;                              // publish_kernel: this rank may push (nothing void, everything fits)
+    unsigned long long snap_total, snap_open;          // publish_kernel: this step's row / open-row counts, so that the scan
+                                                       // counters are free for the next step's scan while the rows travel
     unsigned long long result[XCHG_RESULT_WORDS];      // settle_kernel: [0] status [1] total rows [2] total open
                                                        // [3] my offset [4] some rank has open-ended rows
                                                        // [5] rows of the job's earlier phases (before this step)
@@ -130,6 +132,8 @@ __global__ void __launch_bounds__(32) publish_kernel(const PushParams p) {
         const bool ok = valid && !any_bad && base + mine + n_total <= p.row_cap;
         p.self->my_offset = base + mine;
         p.self->push_ok = ok ? 1u : 0u;
+        p.self->snap_total = n_total;
+        p.self->snap_open = n_open;
     }
 }
 
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(256) push_kernel(const PushParams p) {
     const uint32_t par = p.step & 1u;
     const unsigned long long off = p.self->my_offset;
     const bool ok = p.self->push_ok != 0;
-    const unsigned long long n_total = p.counters[C_TOTAL], n_open = p.counters[C_OPEN];
+    const unsigned long long n_total = p.self->snap_total, n_open = p.self->snap_open;   // (not the scan counters: see XchgBlock)
     if (ok) {
         // four columns, each copied with 16-byte peer stores: the destination starts at an arbitrary row, so every column
         // has a scalar head up to the first 16-byte boundary of the DESTINATION, a vector body (four scalar loads from my
