@@ -278,7 +278,12 @@ extern "C" int crf_ctx_destroy(crf_ctx *c) {
 
 extern "C" int crf_ctx_set_stream(crf_ctx *c, void *stream) {
     if (!c) { set_err("null context"); return CRF_ERR_ARG; }
-    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    cudaStream_t next = stream ? (cudaStream_t)stream : c->own_stream;
+    if (next != c->stream) {                            // cached device blocks are handed out again without stream ordering:
+        CU(cudaSetDevice(c->device));                   // whatever the old stream still does with them finishes first
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    c->stream = next;
     return CRF_OK;
 }
 

@@ -41,8 +41,10 @@ int crf_abi_version(void);
 
 /* ---- context ---------------------------------------------------------------------------- */
 int crf_ctx_create(int device, crf_ctx **ctx);
+/* Destroy the context's sequences and exchange blocks first: they keep pointers into it. */
 int crf_ctx_destroy(crf_ctx *ctx);
-/* Run all work of this context on `cuda_stream` (a cudaStream_t; NULL = the context's own). */
+/* Run all work of this context on `cuda_stream` (a cudaStream_t; NULL = the context's own).  Switching waits for the work
+ * queued on the previous stream. */
 int crf_ctx_set_stream(crf_ctx *ctx, void *cuda_stream);
 int crf_ctx_synchronize(crf_ctx *ctx);
 
