@@ -553,6 +553,7 @@ class Fasta:
     `names_blob` (NUL-separated, as crf_write_rows takes them)."""
 
     def __init__(self, path, n_threads=0, pinned=False):
+        """pinned: False / True (page-locked base buffer and planes) / 2 (page-locked planes only: the text stays pageable)."""
         self._h = ctypes.c_void_p()
         _check(lib().crf_fasta_open(os.fsencode(path), n_threads, int(pinned), ctypes.byref(self._h)))
         n_rec, total, pin = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()

@@ -134,7 +134,7 @@ def _whole_fasta_to_bed(fa, args, bed_path):
             whole_file = first == 0 and last == fa.n_records          # the usual case: hand the name table over as it is
             _cabi.write_rows(bed_path, fa.names_blob if whole_file else fa.names[first:last], blob, offsets, rec, start,
                              end, k, append=True)
-            np.add.at(counts, rec.astype(np.int64) + first, 1)
+            counts[first:last] += np.bincount(rec, minlength=last - first)
     return counts
 
 
@@ -142,7 +142,8 @@ def _run_fasta(parser, args):
     if not args.output_prefix:
         args.output_prefix = re.sub(".fa(sta)?(.gz)?", "", args.input_sequence)   # the (unanchored) regex of prf:114
     bed_path = f"{os.path.basename(args.output_prefix)}.bed"                       # always in the working directory
-    with fasta.open_fasta(args.input_sequence, pinned=True) as fa:
+    # (page-locked planes only: the planes are what is uploaded, the text stays on the host for the motif column)
+    with fasta.open_fasta(args.input_sequence, pinned=2) as fa:
         if args.interval:
             fields = re.split("[:-]", args.interval)
             if len(fields) != 3:

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <unordered_map>
 #include <utility>
@@ -1830,30 +1831,51 @@ static int write_rows_impl(const char *path, int append, int tsv, const char *na
         }
     };
     if (tsv && !append) put("start_0based\tend\tmotif\n", 23);
-    std::vector<char> buf(1 << 22);
-    size_t used = 0;
-    for (uint64_t i = 0; i < n_rows && ok; ++i) {
-        const uint32_t r = record[i], k = motif_size[i];
-        const size_t need = (tsv ? 0 : name_len[r] + 1) + 24 + k + 1;
-        if (used + need > buf.size()) {
-            put(buf.data(), used);
-            used = 0;
-            if (need > buf.size()) buf.resize(need * 2);
+    // Rows are formatted by a few threads, each a contiguous slice of a "wave" into its own buffer (the motif column is a
+    // random read into the text: a cache miss per row), and the buffers of a wave are written in row order.
+    auto row_bytes = [&](uint64_t i) -> size_t { return (tsv ? 0 : name_len[record[i]] + 1) + 24 + motif_size[i] + 1; };
+    auto format_rows = [&](uint64_t lo, uint64_t hi, std::vector<char> &buf) -> size_t {
+        size_t need = 0;
+        for (uint64_t i = lo; i < hi; ++i) need += row_bytes(i);
+        if (buf.size() < need) buf.resize(need);
+        char *p = buf.data();
+        for (uint64_t i = lo; i < hi; ++i) {
+            const uint32_t r = record[i], k = motif_size[i];
+            if (!tsv) { memcpy(p, name_ptr[r], name_len[r]); p += name_len[r]; *p++ = '\t'; }
+            p = put_u32(p, start[i]); *p++ = '\t';
+            p = put_u32(p, end[i]); *p++ = '\t';
+            const uint8_t *m = bases + offsets[r] + start[i];
+            for (uint32_t j = 0; j < k; ++j) {
+                uint8_t c = m[j];
+                if (c >= 'a' && c <= 'z') c -= 32;
+                *p++ = (char)c;
+            }
+            *p++ = '\n';
         }
-        char *p = buf.data() + used;
-        if (!tsv) { memcpy(p, name_ptr[r], name_len[r]); p += name_len[r]; *p++ = '\t'; }
-        p = put_u32(p, start[i]); *p++ = '\t';
-        p = put_u32(p, end[i]); *p++ = '\t';
-        const uint8_t *m = bases + offsets[r] + start[i];
-        for (uint32_t j = 0; j < k; ++j) {
-            uint8_t c = m[j];
-            if (c >= 'a' && c <= 'z') c -= 32;
-            *p++ = (char)c;
+        return (size_t)(p - buf.data());
+    };
+    const uint64_t SLICE_ROWS = 1 << 15;
+    const uint32_t n_thr = n_rows < 4 * SLICE_ROWS ? 1u : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::vector<char>> bufs(n_thr);
+    std::vector<size_t> used(n_thr, 0);
+    std::vector<std::thread> th(n_thr);
+    bool no_memory = false;
+    for (uint64_t wave = 0; wave < n_rows && ok; wave += SLICE_ROWS * n_thr) {
+        for (uint32_t t = 0; t < n_thr; ++t) {
+            const uint64_t lo = std::min(n_rows, wave + SLICE_ROWS * t), hi = std::min(n_rows, lo + SLICE_ROWS);
+            used[t] = 0;
+            if (lo == hi) continue;
+            auto job = [&, t, lo, hi]() {
+                try { used[t] = format_rows(lo, hi, bufs[t]); } catch (const std::bad_alloc &) { no_memory = true; }
+            };
+            if (n_thr == 1) { job(); continue; }
+            try { th[t] = std::thread(job); } catch (const std::system_error &) { job(); }
         }
-        *p++ = '\n';
-        used = (size_t)(p - buf.data());
+        for (auto &t : th)
+            if (t.joinable()) t.join();
+        if (no_memory) throw std::bad_alloc();
+        for (uint32_t t = 0; t < n_thr; ++t) put(bufs[t].data(), used[t]);
     }
-    put(buf.data(), used);
     if (ferror(f)) ok = false;
     closer.f = nullptr;
     if (fclose(f) != 0) ok = false;

@@ -30,6 +30,7 @@ struct crf_fasta {
     uint32_t *planes = nullptr;
     uint64_t plane_words = 0;
     bool planes_pinned = false;
+    bool want_pinned_planes = false;                     // crf_fasta_open(pinned & 3): page-lock the planes crf_fasta_packed makes
     std::vector<uint64_t> exotic;
 };
 
@@ -325,7 +326,8 @@ static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf
     fa->total = total;
 
     const size_t alloc = std::max<uint64_t>(total, 1);
-    if (pinned) {
+    fa->want_pinned_planes = (pinned & 3) != 0;
+    if (pinned & 1) {
         void *p = nullptr;
         if (cudaHostAlloc(&p, alloc, cudaHostAllocDefault) == cudaSuccess) {
             fa->bases = (uint8_t *)p;

@@ -169,7 +169,7 @@ extern "C" int crf_mask_runs(const uint32_t *NM, uint64_t n_bases, uint32_t n_th
 }
 
 // Packed planes of a FASTA file read by crf_fasta_open, made on first use (threaded) and kept with the handle; page-locked
-// when the reader's base buffer is.
+// when crf_fasta_open was asked for it (pinned & 3).
 extern "C" int crf_fasta_packed(crf_fasta *fa, uint32_t n_threads, const uint32_t **H, const uint32_t **L, const uint32_t **NM,
                                 const uint64_t **exotic, uint64_t *n_exotic) {
     if (!fa || !H || !L || !NM || !exotic || !n_exotic) { set_err("crf_fasta_packed: null argument"); return CRF_ERR_ARG; }
@@ -179,7 +179,7 @@ extern "C" int crf_fasta_packed(crf_fasta *fa, uint32_t n_threads, const uint32_
             const uint64_t n_words = (fa->total + 31) / 32 + 1;
             const size_t bytes = (size_t)n_words * 12;
             void *p = nullptr;
-            if (fa->pinned && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) fa->planes_pinned = true;
+            if (fa->want_pinned_planes && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) fa->planes_pinned = true;
             else { cudaGetLastError(); p = malloc(bytes); }
             if (!p) { set_err("crf_fasta_packed: out of host memory"); return CRF_ERR_NOMEM; }
             fa->planes = (uint32_t *)p;

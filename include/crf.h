@@ -267,7 +267,9 @@ int crf_write_rows(const char *path, int append, int tsv, const char *names, con
  * order, .name = first whitespace-delimited header token, .seq = the lines joined, case preserved).  Plain or
  * gzip (concatenated members too; BGZF/bgzip blocks are inflated in parallel).  The result is laid out as crf_seq_load_ascii and crf_write_rows
  * take it: all records back to back, n_records+1 offsets, NUL-separated names.  n_threads = 0: up to 16.
- * pinned != 0: page-locked buffer (cudaHostAlloc) when a device is present, for a faster upload.
+ * pinned: bit 0 = page-locked base buffer (cudaHostAlloc, when a device is present: a faster upload of the text), bit 1 =
+ * page-locked planes only (crf_fasta_packed; bit 0 implies it) -- what a caller that uploads the planes and keeps the text
+ * on the host for the motif column wants: page-locking gigabytes it never uploads costs seconds.
  * The pointers of crf_fasta_data stay valid until crf_fasta_close. */
 typedef struct crf_fasta crf_fasta;
 int crf_fasta_open(const char *path, uint32_t n_threads, int pinned, crf_fasta **fasta);

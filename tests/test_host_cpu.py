@@ -190,6 +190,41 @@ def test_native_row_writer_bed_and_tsv(tmp_path):
     assert bed.read_text() == "chr1\t0\t8\tACGT\nchrZ\t0\t4\tACGT\nchrZ\t3\t9\tT\n"
 
 
+def test_native_row_writer_many_rows_threaded(tmp_path):
+    """Above 131 072 rows crf_write_rows formats slices of rows on several threads and writes the buffers in row order: 300 000
+    rows (ragged motif sizes, three records with names of different length, lower-case text) against a Python formatter,
+    BED, appended BED and TSV; a row count that is not a multiple of the slice size."""
+    import random
+    from crf_b200 import _cabi
+    rng = random.Random(12)
+    text = "".join(rng.choice("ACGTacgtN") for _ in range(30_000)).encode()
+    offsets = [0, 9_000, 9_000, 30_000]                       # the middle record is empty
+    names = ["chr1", "an_empty_record", "chrUn_KI270742v1"]
+    n = 300_001
+    rec = np.sort(np.array([rng.choice([0, 2]) for _ in range(n)], dtype=np.uint32))
+    length = np.where(rec == 0, 9_000, 21_000)
+    k = np.array([rng.randint(1, 50) for _ in range(n)], dtype=np.uint32)
+    start = np.array([rng.randint(0, int(length[i]) - 60) for i in range(n)], dtype=np.uint32)
+    end = start + k * 3
+
+    def expected(tsv):
+        out = []
+        for r, s0, e0, k0 in zip(rec.tolist(), start.tolist(), end.tolist(), k.tolist()):
+            motif = text[offsets[r] + s0:offsets[r] + s0 + k0].decode().upper()
+            out.append(f"{s0}\t{e0}\t{motif}\n" if tsv else f"{names[r]}\t{s0}\t{e0}\t{motif}\n")
+        return "".join(out)
+
+    bed = tmp_path / "big.bed"
+    nbytes = _cabi.write_rows(str(bed), names, text, offsets, rec, start, end, k)
+    want = expected(False)
+    assert bed.read_text() == want and nbytes == len(want)
+    _cabi.write_rows(str(bed), names, text, offsets, rec[:5], start[:5], end[:5], k[:5], append=True)
+    assert bed.read_text() == want + "".join(want.splitlines(keepends=True)[:5])
+    tsv = tmp_path / "big.tsv"
+    _cabi.write_rows(str(tsv), None, text, offsets, rec, start, end, k, tsv=True)
+    assert tsv.read_text() == "start_0based\tend\tmotif\n" + expected(True)
+
+
 # ---- min_repeats == 1: the host half (position-0 wrap-around, early-break selection) with the GPU scan replaced by
 # ---- a numpy statement of what crf_scan documents for that setting
 
