@@ -134,7 +134,7 @@ def _whole_fasta_to_bed(fa, args, bed_path):
             whole_file = first == 0 and last == fa.n_records          # the usual case: hand the name table over as it is
             _cabi.write_rows(bed_path, fa.names_blob if whole_file else fa.names[first:last], blob, offsets, rec, start,
                              end, k, append=True)
-            counts[first:last] += np.bincount(rec, minlength=last - first)
+            counts[first:last] += np.bincount(rec.astype(np.int64, copy=False), minlength=last - first)
     return counts
 
 
