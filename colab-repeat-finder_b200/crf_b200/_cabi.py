@@ -27,7 +27,7 @@ EXPORTS = [
     "crf_seq_load_packed_runs", "crf_seq_load_packed_runs_ranges", "crf_mask_runs",
     "crf_fasta_packed", "crf_seq_load_ascii", "crf_seq_load_ascii_ranges", "crf_seq_set_output_map", "crf_seq_destroy", "crf_seq_info", "crf_scan", "crf_fetch",
     "crf_scan_stats", "crf_run_end", "crf_fetch_open", "crf_patch_end", "crf_write_rows",
-    "crf_fasta_open", "crf_fasta_info", "crf_fasta_data", "crf_fasta_close",
+    "crf_fasta_open", "crf_fasta_info", "crf_fasta_data", "crf_fasta_close", "crf_gunzip",
     "crf_xchg_create", "crf_xchg_destroy", "crf_xchg_export", "crf_xchg_connect_ipc", "crf_xchg_connect_local",
     "crf_xchg_set_timeout", "crf_xchg_set_compact", "crf_scan_gather", "crf_xchg_push", "crf_xchg_wait", "crf_xchg_step_result", "crf_xchg_fetch",
     "crf_xchg_patch_end",
@@ -114,6 +114,7 @@ def lib():
         L.crf_fasta_info.argtypes = [vp, P(u64), P(u64), P(i)]
         L.crf_fasta_data.argtypes = [vp, P(vp), P(vp), P(vp), P(u64)]
         L.crf_fasta_close.argtypes = [vp]
+        L.crf_gunzip.argtypes = [vp, ctypes.c_uint64, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
         L.crf_xchg_create.argtypes = [vp, u32, u32, u64, P(vp)]
         L.crf_xchg_destroy.argtypes = [vp]
         L.crf_xchg_export.argtypes = [vp, vp]
@@ -455,6 +456,23 @@ def mask_runs(nm, n_bases, n_threads=0):
             continue
         _check(rc)
         return runs[:n.value].copy()
+
+
+def gunzip(data, use_zlib=False):
+    """Host-only: gzip bytes -> bytes through crf_gunzip: the FASTA reader's decoder with zlib behind it (use_zlib False / 0),
+    zlib alone (True / 1), or the reader's decoder alone (2: NotImplementedError for what it declines)."""
+    data = bytes(data)
+    src = ctypes.cast(ctypes.c_char_p(data), ctypes.c_void_p)
+    cap = max(4 * len(data), 1 << 12)
+    while True:
+        out = np.empty(cap, np.uint8)
+        n = ctypes.c_uint64()
+        rc = lib().crf_gunzip(src, len(data), ctypes.c_void_p(out.ctypes.data), cap, ctypes.byref(n), int(use_zlib))
+        if rc == CRF_ERR_CAPACITY:
+            cap = int(n.value)
+            continue
+        _check(rc)
+        return out[:n.value].tobytes()
 
 
 def pack_ascii(bases, n_threads=0, out=None):

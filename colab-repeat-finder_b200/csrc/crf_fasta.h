@@ -13,6 +13,8 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include "crf_inflate.h"
+
 #include <atomic>
 #include <exception>
 #include <chrono>
@@ -243,6 +245,7 @@ static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf
     };
     FileBytes file;
     std::vector<uint8_t> plain;
+    crf_inflate::OutBuf inflated;
     if (!open_bytes(path, file)) { set_err("crf_fasta_open: cannot read %s", path); return CRF_ERR_ARG; }
     const uint8_t *t = file.data;
     uint64_t n = file.size;
@@ -251,10 +254,12 @@ static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf
         bool bad = false;
         const bool bgzf = inflate_bgzf(file, n_threads, plain, &bad);
         if (bgzf && bad) { set_err("crf_fasta_open: %s has a corrupt BGZF block", path); return CRF_ERR_ARG; }
-        if (!bgzf && !inflate_all(file, plain)) { set_err("crf_fasta_open: %s is not a valid gzip stream", path); return CRF_ERR_ARG; }
-        t = plain.data();
-        n = plain.size();
-        lap(bgzf ? "bgzf" : "gzip");
+        // a plain gzip stream: the reader's own decoder (crf_inflate.h); whatever it does not take goes to zlib, which decides
+        const bool own = !bgzf && getenv("CRF_GUNZIP_ZLIB") == nullptr && crf_inflate::gunzip(file.data, file.size, inflated, n_threads);
+        if (!bgzf && !own && !inflate_all(file, plain)) { set_err("crf_fasta_open: %s is not a valid gzip stream", path); return CRF_ERR_ARG; }
+        t = own ? inflated.p : plain.data();
+        n = own ? inflated.size : plain.size();
+        lap(bgzf ? "bgzf" : own ? "gunzip" : "gzip/zlib");
     }
     lap("read");
 
@@ -370,6 +375,38 @@ static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf
     guard.p = nullptr;
     *out = fa;
     return CRF_OK;
+}
+
+// gzip -> bytes with the reader's decoder (use_zlib == 0: falls back to zlib like the reader does; 2: no fall-back,
+// CRF_ERR_UNSUPPORTED instead) or with zlib only (1).
+// CRF_ERR_CAPACITY with *out_n = the size needed when `cap` is too small.
+extern "C" int crf_gunzip(const uint8_t *gz, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_n, int use_zlib) {
+    if (!gz || !out_n || (cap && !out)) { set_err("crf_gunzip: null argument"); return CRF_ERR_ARG; }
+    try {
+        using namespace fasta_detail;
+        crf_inflate::OutBuf fast;
+        std::vector<uint8_t> slow;
+        const uint8_t *p = nullptr;
+        uint64_t got = 0;
+        if (use_zlib != 1 && crf_inflate::gunzip(gz, (size_t)n, fast, 4)) {
+            p = fast.p; got = fast.size;
+        } else if (use_zlib == 2) {
+            set_err("crf_gunzip: the reader's decoder does not take this stream");
+            return CRF_ERR_UNSUPPORTED;
+        } else {
+            FileBytes in;
+            in.data = gz; in.size = (size_t)n;
+            if (!inflate_all(in, slow)) { set_err("crf_gunzip: not a valid gzip stream"); return CRF_ERR_ARG; }
+            p = slow.data(); got = slow.size();
+        }
+        *out_n = got;
+        if (got > cap) { set_err("crf_gunzip: capacity %llu too small for %llu bytes", (unsigned long long)cap, (unsigned long long)got); return CRF_ERR_CAPACITY; }
+        if (got) memcpy(out, p, (size_t)got);
+        return CRF_OK;
+    } catch (const std::bad_alloc &) {
+        set_err("crf_gunzip: out of host memory");
+        return CRF_ERR_NOMEM;
+    }
 }
 
 extern "C" int crf_fasta_info(const crf_fasta *fa, uint64_t *n_records, uint64_t *total_bases, int *pinned) {

@@ -281,6 +281,11 @@ int crf_fasta_data(const crf_fasta *fasta, const uint8_t **bases, const uint64_t
 int crf_fasta_packed(crf_fasta *fasta, uint32_t n_threads, const uint32_t **H, const uint32_t **L, const uint32_t **NM,
                      const uint64_t **exotic, uint64_t *n_exotic);
 int crf_fasta_close(crf_fasta *fasta);
+/* Host only: all members of a gzip stream -> bytes, with the FASTA reader's own DEFLATE decoder (use_zlib == 0; it hands
+ * anything it does not take to zlib, as the reader does), with zlib alone (use_zlib == 1), or with the reader's decoder
+ * alone (use_zlib == 2: CRF_ERR_UNSUPPORTED for what it declines -- corrupt input included).  CRF_ERR_CAPACITY with *out_n =
+ * the size needed when `cap` is too small; CRF_ERR_ARG for a stream zlib rejects too. */
+int crf_gunzip(const uint8_t *gz, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_n, int use_zlib);
 
 #ifdef __cplusplus
 }

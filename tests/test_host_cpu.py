@@ -190,6 +190,126 @@ def test_native_row_writer_bed_and_tsv(tmp_path):
     assert bed.read_text() == "chr1\t0\t8\tACGT\nchrZ\t0\t4\tACGT\nchrZ\t3\t9\tT\n"
 
 
+def test_gunzip_decoder_against_zlib():
+    """The FASTA reader's own DEFLATE decoder (csrc/crf_inflate.h, crf_gunzip mode 2 = no zlib behind it) against Python's zlib:
+    stored / fixed / dynamic blocks, Huffman-only and RLE strategies, every level and window size, flush points inside the
+    stream, FNAME / MTIME header fields, several members, inputs from 0 bytes to 600 kB of DNA, text, runs, zeros and noise.
+    A flipped bit or a cut stream is an error (or, where the flip is harmless, the same bytes zlib gives) -- never other bytes."""
+    import gzip
+    import io
+    import random
+    import zlib
+    from crf_b200 import _cabi
+    rng = random.Random(20261018)
+
+    def gz(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=31, memlevel=8, chunks=None):
+        c = zlib.compressobj(level, zlib.DEFLATED, wbits, memlevel, strategy)
+        out, pos = b"", 0
+        for n in chunks or []:
+            out += c.compress(data[pos:pos + n]) + c.flush(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH, zlib.Z_NO_FLUSH]))
+            pos += n
+        return out + c.compress(data[pos:]) + c.flush()
+
+    def make(n):
+        kind = rng.choice(["dna", "soft-masked", "text", "zeros", "noise", "runs", "fasta", "two letters", "periodic"])
+        if kind == "dna":
+            return bytes(rng.choice(b"ACGT") for _ in range(n))
+        if kind == "soft-masked":
+            return bytes(rng.choice(b"ACGTacgtN") for _ in range(n))
+        if kind == "text":
+            return " ".join(rng.choice(["the", "quick", "brown", "fox", "jumps", "over", "lazy", "dog", "\n"])
+                            for _ in range(n // 4 + 1)).encode()[:n]
+        if kind == "zeros":
+            return bytes(n)
+        if kind == "noise":
+            return rng.randbytes(n)
+        if kind == "runs":
+            return b"".join(bytes([rng.randrange(256)]) * rng.randint(1, 600) for _ in range(n // 100 + 1))[:n]
+        if kind == "fasta":
+            s = bytes(rng.choice(b"ACGT") for _ in range(n))
+            return b">chr\n" + b"\n".join(s[i:i + 60] for i in range(0, len(s), 60))
+        if kind == "two letters":
+            return bytes(rng.choice(b"AB") for _ in range(n))
+        unit = rng.randbytes(rng.randint(1, 40))
+        return (unit * rng.randint(1, 3000) + rng.randbytes(rng.randint(0, 3000)))[:max(n, 1)]
+
+    n_cases = n_rejected = 0
+    for _ in range(260):
+        data = make(rng.choice([0, 1, 2, rng.randint(0, 300), rng.randint(300, 70_000), rng.randint(70_000, 600_000)]))
+        mode = rng.random()
+        if mode < 0.15:
+            comp = gz(data, level=0)
+        elif mode < 0.3:
+            comp = gz(data, level=rng.randint(1, 9), strategy=zlib.Z_FIXED)
+        elif mode < 0.4:
+            comp = gz(data, level=rng.randint(1, 9), strategy=zlib.Z_HUFFMAN_ONLY)
+        elif mode < 0.5:
+            comp = gz(data, level=rng.randint(1, 9), strategy=zlib.Z_RLE)
+        elif mode < 0.6:
+            comp = gz(data, level=rng.randint(1, 9), chunks=[rng.randint(0, max(1, len(data) // 3)) for _ in range(3)])
+        elif mode < 0.7:
+            comp = gz(data, level=rng.randint(1, 9), memlevel=rng.randint(1, 9), wbits=16 + rng.randint(9, 15))
+        elif mode < 0.8:
+            b = io.BytesIO()
+            with gzip.GzipFile(filename="some_name.fa", mode="wb", fileobj=b, compresslevel=rng.randint(1, 9),
+                               mtime=rng.randint(0, 2 ** 31)) as f:
+                f.write(data)
+            comp = b.getvalue()
+        else:
+            comp = gz(data, level=rng.randint(1, 9))
+        want = data
+        if rng.random() < 0.25:                                         # a second member
+            more = make(rng.randint(0, 5000))
+            comp, want = comp + gz(more, level=rng.randint(0, 9)), data + more
+        assert _cabi.gunzip(comp, use_zlib=2) == want                   # the reader's decoder alone
+        assert _cabi.gunzip(comp) == want and _cabi.gunzip(comp, use_zlib=1) == want
+        n_cases += 1
+        if len(comp) > 20:
+            bad = bytearray(comp)
+            bad[rng.randrange(10, len(bad))] ^= 1 << rng.randrange(8)
+            try:
+                got = _cabi.gunzip(bytes(bad), use_zlib=2)
+                ref = zlib.decompressobj(31)
+                try:
+                    z = ref.decompress(bytes(bad))
+                except zlib.error:
+                    z = None
+                if z is not None and ref.eof and not ref.unused_data:
+                    assert got == z
+            except NotImplementedError:
+                n_rejected += 1
+            try:                                                        # a cut stream: an error, unless the cut is the end of member one
+                cut = _cabi.gunzip(comp[:rng.randrange(0, len(comp) - 1)], use_zlib=rng.choice([0, 2]))
+                assert cut == data and want != data
+            except (ValueError, NotImplementedError):
+                pass
+    assert n_cases == 260 and n_rejected > 150
+
+
+def test_fasta_reader_gzip_decoders_agree(tmp_path, monkeypatch):
+    """A gzip FASTA through the reader's own decoder and through zlib alone (CRF_GUNZIP_ZLIB=1): same records, same bases."""
+    import gzip
+    import random
+    from crf_b200 import _cabi
+    rng = random.Random(3)
+    recs = [(f"r{i} x", "".join(rng.choice("ACGTacgtN") for _ in range(rng.randint(0, 200_000)))) for i in range(5)]
+    text = "".join(f">{n}\n" + "".join(s[i:i + 70] + "\n" for i in range(0, len(s), 70)) for n, s in recs)
+    path = tmp_path / "x.fa.gz"
+    for level in (1, 6, 9):
+        with gzip.open(path, "wt", compresslevel=level) as f:
+            f.write(text)
+        out = []
+        for use_zlib in (False, True):
+            if use_zlib:
+                monkeypatch.setenv("CRF_GUNZIP_ZLIB", "1")
+            else:
+                monkeypatch.delenv("CRF_GUNZIP_ZLIB", raising=False)
+            with _cabi.Fasta(str(path)) as fa:
+                out.append((list(fa.names), fa.offsets.tolist(), fa.bases.tobytes()))
+        assert out[0] == out[1]
+        assert out[0][0] == [n.split()[0] for n, _ in recs] and out[0][2] == "".join(s for _, s in recs).encode()
+
+
 def test_native_row_writer_many_rows_threaded(tmp_path):
     """Above 131 072 rows crf_write_rows formats slices of rows on several threads and writes the buffers in row order: 300 000
     rows (ragged motif sizes, three records with names of different length, lower-case text) against a Python formatter,
