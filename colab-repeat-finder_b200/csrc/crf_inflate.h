@@ -1,7 +1,7 @@
 // gzip -> bytes for the FASTA reader (host only; part of row f1 of DESIGN.md: the reference reads `ref.fa.gz` through
 // pyfastx, perfect_repeat_finder.py:117).
 //
-// A plain gzip file is ONE DEFLATE stream (RFC 1951/1952) and cannot be split over threads, so how fast it is decoded
+// A plain gzip file is ONE DEFLATE stream (RFC 1951/1952) with no index of block starts, so how fast it is decoded
 // decides how long a `.fa.gz` run takes: zlib's inflate does ~110 MB/s of FASTA text (literal-heavy, 2-3 bit codes, one
 // symbol per loop), 25 s for a human genome that is scanned in milliseconds.  This decoder is written for that data:
 //   * 64-bit bit buffer, refilled branch-free with one unaligned load (8 input bytes are always there in the main loop);
@@ -9,17 +9,26 @@
 //     decoded back to back without refilling in between; 8-bit table for the distance symbols;
 //   * the whole output is one contiguous buffer (realloc/mremap-grown), so a match is a plain copy from earlier output --
 //     no 32 KB window to maintain -- done 16 bytes at a time when the distance allows;
+//   * a big stream is decoded on several threads all the same (gunzip_parallel below): chunks find a block start by trial,
+//     decode into 16-bit symbols that stand for "byte j of the 32 KB I did not see", and are resolved once the chunk in
+//     front is known;
 //   * the CRC-32 of every member is checked afterwards on several threads (crc32_combine), as is ISIZE.
 // Anything unexpected (a code set zlib would reject, a bad CRC, trailing bytes that are no gzip member) makes gunzip()
 // return false and the caller falls back to zlib, which then gives the verdict.  tests/test_host_cpu.py compares both with
 // Python's zlib on streams of every block type.
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -35,6 +44,12 @@ struct OutBuf {                                          // malloc'ed so that gr
         if (!q) return false;
         p = q;
         cap = need;
+#ifdef MADV_HUGEPAGE
+        if (need >= ((size_t)8 << 20)) {                 // first touch of a big buffer costs as much as decoding into it:
+            const uintptr_t lo = ((uintptr_t)p + 4095) & ~(uintptr_t)4095, hi = ((uintptr_t)p + need) & ~(uintptr_t)4095;
+            if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);       // ask for 2 MB pages (advice only)
+        }
+#endif
         return true;
     }
 };
@@ -155,13 +170,41 @@ static void build_multi(const uint32_t *lt, uint64_t *mt) {
     }
 }
 
-struct Decoder {
-    const uint8_t *in, *in_end;
+struct Tables {                                          // per decoder: the tables of the current block, and the fixed code's
+    std::vector<uint32_t> lt, dt, flt, fdt;
+    std::vector<uint64_t> mt, fmt;
+    Tables() : lt(LITLEN_CAP), dt(DIST_CAP), mt((size_t)1 << MULTI_BITS) {}
+    bool fixed() {
+        if (!flt.empty()) return true;
+        uint8_t l[288], d[32];                           // the fixed code of RFC 1951 3.2.6
+        for (int s = 0; s < 288; ++s) l[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+        for (int s = 0; s < 32; ++s) d[s] = 5;
+        flt.resize(LITLEN_CAP); fdt.resize(DIST_CAP); fmt.resize((size_t)1 << MULTI_BITS);
+        if (!build_table(l, 288, LITLEN_BITS, flt.data(), LITLEN_CAP, litlen_entry) ||
+            !build_table(d, 32, DIST_BITS, fdt.data(), DIST_CAP, dist_entry)) return false;
+        build_multi(flt.data(), fmt.data());
+        return true;
+    }
+};
+
+// T = uint8_t: bytes.  T = uint16_t: "marker" symbols for a decoder that starts in the middle of a stream (gunzip_parallel):
+// 0..255 = a byte, 256 + j = whatever byte j of the unknown 32 KB before the starting point is; the buffer then begins with
+// those 32 768 markers, so that matches reaching back before the start copy them like anything else.
+template <class T>
+struct DecoderT {
+    const uint8_t *base = nullptr, *in = nullptr, *in_end = nullptr;
     uint64_t bb = 0;                                     // bit buffer: the next input bits, least significant first
     int bc = 0;                                          // valid bits in it
-    OutBuf *out;
-    size_t op;                                           // bytes of output so far
+    OutBuf *out = nullptr;                               // (capacity in bytes; `op` counts elements of T)
+    size_t op = 0;
+    size_t op_limit = ~(size_t)0;                        // give up beyond this many elements (marker chunks: bounded memory)
 
+    inline uint64_t bitpos() const { return 8 * (uint64_t)(in - base) - (uint64_t)bc; }
+    inline void seek(uint64_t bit) {
+        in = base + (bit >> 3); bb = 0; bc = 0;
+        uint32_t v;
+        if (bit & 7) bits((int)(bit & 7), &v);
+    }
     inline void refill() {
         if (in_end - in >= 8) {
             uint64_t w;
@@ -197,8 +240,9 @@ struct Decoder {
         if ((len ^ 0xFFFFu) != nlen) return false;
         in += 4;
         if ((size_t)(in_end - in) < len) return false;
-        if (!out->reserve(op + len + 512)) return false;
-        memcpy(out->p + op, in, len);
+        if (op > op_limit || !out->reserve((op + len + 512) * sizeof(T))) return false;
+        T *dst = (T *)out->p + op;
+        for (uint32_t i = 0; i < len; ++i) dst[i] = in[i];
         in += len;
         op += len;
         return true;
@@ -211,14 +255,14 @@ struct Decoder {
         const uint8_t *in_ = in, *const end_ = in_end;
         uint64_t b = bb;
         int c = bc;
-        size_t o = op, cap = out->cap;
-        uint8_t *buf = out->p;
+        size_t o = op, cap = out->cap / sizeof(T);
+        T *buf = (T *)out->p;
         bool ok = false;
         for (;;) {
             if (cap - o < 512) {                         // room for a run of literals + the longest match + copy overrun
-                if (!out->reserve(o + o / 2 + (1u << 20))) break;
-                buf = out->p;
-                cap = out->cap;
+                if (o > op_limit || !out->reserve((o + o / 2 + (1u << 20)) * sizeof(T))) break;
+                buf = (T *)out->p;
+                cap = out->cap / sizeof(T);
             }
             if (end_ - in_ >= 8) {
                 uint64_t w;
@@ -233,7 +277,12 @@ struct Decoder {
             if (m >> 40) {                               // a run of literals, up to four per look-up
                 do {
                     const uint32_t four = (uint32_t)m;
-                    memcpy(buf + o, &four, 4);
+                    if (sizeof(T) == 1) {
+                        memcpy(buf + o, &four, 4);
+                    } else {
+                        buf[o] = (T)(four & 0xFF); buf[o + 1] = (T)((four >> 8) & 0xFF);
+                        buf[o + 2] = (T)((four >> 16) & 0xFF); buf[o + 3] = (T)(four >> 24);
+                    }
                     o += (size_t)(m >> 40);
                     const int used = (int)((m >> 32) & 0xFF);
                     b >>= used; c -= used;
@@ -253,7 +302,7 @@ struct Decoder {
             b >>= tot; c -= (int)tot;
             if (c < 0) break;
             const uint32_t kind = e_kind(e);
-            if (kind == K_LITERAL) { buf[o++] = (uint8_t)e_value(e); continue; }     // (a literal with a long code)
+            if (kind == K_LITERAL) { buf[o++] = (T)e_value(e); continue; }           // (a literal with a long code)
             if (kind != K_LENGTH) { ok = kind == K_EOB; break; }                      // end of block, or an unused code
             const uint32_t xl = e_extra(e);
             const uint32_t len = e_value(e) + (uint32_t)((s >> (tot - xl)) & ((1u << xl) - 1));
@@ -269,12 +318,13 @@ struct Decoder {
             const uint32_t xd = e_extra(d);
             const size_t dist = e_value(d) + (size_t)((s >> (tot - xd)) & ((1u << xd) - 1));
             if (dist > o) break;                         // reaches back beyond the start of the output
-            uint8_t *dst = buf + o;
-            const uint8_t *src = dst - dist;
+            T *dst = buf + o;
+            const T *src = dst - dist;
             if (dist >= 16) {
-                for (uint32_t i = 0; i < len; i += 16) memcpy(dst + i, src + i, 16);
+                for (uint32_t i = 0; i < len; i += 16) memcpy(dst + i, src + i, 16 * sizeof(T));
             } else if (dist == 1) {
-                memset(dst, *src, len);
+                const T v = *src;
+                for (uint32_t i = 0; i < len; ++i) dst[i] = v;
             } else {
                 for (uint32_t i = 0; i < len; ++i) dst[i] = src[i];
             }
@@ -325,40 +375,32 @@ struct Decoder {
                build_table(lens + hlit, (int)hdist, DIST_BITS, dt, DIST_CAP, dist_entry);
     }
 
-    // one raw DEFLATE stream from `in`; on success `in` is the first byte after it
-    bool inflate_stream() {
-        std::vector<uint32_t> lt(LITLEN_CAP), dt(DIST_CAP), flt, fdt;
-        std::vector<uint64_t> mt(1u << MULTI_BITS), fmt;
+    // Blocks from the current position.  RUN_FINAL: the final block is done and `in` is the first byte after the stream.
+    // RUN_STOPPED: the next block starts at bitpos() >= stop_bit (nothing of it has been read).  RUN_ERROR: invalid data.
+    enum { RUN_ERROR = 0, RUN_STOPPED = 1, RUN_FINAL = 2 };
+    int run(Tables &tb, uint64_t stop_bit = ~0ull) {
         for (;;) {
+            if (bitpos() >= stop_bit) return RUN_STOPPED;
             uint32_t final_block, type;
-            if (!bits(1, &final_block) || !bits(2, &type)) return false;
+            if (!bits(1, &final_block) || !bits(2, &type)) return RUN_ERROR;
             if (type == 0) {
-                if (!stored_block()) return false;
+                if (!stored_block()) return RUN_ERROR;
             } else if (type == 1) {
-                if (flt.empty()) {                       // the fixed code of RFC 1951 3.2.6
-                    uint8_t l[288], d[32];
-                    for (int s = 0; s < 288; ++s) l[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
-                    for (int s = 0; s < 32; ++s) d[s] = 5;
-                    flt.resize(LITLEN_CAP); fdt.resize(DIST_CAP);
-                    if (!build_table(l, 288, LITLEN_BITS, flt.data(), LITLEN_CAP, litlen_entry) ||
-                        !build_table(d, 32, DIST_BITS, fdt.data(), DIST_CAP, dist_entry)) return false;
-                    fmt.resize(1u << MULTI_BITS);
-                    build_multi(flt.data(), fmt.data());
-                }
-                if (!huffman_block(flt.data(), fdt.data(), fmt.data())) return false;
+                if (!tb.fixed() || !huffman_block(tb.flt.data(), tb.fdt.data(), tb.fmt.data())) return RUN_ERROR;
             } else if (type == 2) {
-                if (!dynamic_tables(lt.data(), dt.data())) return false;
-                build_multi(lt.data(), mt.data());
-                if (!huffman_block(lt.data(), dt.data(), mt.data())) return false;
+                if (!dynamic_tables(tb.lt.data(), tb.dt.data())) return RUN_ERROR;
+                build_multi(tb.lt.data(), tb.mt.data());
+                if (!huffman_block(tb.lt.data(), tb.dt.data(), tb.mt.data())) return RUN_ERROR;
             } else {
-                return false;
+                return RUN_ERROR;
             }
             if (final_block) break;
         }
         to_byte_boundary();
-        return true;
+        return RUN_FINAL;
     }
 };
+typedef DecoderT<uint8_t> Decoder;
 
 struct Member { size_t out_lo, out_hi; uint32_t crc, isize; };
 
@@ -386,12 +428,230 @@ static uint32_t crc32_parallel(const uint8_t *p, size_t n, unsigned n_threads) {
     return (uint32_t)crc;
 }
 
+// ---- one DEFLATE stream on several threads ----------------------------------------------------------------------------------
+// The stream is cut into chunks of `chunk_bytes` of compressed data, P chunks per round.  The first chunk of a round starts
+// at a known block boundary and is decoded straight into `out`.  Every other chunk has to FIND a block boundary first --
+// bit offsets are tried one by one until a non-final dynamic-Huffman block header parses into two complete codes, the block
+// decodes and another plausible header follows -- and, not knowing the 32 KB before it, decodes into 16-bit marker symbols
+// (DecoderT<uint16_t>).  Each chunk stops at the first block boundary at or beyond its nominal end.  Then the chunks are
+// stitched in order: the boundary the previous chunk stopped at must be exactly where this one started (if this one
+// started later -- stored or fixed blocks are no starting points -- the previous decoder carries on up to it; if it started
+// EARLIER, it started on a phantom: give up); the last 32 KB in front of each chunk are handed down the chain and all chunks
+// are resolved into `out` in parallel.  Whatever goes wrong returns false, and so does a CRC mismatch afterwards (gunzip):
+// the serial decoder then does the job.
+struct MarkerChunk {
+    OutBuf buf;                                          // uint16_t symbols: 32 768 window markers, then the output
+    DecoderT<uint16_t> dec;
+    Tables tb;
+    uint64_t start_bit = ~0ull;                          // where it found its first block (~0: nowhere)
+    int state = 0;                                       // RUN_* of its decoder
+};
+constexpr size_t WINDOW = 32768;
+
+static bool marker_reset(MarkerChunk &c, size_t expect_out) {
+    if (!c.buf.reserve((WINDOW + expect_out + (1u << 16)) * 2)) return false;
+    uint16_t *q = (uint16_t *)c.buf.p;
+    for (size_t j = 0; j < WINDOW; ++j) q[j] = (uint16_t)(256 + j);
+    c.dec.out = &c.buf;
+    c.dec.op = WINDOW;
+    c.dec.op_limit = WINDOW + 3 * expect_out;            // (a stream that expands far more than FASTA text is left to one thread)
+    return true;
+}
+
+// first plausible block start in [from_bit, to_bit), decoding begun: on return the decoder stands behind the first block
+static bool marker_find_start(MarkerChunk &c, const uint8_t *gz, size_t n, uint64_t from_bit, uint64_t to_bit, size_t expect_out) {
+    for (uint64_t p = from_bit; p < to_bit; ++p) {
+        const uint32_t three = (gz[p >> 3] | ((uint32_t)gz[(p >> 3) + 1] << 8)) >> (p & 7);
+        if ((three & 7u) != 4u) continue;                // BFINAL = 0, BTYPE = 2 (dynamic), least significant bit first
+        DecoderT<uint16_t> &d = c.dec;
+        d.base = gz; d.in_end = gz + n;
+        d.seek(p + 3);
+        if (!d.dynamic_tables(c.tb.lt.data(), c.tb.dt.data())) continue;
+        if (!marker_reset(c, expect_out)) return false;
+        build_multi(c.tb.lt.data(), c.tb.mt.data());
+        if (!d.huffman_block(c.tb.lt.data(), c.tb.dt.data(), c.tb.mt.data())) continue;
+        {                                                // what follows must look like a block too
+            DecoderT<uint16_t> peek = d;
+            uint32_t fin, type;
+            if (!peek.bits(1, &fin) || !peek.bits(2, &type) || type == 3) continue;
+            if (type == 2) {
+                Tables scratch;
+                if (!peek.dynamic_tables(scratch.lt.data(), scratch.dt.data())) continue;
+            } else if (type == 0) {
+                peek.to_byte_boundary();
+                if (peek.in_end - peek.in < 4) continue;
+                const uint32_t len = peek.in[0] | (peek.in[1] << 8), nlen = peek.in[2] | (peek.in[3] << 8);
+                if ((len ^ 0xFFFFu) != nlen) continue;
+            }
+        }
+        c.start_bit = p;
+        return true;
+    }
+    return false;
+}
+
+static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf &out, size_t *op_io, size_t *end_pos,
+                            unsigned n_threads, size_t chunk_bytes) {
+    const unsigned P = std::min(16u, n_threads);
+    if (P < 2 || n < data_pos + 2 * chunk_bytes + 64) return false;
+    const size_t ratio = 5;                              // expected output per compressed byte (buffers grow if it is more)
+    DecoderT<uint8_t> head;
+    Tables head_tb;
+    head.base = gz; head.in = gz + data_pos; head.in_end = gz + n; head.out = &out; head.op = *op_io;
+    std::vector<MarkerChunk> chunks(P);
+    const uint64_t end_bit = 8 * (uint64_t)(n - 8);      // (the trailer is no block)
+    const bool trace = getenv("CRF_GUNZIP_TRACE") != nullptr;
+    unsigned n_rounds = 0, n_used = 0, n_carried = 0;
+    std::vector<uint8_t> luts;
+    double ms_decode = 0, ms_stitch = 0, ms_resolve = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    for (;;) {
+        ++n_rounds;
+        auto t_round = now();
+        // nominal chunk ends of this round (bytes); the round's first chunk starts where the stream stands
+        const uint64_t here = head.bitpos();
+        std::vector<uint64_t> cut(P + 1);
+        for (unsigned k = 0; k <= P; ++k) cut[k] = std::min<uint64_t>(end_bit, here + 8 * (uint64_t)k * chunk_bytes);
+        int head_state = 0;
+        std::atomic<bool> threw{false};
+        std::vector<std::thread> th;
+        auto work = [&](unsigned k) {
+          try {
+            if (k == 0) {
+                head_state = head.run(head_tb, cut[1]);
+                return;
+            }
+            MarkerChunk &c = chunks[k];
+            c.start_bit = ~0ull; c.state = 0;
+            if (cut[k] >= end_bit) return;
+            uint64_t from = cut[k];
+            while (from < cut[k + 1] && marker_find_start(c, gz, n, from, cut[k + 1], ratio * chunk_bytes)) {
+                c.state = c.dec.run(c.tb, cut[k + 1]);
+                if (c.state != DecoderT<uint16_t>::RUN_ERROR) return;
+                from = c.start_bit + 1;                  // it was no block after all: look further
+                c.start_bit = ~0ull;
+            }
+            c.state = 0;
+          } catch (...) { threw = true; }                // (bad_alloc in a worker must not leave its thread)
+        };
+        for (unsigned k = 1; k < P; ++k) {
+            try { th.emplace_back(work, k); } catch (const std::exception &) { work(k); }
+        }
+        work(0);
+        for (auto &t : th) t.join();
+        if (threw || head_state == Decoder::RUN_ERROR) return false;
+        ms_decode += ms_since(t_round);
+        t_round = now();
+        // stitch: `pos` = the true block boundary reached so far, by the decoder `last` (-1: the head)
+        int last = -1;
+        bool final_seen = head_state == Decoder::RUN_FINAL;
+        uint64_t pos = final_seen ? 0 : head.bitpos();
+        std::vector<unsigned> used;
+        for (unsigned k = 1; k < P; ++k) {
+            MarkerChunk &c = chunks[k];
+            if (c.start_bit == ~0ull) continue;          // found nothing in its range: the previous decoder covers it
+            if (final_seen) return false;                // a "block" behind the end of the stream
+            if (pos > c.start_bit) return false;         // started on a phantom
+            if (pos < c.start_bit) {                     // carry the previous decoder on up to this chunk's start
+                int st;
+                if (last < 0) { st = head.run(head_tb, c.start_bit); pos = head.bitpos(); }
+                else { st = chunks[last].dec.run(chunks[last].tb, c.start_bit); pos = chunks[last].dec.bitpos(); }
+                if (st != Decoder::RUN_STOPPED || pos != c.start_bit) return false;
+                ++n_carried;
+            }
+            used.push_back(k);
+            last = (int)k;
+            final_seen = c.state == DecoderT<uint16_t>::RUN_FINAL;
+            pos = final_seen ? 0 : c.dec.bitpos();
+        }
+        // resolve the marker chunks behind the head's output
+        size_t total = head.op;
+        std::vector<size_t> at(used.size());
+        for (size_t i = 0; i < used.size(); ++i) { at[i] = total; total += chunks[used[i]].dec.op - WINDOW; }
+        if (!out.reserve(total + total / 8 + (1u << 20))) return false;
+        std::vector<std::vector<uint8_t>> window(used.size(), std::vector<uint8_t>(WINDOW, 0));
+        for (size_t i = 0; i < used.size(); ++i) {       // the 32 KB in front of each chunk, handed down the chain
+            std::vector<uint8_t> &w = window[i];
+            if (i == 0) {
+                const size_t have = std::min(WINDOW, head.op);
+                memcpy(w.data() + WINDOW - have, out.p + head.op - have, have);
+            } else {
+                const MarkerChunk &pc = chunks[used[i - 1]];
+                const uint16_t *sym = (const uint16_t *)pc.buf.p;
+                const size_t n_prev = pc.dec.op - WINDOW, have = std::min(WINDOW, n_prev);
+                const std::vector<uint8_t> &pw = window[i - 1];
+                memcpy(w.data(), pw.data() + have, WINDOW - have);
+                for (size_t j = 0; j < have; ++j) {
+                    const uint16_t v = sym[pc.dec.op - have + j];
+                    w[WINDOW - have + j] = v < 256 ? (uint8_t)v : pw[v - 256];
+                }
+            }
+        }
+        th.clear();
+        ms_stitch += ms_since(t_round);
+        t_round = now();
+        luts.resize(used.size() * (256 + WINDOW));       // (allocated here: nothing in the workers throws)
+        auto resolve = [&](size_t i) {                   // (no allocation in here: nothing to throw)
+            const MarkerChunk &c = chunks[used[i]];
+            const uint16_t *sym = (const uint16_t *)c.buf.p + WINDOW;
+            const size_t cnt = c.dec.op - WINDOW;
+            const uint8_t *w = window[i].data();
+            uint8_t *dst = out.p + at[i];
+            // In DNA text nearly every byte is a copy of a copy (gzip finds a match everywhere), so markers do not die out
+            // with distance from the chunk start: about half of ALL symbols are markers.  One table, no branch:
+            uint8_t *lut = luts.data() + i * (256 + WINDOW);
+            for (size_t v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
+            memcpy(lut + 256, w, WINDOW);
+            size_t j = 0;
+            for (; j + 4 <= cnt; j += 4) {
+                uint64_t four;
+                memcpy(&four, sym + j, 8);
+                const uint32_t r = (uint32_t)lut[four & 0xFFFF] | ((uint32_t)lut[(four >> 16) & 0xFFFF] << 8) |
+                                   ((uint32_t)lut[(four >> 32) & 0xFFFF] << 16) | ((uint32_t)lut[four >> 48] << 24);
+                memcpy(dst + j, &r, 4);
+            }
+            for (; j < cnt; ++j) dst[j] = lut[sym[j]];
+        };
+        for (size_t i = 1; i < used.size(); ++i) {
+            try { th.emplace_back(resolve, i); } catch (const std::exception &) { resolve(i); }
+        }
+        if (!used.empty()) resolve(0);
+        for (auto &t : th) t.join();
+        n_used += (unsigned)used.size();
+        ms_resolve += ms_since(t_round);
+        if (final_seen) {
+            if (trace) fprintf(stderr, "[crf_inflate] parallel: %u round(s), %u marker chunk(s) stitched, %u carried on to a later start"
+                               " (decode %.0f ms, stitch %.0f ms, resolve %.0f ms)\n",
+                               n_rounds, n_used, n_carried, ms_decode, ms_stitch, ms_resolve);
+            const uint8_t *after = last < 0 ? head.in : chunks[last].dec.in;
+            *op_io = total;
+            *end_pos = (size_t)(after - gz);
+            return true;
+        }
+        // next round: the head decoder goes on from the boundary the last chunk reached
+        if (pos <= here || pos >= end_bit) return false; // no progress, or blocks that run into the trailer: not a sane stream
+        head.op = total;
+        if (last >= 0) head.seek(pos);
+    }
+}
+
+#ifndef CRF_INFLATE_CHUNK_BYTES
+#define CRF_INFLATE_CHUNK_BYTES (8u << 20)
+#endif
+
 // All members of a gzip file -> out.  False: not handled here (the caller lets zlib decide).
-static bool gunzip(const uint8_t *gz, size_t n, OutBuf &out, unsigned n_threads) {
+// parallel_chunk_bytes: chunk size of the several-threads decoder (0: the default; ~0: one thread only).
+static bool gunzip(const uint8_t *gz, size_t n, OutBuf &out, unsigned n_threads, size_t parallel_chunk_bytes = 0) {
     if (n < 18) return false;
+    if (!parallel_chunk_bytes) {
+        const char *kb = getenv("CRF_GUNZIP_CHUNK_KB");  // (tests: small chunks send small inputs through the several-threads path)
+        parallel_chunk_bytes = kb && atoi(kb) > 0 ? (size_t)atoi(kb) << 10 : (size_t)CRF_INFLATE_CHUNK_BYTES;
+    }
     const uint32_t isize_hint = gz[n - 4] | (gz[n - 3] << 8) | (gz[n - 2] << 16) | ((uint32_t)gz[n - 1] << 24);
     if (!out.reserve(std::max<size_t>((size_t)isize_hint, n * 4) + (1u << 20))) return false;
     std::vector<Member> members;
+    Tables tb;
     size_t pos = 0, op = 0;
     while (pos < n) {
         if (n - pos < 18 || gz[pos] != 0x1f || gz[pos + 1] != 0x8b || gz[pos + 2] != 8) return false;
@@ -413,18 +673,27 @@ static bool gunzip(const uint8_t *gz, size_t n, OutBuf &out, unsigned n_threads)
             }
         if (flg & 2) p += 2;                             // FHCRC
         if (p >= n) return false;
-        Decoder d;
-        d.in = gz + p; d.in_end = gz + n; d.out = &out; d.op = op;
-        if (!d.inflate_stream()) return false;
-        p = (size_t)(d.in - gz);
-        if (n - p < 8) return false;
         Member m;
-        m.out_lo = op; m.out_hi = d.op;
+        m.out_lo = op;
+        size_t after = 0, op_par = op;
+        // several threads for a big first member that is the whole file (the trailer it ends at is the end of the input)
+        if (pos == 0 && parallel_chunk_bytes != ~(size_t)0 && n_threads > 1 &&
+            gunzip_parallel(gz, n, p, out, &op_par, &after, n_threads, parallel_chunk_bytes) && after + 8 == n) {
+            op = op_par;
+            p = after;
+        } else {
+            Decoder d;
+            d.base = gz; d.in = gz + p; d.in_end = gz + n; d.out = &out; d.op = op;
+            if (d.run(tb) != Decoder::RUN_FINAL) return false;
+            op = d.op;
+            p = (size_t)(d.in - gz);
+        }
+        if (n - p < 8) return false;
+        m.out_hi = op;
         m.crc = gz[p] | (gz[p + 1] << 8) | (gz[p + 2] << 16) | ((uint32_t)gz[p + 3] << 24);
         m.isize = gz[p + 4] | (gz[p + 5] << 8) | (gz[p + 6] << 16) | ((uint32_t)gz[p + 7] << 24);
         if ((uint32_t)(m.out_hi - m.out_lo) != m.isize) return false;
         members.push_back(m);
-        op = d.op;
         pos = p + 8;
     }
     for (const Member &m : members)

@@ -286,6 +286,60 @@ def test_gunzip_decoder_against_zlib():
     assert n_cases == 260 and n_rejected > 150
 
 
+def test_gunzip_one_stream_on_several_threads(monkeypatch, capfd):
+    """A plain gzip stream decoded by several threads (crf_inflate.h: gunzip_parallel -- chunks that find a block boundary by
+    trial, decode into 16-bit marker symbols without knowing the 32 KB before them, and are stitched and resolved afterwards).
+    Small chunk sizes (CRF_GUNZIP_CHUNK_KB) send streams of 0.3 - 2 MB through it: DNA, text, runs, zeros and noise mixed in
+    one stream (dynamic, stored and -- Z_FIXED -- fixed blocks, flush points); the bytes must be zlib's, the trace must show
+    that the threaded path did the work, and that the case "a chunk starts later than the previous one stopped" came up."""
+    import random
+    import re
+    import zlib
+    from crf_b200 import _cabi
+    rng = random.Random(77)
+    monkeypatch.setenv("CRF_GUNZIP_TRACE", "1")
+
+    def piece(kind, n):
+        if kind == "dna":
+            return bytes(rng.choice(b"ACGT") for _ in range(n))
+        if kind == "soft-masked":
+            return bytes(rng.choice(b"ACGTacgtN\n") for _ in range(n))
+        if kind == "text":
+            return " ".join(rng.choice(["the", "quick", "brown", "fox", "jumps", "over", "lazy", "dog", "\n"])
+                            for _ in range(n // 4 + 1)).encode()[:n]
+        if kind == "zeros":
+            return bytes(n)
+        if kind == "noise":
+            return rng.randbytes(n)
+        unit = rng.randbytes(rng.randint(1, 40))
+        return (unit * (n // len(unit) + 1))[:n]
+
+    n_parallel = n_chunks = n_carried = 0
+    for case in range(30):
+        if case < 4:                                     # stored blocks in the middle: chunks that start there find a later block
+            kinds = ["dna", "noise", "dna", "noise", "soft-masked"]
+        else:
+            kinds = [rng.choice(["dna", "soft-masked", "text", "zeros", "noise", "periodic"]) for _ in range(rng.randint(1, 6))]
+        data = b"".join(piece(k, rng.randint(50_000, 400_000)) for k in kinds)
+        strategy = rng.choice([zlib.Z_DEFAULT_STRATEGY] * 5 + [zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE])
+        c = zlib.compressobj(rng.randint(1, 9), zlib.DEFLATED, 31, rng.randint(4, 9), strategy)
+        comp, pos = b"", 0
+        for _ in range(rng.choice([0, 0, 2])):
+            n = rng.randint(0, len(data) // 3)
+            comp += c.compress(data[pos:pos + n]) + c.flush(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH]))
+            pos += n
+        comp += c.compress(data[pos:]) + c.flush()
+        monkeypatch.setenv("CRF_GUNZIP_CHUNK_KB", str(rng.choice([4, 16, 64])))
+        capfd.readouterr()
+        assert _cabi.gunzip(comp, use_zlib=2) == data, (case, kinds)
+        m = re.search(r"parallel: (\d+) round\(s\), (\d+) marker chunk\(s\) stitched, (\d+) carried", capfd.readouterr().err)
+        if m:
+            n_parallel += 1
+            n_chunks += int(m.group(2))
+            n_carried += int(m.group(3))
+    assert n_parallel >= 20 and n_chunks >= 60 and n_carried >= 3
+
+
 def test_fasta_reader_gzip_decoders_agree(tmp_path, monkeypatch):
     """A gzip FASTA through the reader's own decoder and through zlib alone (CRF_GUNZIP_ZLIB=1): same records, same bases."""
     import gzip
