@@ -340,6 +340,27 @@ def test_gunzip_one_stream_on_several_threads(monkeypatch, capfd):
     assert n_parallel >= 20 and n_chunks >= 60 and n_carried >= 3
 
 
+def test_gunzip_fuzz_under_sanitizers(tmp_path):
+    """tests/fuzz_inflate.cpp built with AddressSanitizer + UBSan against csrc/crf_inflate.h: random zlib-made streams (a
+    quarter with flipped bits) through the several-threads decoder with tiny chunks -- decoders that start on a phantom block
+    boundary decode garbage, and must do so without touching a byte outside their buffers."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(os.path.dirname(here), "colab-repeat-finder_b200", "csrc")
+    exe = str(tmp_path / "fuzz_inflate")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-pthread",
+           "-I", csrc, os.path.join(here, "fuzz_inflate.cpp"), "-o", exe, "-lz"]
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    if built.returncode != 0:
+        pytest.skip("sanitizer build not available here: " + built.stderr[-300:])
+    run = subprocess.run([exe, "2026", "24"], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-4000:]
+    assert "24 cases" in run.stdout
+
+
 def test_fasta_reader_gzip_decoders_agree(tmp_path, monkeypatch):
     """A gzip FASTA through the reader's own decoder and through zlib alone (CRF_GUNZIP_ZLIB=1): same records, same bases."""
     import gzip
