@@ -200,17 +200,15 @@ def stitch(plan, open_runs, run_end_fn, exchange_fn=None, rank=0, owner=None):
     return [(rec, s, final_i0[i] + k, k) for i, (rec, s, _e, k) in enumerate(open_runs)]
 
 
-MAX_OPEN_PER_RANK = 256
-
-
 def stitch_collective(plan, open_mine, run_end_fn, rank, world, dist, device):
-    """stitch() for world > 1 with fixed-size tensor collectives (two small all-gathers + one all-reduce
-    per hop) instead of pickled objects.  open_mine: this rank's (record, start, end_lower_bound, k) rows.
-    Returns the stitched rows of ALL ranks, identical on every rank."""
+    """stitch() for world > 1 with tensor collectives (a count all-gather, a row all-gather sized by the largest count, one
+    all-reduce per hop) instead of pickled objects.  open_mine: this rank's (record, start, end_lower_bound, k) rows --
+    any number of them.  Returns the stitched rows of ALL ranks, identical on every rank."""
     import torch
-    if len(open_mine) > MAX_OPEN_PER_RANK:
-        raise RuntimeError(f"{len(open_mine)} open runs on one rank (limit {MAX_OPEN_PER_RANK})")
-    mine = torch.full((MAX_OPEN_PER_RANK + 1, 4), -1, dtype=torch.int64)
+    counts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, torch.tensor([len(open_mine)], dtype=torch.int64, device=device))
+    slots = max(int(counts.max().item()), 1)
+    mine = torch.full((slots + 1, 4), -1, dtype=torch.int64)
     mine[0, 0] = len(open_mine)
     if open_mine:
         mine[1:1 + len(open_mine)] = torch.tensor(open_mine, dtype=torch.int64)
