@@ -646,7 +646,12 @@ static bool gunzip(const uint8_t *gz, size_t n, OutBuf &out, unsigned n_threads,
     if (n < 18) return false;
     if (!parallel_chunk_bytes) {
         const char *kb = getenv("CRF_GUNZIP_CHUNK_KB");  // (tests: small chunks send small inputs through the several-threads path)
-        parallel_chunk_bytes = kb && atoi(kb) > 0 ? (size_t)atoi(kb) << 10 : (size_t)CRF_INFLATE_CHUNK_BYTES;
+        if (kb && atoi(kb) > 0) {
+            parallel_chunk_bytes = (size_t)atoi(kb) << 10;
+        } else {                                         // 8 MB, less when that would leave threads without a chunk (>= 1 MB:
+            const size_t P = std::min(16u, std::max(1u, n_threads));             // finding a block start costs 1-15 ms)
+            parallel_chunk_bytes = std::min<size_t>(CRF_INFLATE_CHUNK_BYTES, std::max<size_t>((size_t)1 << 20, n / P + 1));
+        }
     }
     const uint32_t isize_hint = gz[n - 4] | (gz[n - 3] << 8) | (gz[n - 2] << 16) | ((uint32_t)gz[n - 1] << 24);
     if (!out.reserve(std::max<size_t>((size_t)isize_hint, n * 4) + (1u << 20))) return false;
