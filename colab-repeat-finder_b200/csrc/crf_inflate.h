@@ -34,9 +34,31 @@
 
 namespace crf_inflate {
 
-struct OutBuf {                                          // malloc'ed so that growing it is a realloc (mremap for big blocks)
+// Output buffer that grows.  On Linux its own anonymous mapping, grown with mremap (pages move, bytes are not copied) and
+// advised MADV_HUGEPAGE as a whole: first touch of a big buffer otherwise costs as much as decoding into it (488 MB: 409 ms
+// on one thread in 4 KB pages).  (malloc + madvise on a part of the block splits the mapping, after which realloc can no
+// longer mremap and copies instead: 160 ms for one growth step of a 155 MB buffer.)
+struct OutBuf {
     uint8_t *p = nullptr;
     size_t size = 0, cap = 0;
+    OutBuf() {}
+    OutBuf(const OutBuf &) = delete;
+    OutBuf &operator=(const OutBuf &) = delete;
+#if defined(__linux__)
+    ~OutBuf() { if (p) munmap(p, cap); }
+    bool reserve(size_t need) {
+        if (need <= cap) return true;
+        need = (need + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        void *q = p ? mremap(p, cap, need, MREMAP_MAYMOVE) : mmap(nullptr, need, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (q == MAP_FAILED) return false;
+        p = (uint8_t *)q;
+        cap = need;
+#ifdef MADV_HUGEPAGE
+        madvise(p, cap, MADV_HUGEPAGE);                  // (advice only)
+#endif
+        return true;
+    }
+#else
     ~OutBuf() { free(p); }
     bool reserve(size_t need) {
         if (need <= cap) return true;
@@ -44,14 +66,9 @@ struct OutBuf {                                          // malloc'ed so that gr
         if (!q) return false;
         p = q;
         cap = need;
-#ifdef MADV_HUGEPAGE
-        if (need >= ((size_t)8 << 20)) {                 // first touch of a big buffer costs as much as decoding into it:
-            const uintptr_t lo = ((uintptr_t)p + 4095) & ~(uintptr_t)4095, hi = ((uintptr_t)p + need) & ~(uintptr_t)4095;
-            if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);       // ask for 2 MB pages (advice only)
-        }
-#endif
         return true;
     }
+#endif
 };
 
 enum : uint32_t { K_INVALID = 0, K_LITERAL = 1, K_LENGTH = 2, K_EOB = 3, K_SUB = 4 };
@@ -198,6 +215,7 @@ struct DecoderT {
     OutBuf *out = nullptr;                               // (capacity in bytes; `op` counts elements of T)
     size_t op = 0;
     size_t op_limit = ~(size_t)0;                        // give up beyond this many elements (marker chunks: bounded memory)
+    bool hit_limit = false;                              // ... and say that this, not bad data, was the reason
 
     inline uint64_t bitpos() const { return 8 * (uint64_t)(in - base) - (uint64_t)bc; }
     inline void seek(uint64_t bit) {
@@ -240,7 +258,8 @@ struct DecoderT {
         if ((len ^ 0xFFFFu) != nlen) return false;
         in += 4;
         if ((size_t)(in_end - in) < len) return false;
-        if (op > op_limit || !out->reserve((op + len + 512) * sizeof(T))) return false;
+        if (op > op_limit) { hit_limit = true; return false; }
+        if (!out->reserve((op + len + 512) * sizeof(T))) return false;
         T *dst = (T *)out->p + op;
         for (uint32_t i = 0; i < len; ++i) dst[i] = in[i];
         in += len;
@@ -260,7 +279,8 @@ struct DecoderT {
         bool ok = false;
         for (;;) {
             if (cap - o < 512) {                         // room for a run of literals + the longest match + copy overrun
-                if (o > op_limit || !out->reserve((o + o / 2 + (1u << 20)) * sizeof(T))) break;
+                if (o > op_limit) { hit_limit = true; break; }
+                if (!out->reserve((o + o / 2 + (1u << 20)) * sizeof(T))) break;
                 buf = (T *)out->p;
                 cap = out->cap / sizeof(T);
             }
@@ -447,6 +467,10 @@ struct MarkerChunk {
     int state = 0;                                       // RUN_* of its decoder
 };
 constexpr size_t WINDOW = 32768;
+#ifndef CRF_INFLATE_MARKER_BUDGET
+#define CRF_INFLATE_MARKER_BUDGET ((size_t)96 << 20)
+#endif
+constexpr size_t MARKER_BUDGET_MIN = CRF_INFLATE_MARKER_BUDGET;      // output symbols per chunk, at least
 
 static bool marker_reset(MarkerChunk &c, size_t expect_out) {
     if (!c.buf.reserve((WINDOW + expect_out + (1u << 16)) * 2)) return false;
@@ -454,7 +478,11 @@ static bool marker_reset(MarkerChunk &c, size_t expect_out) {
     for (size_t j = 0; j < WINDOW; ++j) q[j] = (uint16_t)(256 + j);
     c.dec.out = &c.buf;
     c.dec.op = WINDOW;
-    c.dec.op_limit = WINDOW + 3 * expect_out;            // (a stream that expands far more than FASTA text is left to one thread)
+    // Budget of a chunk: 3 x what FASTA text expands to, and room for the N runs of a genome (tens of Mbp that take a few KB of
+    // input) -- buffers grow on demand, so only a chunk that does expand like that pays for it.  A chunk beyond it stops, the
+    // decoder in front may spend the same again to cover it, and failing that the stream is left to one thread.
+    c.dec.op_limit = WINDOW + std::max<size_t>(3 * expect_out, MARKER_BUDGET_MIN);
+    c.dec.hit_limit = false;
     return true;
 }
 
@@ -501,6 +529,10 @@ static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf
     std::vector<MarkerChunk> chunks(P);
     const uint64_t end_bit = 8 * (uint64_t)(n - 8);      // (the trailer is no block)
     const bool trace = getenv("CRF_GUNZIP_TRACE") != nullptr;
+    auto give_up = [&](const char *why) {                // (the caller then decodes the stream on one thread)
+        if (trace) fprintf(stderr, "[crf_inflate] parallel: gave up: %s\n", why);
+        return false;
+    };
     unsigned n_rounds = 0, n_used = 0, n_carried = 0;
     std::vector<uint8_t> luts;
     double ms_decode = 0, ms_stitch = 0, ms_resolve = 0;
@@ -531,6 +563,8 @@ static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf
                 if (c.state != DecoderT<uint16_t>::RUN_ERROR) return;
                 from = c.start_bit + 1;                  // it was no block after all: look further
                 c.start_bit = ~0ull;
+                if (c.dec.hit_limit) break;              // ... unless it was the output that outgrew the chunk's budget (a long
+                                                         // run of N: 1000 bytes per byte): the decoder in front covers this range
             }
             c.state = 0;
           } catch (...) { threw = true; }                // (bad_alloc in a worker must not leave its thread)
@@ -540,7 +574,7 @@ static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf
         }
         work(0);
         for (auto &t : th) t.join();
-        if (threw || head_state == Decoder::RUN_ERROR) return false;
+        if (threw || head_state == Decoder::RUN_ERROR) return give_up("the first chunk of a round does not decode");
         ms_decode += ms_since(t_round);
         t_round = now();
         // stitch: `pos` = the true block boundary reached so far, by the decoder `last` (-1: the head)
@@ -551,13 +585,17 @@ static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf
         for (unsigned k = 1; k < P; ++k) {
             MarkerChunk &c = chunks[k];
             if (c.start_bit == ~0ull) continue;          // found nothing in its range: the previous decoder covers it
-            if (final_seen) return false;                // a "block" behind the end of the stream
-            if (pos > c.start_bit) return false;         // started on a phantom
+            if (final_seen) return give_up("a chunk found a block behind the end of the stream");
+            if (pos > c.start_bit) return give_up("a chunk started on a phantom block");
             if (pos < c.start_bit) {                     // carry the previous decoder on up to this chunk's start
                 int st;
                 if (last < 0) { st = head.run(head_tb, c.start_bit); pos = head.bitpos(); }
-                else { st = chunks[last].dec.run(chunks[last].tb, c.start_bit); pos = chunks[last].dec.bitpos(); }
-                if (st != Decoder::RUN_STOPPED || pos != c.start_bit) return false;
+                else {                                   // (what lies in between may be a chunk that stopped because its output
+                    DecoderT<uint16_t> &pd = chunks[last].dec;                  //  outgrew the budget: the same budget again)
+                    pd.op_limit = pd.op + std::max<size_t>(3 * ratio * chunk_bytes, MARKER_BUDGET_MIN);
+                    st = pd.run(chunks[last].tb, c.start_bit); pos = pd.bitpos();
+                }
+                if (st != Decoder::RUN_STOPPED || pos != c.start_bit) return give_up("the decoder in front does not arrive at a chunk's start");
                 ++n_carried;
             }
             used.push_back(k);
@@ -569,7 +607,7 @@ static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf
         size_t total = head.op;
         std::vector<size_t> at(used.size());
         for (size_t i = 0; i < used.size(); ++i) { at[i] = total; total += chunks[used[i]].dec.op - WINDOW; }
-        if (!out.reserve(total + total / 8 + (1u << 20))) return false;
+        if (!out.reserve(total + total / 8 + (1u << 20))) return give_up("out of memory");
         std::vector<std::vector<uint8_t>> window(used.size(), std::vector<uint8_t>(WINDOW, 0));
         for (size_t i = 0; i < used.size(); ++i) {       // the 32 KB in front of each chunk, handed down the chain
             std::vector<uint8_t> &w = window[i];
@@ -630,7 +668,7 @@ static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf
             return true;
         }
         // next round: the head decoder goes on from the boundary the last chunk reached
-        if (pos <= here || pos >= end_bit) return false; // no progress, or blocks that run into the trailer: not a sane stream
+        if (pos <= here || pos >= end_bit) return give_up("no progress, or blocks that run into the trailer");
         head.op = total;
         if (last >= 0) head.seek(pos);
     }
