@@ -343,6 +343,12 @@ static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf
     }
     if (!fa->bases) fa->bases = (uint8_t *)malloc(alloc);
     if (!fa->bases) { set_err("crf_fasta_open: out of host memory (%llu bases)", (unsigned long long)total); return CRF_ERR_NOMEM; }
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    if (!fa->pinned && alloc >= ((size_t)8 << 20)) {    // gigabytes touched for the first time by the compaction below: 2 MB pages
+        const uintptr_t lo = ((uintptr_t)fa->bases + 4095) & ~(uintptr_t)4095, hi = ((uintptr_t)fa->bases + alloc) & ~(uintptr_t)4095;
+        if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);              // (advice only; the block is never realloc'ed)
+    }
+#endif
 
     lap("alloc");
     uint8_t *dst = fa->bases;
