@@ -36,6 +36,37 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_cabi.ScanStats) == 2 * 8 + 6 * 8 + 2 * 4 + 8
 
 
+def test_ctypes_structs_have_the_layout_a_c_compiler_gives_the_header(tmp_path):
+    """include/crf.h compiled as C99 (-pedantic: the boundary is plain C); sizeof and every field offset of its four structs,
+    as gcc lays them out, against the ctypes mirrors in _cabi."""
+    import shutil
+    import subprocess
+    import pytest
+    from crf_b200 import _cabi
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    mirrors = {"crf_scan_params": _cabi.ScanParams, "crf_seq_info_t": _cabi.SeqInfo, "crf_scan_stats_t": _cabi.ScanStats,
+               "crf_xchg_result_t": _cabi.XchgResult}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "crf.h"', "int main(void) {"]
+    for c_name, mirror in mirrors.items():
+        lines.append(f'    printf("{c_name} sizeof %zu\\n", sizeof({c_name}));')
+        for field, _ in mirror._fields_:
+            lines.append(f'    printf("{c_name} {field} %zu\\n", offsetof({c_name}, {field}));')
+    lines += ["    return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = str(tmp_path / "probe")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe])
+    seen = 0
+    for line in subprocess.check_output([exe], text=True).splitlines():
+        c_name, what, value = line.split()
+        mirror = mirrors[c_name]
+        assert int(value) == (ctypes.sizeof(mirror) if what == "sizeof" else getattr(mirror, what).offset), line
+        seen += 1
+    assert seen == sum(1 + len(m._fields_) for m in mirrors.values())
+    assert _cabi.XCHG_MAX_WORLD == int(re.search(r"#define CRF_XCHG_MAX_WORLD (\d+)", open(os.path.join(ROOT, "include", "crf.h")).read()).group(1))
+
+
 def test_sass_is_sm100a_only():
     import subprocess
     from crf_b200 import build
