@@ -67,6 +67,33 @@ def test_ctypes_structs_have_the_layout_a_c_compiler_gives_the_header(tmp_path):
     assert _cabi.XCHG_MAX_WORLD == int(re.search(r"#define CRF_XCHG_MAX_WORLD (\d+)", open(os.path.join(ROOT, "include", "crf.h")).read()).group(1))
 
 
+def test_c_example_builds_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/fasta_to_bed.c -- the whole path through the C ABI from plain C99 -- compiles with -pedantic -Werror, links
+    against libcrf.so and runs: the host-only half (FASTA reader, packer) works anywhere; without a GPU the context call must
+    return a status and a message (exit 1), with one the BED file must be there."""
+    import shutil
+    import subprocess
+    import pytest
+    from crf_b200 import build
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    lib_dir = os.path.dirname(build.build())
+    exe = str(tmp_path / "fasta_to_bed")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "fasta_to_bed.c"), "-o", exe, "-L", lib_dir, "-l:libcrf.so",
+                           "-Wl,-rpath," + lib_dir])
+    fa = tmp_path / "tiny.fa"
+    fa.write_text(">a desc\nACGTACGTACGTACGTACGTNNNN\nacacacacacacacacac\n>b\nTTTTTTTTTTTTTTTTTTTT\n")
+    bed = tmp_path / "tiny.bed"
+    run = subprocess.run([exe, str(fa), str(bed)], capture_output=True, text=True)
+    assert "2 records, 62 bp" in run.stdout
+    if run.returncode == 0:                              # a GPU is present
+        assert bed.read_text() == "a\t0\t20\tACGT\na\t24\t42\tAC\nb\t0\t20\tT\n"
+    else:
+        assert run.returncode == 1 and "crf_ctx_create" in run.stderr and "status" in run.stderr
+    assert subprocess.run([exe], capture_output=True).returncode == 2
+
+
 def test_sass_is_sm100a_only():
     import subprocess
     from crf_b200 import build
