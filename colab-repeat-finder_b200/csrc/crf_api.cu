@@ -1859,7 +1859,7 @@ static int write_rows_impl(const char *path, int append, int tsv, const char *na
     std::vector<std::vector<char>> bufs(n_thr);
     std::vector<size_t> used(n_thr, 0);
     std::vector<std::thread> th(n_thr);
-    bool no_memory = false;
+    std::atomic<bool> no_memory{false};             // (set by the formatting threads)
     for (uint64_t wave = 0; wave < n_rows && ok; wave += SLICE_ROWS * n_thr) {
         for (uint32_t t = 0; t < n_thr; ++t) {
             const uint64_t lo = std::min(n_rows, wave + SLICE_ROWS * t), hi = std::min(n_rows, lo + SLICE_ROWS);
