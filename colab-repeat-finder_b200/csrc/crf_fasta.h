@@ -157,7 +157,11 @@ static void run_parallel(unsigned n_threads, size_t n_items, const std::function
 // in a 'BC' extra field, so the blocks are found by hopping over the headers and inflated on all threads.
 // Returns false if the file is not BGZF from the first to the last byte (the caller then inflates it serially);
 // *bad is set if it is BGZF but a block is corrupt.
-static bool inflate_bgzf(const FileBytes &in, unsigned n_threads, std::vector<uint8_t> &out, bool *bad) {
+// Each block is decoded by the reader's own DEFLATE decoder (crf_inflate.h, ~2 x zlib on FASTA text) into a scratch buffer --
+// its copies may write a few bytes beyond a match, which in the shared output would be the next block's -- and copied to its
+// place once length and CRC-32 agree; a block it does not take (or CRF_GUNZIP_ZLIB=1) goes through zlib, which then decides.
+// The output is a mapping of its own (no zero-fill before the blocks arrive, 2 MB pages).
+static bool inflate_bgzf(const FileBytes &in, unsigned n_threads, crf_inflate::OutBuf &out, bool *bad) {
     struct Block { uint64_t cdata, clen, out; uint32_t isize, crc; };
     std::vector<Block> blocks;
     const uint8_t *d = in.data;
@@ -188,28 +192,52 @@ static bool inflate_bgzf(const FileBytes &in, unsigned n_threads, std::vector<ui
         blocks.push_back(b);
         pos += bsize;
     }
-    out.resize(total);
-    std::atomic<bool> failed{false};
+    if (!out.reserve(total + 64)) throw std::bad_alloc();
+    out.size = total;
+    uint8_t *const dst = out.p;
+    const bool own_decoder = getenv("CRF_GUNZIP_ZLIB") == nullptr;
+    std::atomic<bool> failed{false}, no_memory{false};
     const size_t GROUP = 128;                             // blocks per work item (<= 8 MiB of text)
     run_parallel(n_threads, (blocks.size() + GROUP - 1) / GROUP, [&](size_t g) {
+      try {
+        crf_inflate::OutBuf scratch;
+        crf_inflate::Tables tables;
         z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (inflateInit2(&zs, -15) != Z_OK) { failed = true; return; }
+        bool zs_ready = false;
         for (size_t i = g * GROUP; i < std::min(blocks.size(), (g + 1) * GROUP) && !failed; ++i) {
             const Block &b = blocks[i];
             if (b.isize == 0) continue;                   // the empty end-of-file block
+            if (own_decoder) {
+                crf_inflate::Decoder dec;
+                dec.base = dec.in = d + b.cdata;
+                dec.in_end = dec.in + b.clen;
+                dec.out = &scratch;
+                dec.op = 0;
+                if (dec.run(tables) == crf_inflate::Decoder::RUN_FINAL && dec.op == b.isize &&
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), scratch.p, b.isize) == b.crc) {
+                    memcpy(dst + b.out, scratch.p, b.isize);
+                    continue;
+                }
+            }
+            if (!zs_ready) {
+                memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) { failed = true; return; }
+                zs_ready = true;
+            }
             zs.next_in = const_cast<Bytef *>(d + b.cdata);
             zs.avail_in = (uInt)b.clen;
-            zs.next_out = out.data() + b.out;
+            zs.next_out = dst + b.out;
             zs.avail_out = b.isize;
             const int rc = inflate(&zs, Z_FINISH);
             if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-                (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data() + b.out, b.isize) != b.crc)
+                (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + b.out, b.isize) != b.crc)
                 failed = true;
             inflateReset(&zs);
         }
-        inflateEnd(&zs);
+        if (zs_ready) inflateEnd(&zs);
+      } catch (const std::bad_alloc &) { no_memory = true; failed = true; }      // (nothing leaves a worker thread)
     });
+    if (no_memory) throw std::bad_alloc();
     *bad = failed;
     return true;
 }
@@ -252,13 +280,13 @@ static int fasta_open_impl(const char *path, uint32_t n_threads, int pinned, crf
     if (n_threads == 0) n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
     if (n >= 2 && t[0] == 0x1f && t[1] == 0x8b) {
         bool bad = false;
-        const bool bgzf = inflate_bgzf(file, n_threads, plain, &bad);
+        const bool bgzf = inflate_bgzf(file, n_threads, inflated, &bad);
         if (bgzf && bad) { set_err("crf_fasta_open: %s has a corrupt BGZF block", path); return CRF_ERR_ARG; }
         // a plain gzip stream: the reader's own decoder (crf_inflate.h); whatever it does not take goes to zlib, which decides
         const bool own = !bgzf && getenv("CRF_GUNZIP_ZLIB") == nullptr && crf_inflate::gunzip(file.data, file.size, inflated, n_threads);
         if (!bgzf && !own && !inflate_all(file, plain)) { set_err("crf_fasta_open: %s is not a valid gzip stream", path); return CRF_ERR_ARG; }
-        t = own ? inflated.p : plain.data();
-        n = own ? inflated.size : plain.size();
+        t = bgzf || own ? inflated.p : plain.data();
+        n = bgzf || own ? inflated.size : plain.size();
         lap(bgzf ? "bgzf" : own ? "gunzip" : "gzip/zlib");
     }
     lap("read");

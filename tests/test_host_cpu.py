@@ -64,7 +64,7 @@ def test_fasta_reader_large_multi_piece(tmp_path, eol):
                     assert fa.record(i).tobytes() == seq, (path, threads, i)
 
 
-def _bgzf(raw, block=30000):
+def _bgzf(raw, block=30000, level=6, strategy=0):
     """bgzip's container: gzip members of <= 64 KiB with a 'BC' extra field holding the member's size, then the empty
     end-of-file block."""
     import struct
@@ -72,7 +72,7 @@ def _bgzf(raw, block=30000):
     out = []
     for i in list(range(0, len(raw), block)) + [None]:
         chunk = b"" if i is None else raw[i:i + block]
-        comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
         data = comp.compress(chunk) + comp.flush()
         bsize = 12 + 6 + len(data) + 8
         out.append(b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) +
@@ -80,7 +80,7 @@ def _bgzf(raw, block=30000):
     return b"".join(out)
 
 
-def test_fasta_reader_bgzf_parallel_blocks(tmp_path):
+def test_fasta_reader_bgzf_parallel_blocks(tmp_path, monkeypatch):
     from crf_b200 import _cabi
     rng = np.random.default_rng(11)
     chunks = []
@@ -96,6 +96,19 @@ def test_fasta_reader_bgzf_parallel_blocks(tmp_path):
     for threads in (1, 6):
         with _cabi.Fasta(str(path), n_threads=threads) as fa:
             assert [(n, fa.record(i).tobytes()) for i, n in enumerate(fa.names)] == want
+    # the blocks go through the reader's own DEFLATE decoder; zlib per block (CRF_GUNZIP_ZLIB=1) must give the same, and so
+    # must blocks of every DEFLATE type: stored (level 0), fixed codes (Z_FIXED), full-size 65 280-byte blocks
+    import zlib
+    monkeypatch.setenv("CRF_GUNZIP_ZLIB", "1")
+    with _cabi.Fasta(str(path), n_threads=3) as fa:
+        assert [(n, fa.record(i).tobytes()) for i, n in enumerate(fa.names)] == want
+    monkeypatch.delenv("CRF_GUNZIP_ZLIB")
+    for k, (block, level, strategy) in enumerate([(65280, 0, 0), (65280, 6, zlib.Z_FIXED), (65280, 1, 0), (1000, 9, zlib.Z_HUFFMAN_ONLY)]):
+        variant = tmp_path / f"v{k}.fa.bgz"
+        part = raw[:3_000_000]
+        variant.write_bytes(_bgzf(part, block, level, strategy))
+        with _cabi.Fasta(str(variant), n_threads=4) as fa:
+            assert [(n, fa.record(i).tobytes()) for i, n in enumerate(fa.names)] == _simple_fasta(part)
     # BGZF blocks followed by an ordinary gzip member: not BGZF throughout, read by the serial path
     mixed = tmp_path / "mixed.fa.gz"
     mixed.write_bytes(_bgzf(raw[:1_000_000])[:-28] + gzip.compress(raw[1_000_000:2_000_000], 1))
