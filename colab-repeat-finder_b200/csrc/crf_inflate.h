@@ -585,7 +585,7 @@ static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf
         for (unsigned k = 1; k < P; ++k) {
             MarkerChunk &c = chunks[k];
             if (c.start_bit == ~0ull) continue;          // found nothing in its range: the previous decoder covers it
-            if (final_seen) return give_up("a chunk found a block behind the end of the stream");
+            if (final_seen) break;                       // (what later chunks found belongs to the next member of the file)
             if (pos > c.start_bit) return give_up("a chunk started on a phantom block");
             if (pos < c.start_bit) {                     // carry the previous decoder on up to this chunk's start
                 int st;
@@ -594,6 +594,10 @@ static bool gunzip_parallel(const uint8_t *gz, size_t n, size_t data_pos, OutBuf
                     DecoderT<uint16_t> &pd = chunks[last].dec;                  //  outgrew the budget: the same budget again)
                     pd.op_limit = pd.op + std::max<size_t>(3 * ratio * chunk_bytes, MARKER_BUDGET_MIN);
                     st = pd.run(chunks[last].tb, c.start_bit); pos = pd.bitpos();
+                }
+                if (st == Decoder::RUN_FINAL) {          // the member ends before this chunk: it is the next member's
+                    final_seen = true;
+                    break;
                 }
                 if (st != Decoder::RUN_STOPPED || pos != c.start_bit) return give_up("the decoder in front does not arrive at a chunk's start");
                 ++n_carried;
@@ -719,9 +723,10 @@ static bool gunzip(const uint8_t *gz, size_t n, OutBuf &out, unsigned n_threads,
         Member m;
         m.out_lo = op;
         size_t after = 0, op_par = op;
-        // several threads for a big first member that is the whole file (the trailer it ends at is the end of the input)
-        if (pos == 0 && parallel_chunk_bytes != ~(size_t)0 && n_threads > 1 &&
-            gunzip_parallel(gz, n, p, out, &op_par, &after, n_threads, parallel_chunk_bytes) && after + 8 == n) {
+        // several threads for a member with at least two chunks of input behind its header (for the last or only member that
+        // is known; an earlier one may turn out shorter: the chunks beyond its end are then dropped)
+        if (parallel_chunk_bytes != ~(size_t)0 && n_threads > 1 &&
+            gunzip_parallel(gz, n, p, out, &op_par, &after, n_threads, parallel_chunk_bytes) && after + 8 <= n) {
             op = op_par;
             p = after;
         } else {
