@@ -376,6 +376,88 @@ def test_gunzip_fuzz_under_sanitizers(tmp_path):
     assert "24 cases" in run.stdout
 
 
+def test_reader_and_packer_under_sanitizers(tmp_path, monkeypatch):
+    """tests/fuzz_reader.cpp: csrc/crf_fasta.h + csrc/crf_pack.h compiled without the CUDA runtime under ASan + UBSan.  Plain,
+    gzip (several threads, small chunks), multi-member and BGZF files with ragged lines, CRLF, IUPAC letters, empty records and
+    30 000 short reads: the harness checks the planes, the exotic list and the mask runs against the text base by base; its
+    record table (name, length, FNV-1a of the bases) is compared here with the line-by-line reading of the same bytes."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(os.path.dirname(here), "colab-repeat-finder_b200", "csrc")
+    exe = str(tmp_path / "fuzz_reader")
+    built = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                            "-pthread", "-I", csrc, "-I", os.path.join(os.path.dirname(here), "include"),
+                            os.path.join(here, "fuzz_reader.cpp"), "-o", exe, "-lz"], capture_output=True, text=True)
+    if built.returncode != 0:
+        pytest.skip("sanitizer build not available here: " + built.stderr[-300:])
+    rng = np.random.default_rng(2027)
+
+    def text(n_records, max_len, alphabet, eol):
+        parts = []
+        for r in range(n_records):
+            size = int(rng.integers(0, max_len + 1))
+            seq = rng.choice(np.frombuffer(alphabet, dtype=np.uint8), size=size).tobytes()
+            width = int(rng.choice([60, 61, 70, 1, 1_000_000]))
+            parts.append(b">r%d some text" % r + eol)
+            parts.extend(seq[i:i + width] + eol for i in range(0, size, width))
+        return b"".join(parts)
+
+    files = {}
+    big = text(5, 3_500_000, b"ACGTacgtNNn", b"\n")
+    files["big.fa"] = big
+    files["big.fa.gz"] = gzip.compress(big, 1)
+    files["big.fa.bgz"] = _bgzf(big, 65280)
+    files["members.fa.gz"] = gzip.compress(big[:4_000_000], 6) + gzip.compress(big[4_000_000:], 1)
+    files["iupac_crlf.fa"] = text(40, 30_000, b"ACGTRYKMSWBDHVNacgtn", b"\r\n")
+    reads = text(30_000, 150, b"ACGTN", b"\n")
+    files["reads.fa"] = reads
+    files["reads.fa.gz"] = gzip.compress(reads, 4)
+    for name, raw in files.items():
+        (tmp_path / name).write_bytes(raw)
+    monkeypatch.setenv("CRF_GUNZIP_CHUNK_KB", "256")
+    run = subprocess.run([exe] + [str(tmp_path / n) for n in files], capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-4000:]
+
+    def fnv(seq):
+        h = 1469598103934665603
+        for block in range(0, len(seq), 1 << 16):       # (python ints: keep the loop out of the per-byte path where possible)
+            for c in seq[block:block + (1 << 16)]:
+                h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    plain_of = {"big.fa": big, "big.fa.gz": big, "big.fa.bgz": big, "members.fa.gz": big, "iupac_crlf.fa": files["iupac_crlf.fa"],
+                "reads.fa": reads, "reads.fa.gz": reads}
+    lines = [ln for ln in run.stdout.splitlines() if " records " in ln]
+    assert len(lines) == 2 * len(files)
+    want_cache = {}
+    for ln in lines:
+        head, _, table = ln.partition(";")
+        name = os.path.basename(head.split(" threads ")[0])
+        if name not in want_cache:
+            recs = _simple_fasta(plain_of[name])
+            hashed = name in ("iupac_crlf.fa",)          # hash one file in full (pure-Python FNV is slow), lengths for all
+            want_cache[name] = (recs, hashed)
+        recs, hashed = want_cache[name]
+        got = table.split()
+        assert len(got) == len(recs), name
+        for entry, (rec_name, seq) in zip(got, recs):
+            g_name, g_len, g_hash = entry.rsplit(":", 2)
+            assert g_name == rec_name and int(g_len) == len(seq), (name, entry)
+            if hashed:
+                assert int(g_hash, 16) == fnv(seq), (name, entry)
+    # the same bytes whatever the container and the thread count
+    by_file = {}
+    for ln in lines:
+        head, _, table = ln.partition(";")
+        by_file.setdefault(os.path.basename(head.split(" threads ")[0]), set()).add(table)
+    assert all(len(v) == 1 for v in by_file.values())
+    assert by_file["big.fa"] == by_file["big.fa.gz"] == by_file["big.fa.bgz"] == by_file["members.fa.gz"]
+    assert by_file["reads.fa"] == by_file["reads.fa.gz"]
+
+
 def test_fasta_reader_gzip_decoders_agree(tmp_path, monkeypatch):
     """A gzip FASTA through the reader's own decoder and through zlib alone (CRF_GUNZIP_ZLIB=1): same records, same bases."""
     import gzip
