@@ -1,5 +1,6 @@
 // Sanitizer harness for the host-only half of the library: the FASTA reader (csrc/crf_fasta.h: plain / gzip / BGZF input,
-// header scan, threaded compaction) and the packer (csrc/crf_pack.h: planes, exotic list, mask runs) compiled WITHOUT the CUDA
+// header scan, threaded compaction), the packer (csrc/crf_pack.h: planes, exotic list, mask runs) and the BED / TSV row writer
+// (csrc/crf_rows.h, with FUZZ_READER_ROWS=n) compiled WITHOUT the CUDA
 // runtime -- the three runtime calls they make (page-locked allocation) are stubbed to "no device" -- under AddressSanitizer +
 // UBSan or ThreadSanitizer.  Each file given on the command line is opened with 1 and 7 threads, packed, and the planes are
 // checked against the text base by base; the record table is printed so that the caller (tests/test_host_cpu.py) can compare
@@ -11,6 +12,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <string>
 #include <new>
 #include <vector>
 
@@ -31,6 +33,7 @@ static void set_err(const char *fmt, ...) {
 }
 extern "C" const char *crf_last_error(void) { return g_err; }
 
+#include "crf_rows.h"
 #include "crf_fasta.h"
 #include "crf_pack.h"
 
@@ -77,6 +80,31 @@ static int check_file(const char *path, unsigned threads) {
         for (uint64_t i = 0; i < n_runs; ++i) in_runs += runs[2 * i + 1] - runs[2 * i];
         if (masked != in_runs) bad = 1;
         if (bad) printf("PLANES DIFFER from the text (%s)\n", path);
+    }
+    // the row writer (csrc/crf_rows.h) on made-up rows of these records: `rows` of them, one thread below 131 072 rows and
+    // several above; the caller compares the file with its own formatting of the same rows (row i: record i % n, start
+    // (i * 7919) % (len - k + 1), k = 1 + i % 50 clipped to the record, end = start + 3k)
+    const char *rows_env = getenv("FUZZ_READER_ROWS");
+    if (rows_env && total && threads == 7) {
+        std::vector<uint32_t> rec, st, en, kk;
+        const uint64_t want = strtoull(rows_env, nullptr, 10);
+        for (uint64_t i = 0; rec.size() < want && i < 4 * want + 64; ++i) {
+            const uint64_t r = i % n_rec, len = offsets[r + 1] - offsets[r];
+            if (!len) continue;
+            const uint32_t k = (uint32_t)std::min<uint64_t>(1 + i % 50, len);
+            rec.push_back((uint32_t)r); kk.push_back(k);
+            st.push_back((uint32_t)((i * 7919) % (len - k + 1))); en.push_back(st.back() + 3 * k);
+        }
+        const std::string out = std::string(path) + ".bed";
+        uint64_t bytes = 0;
+        for (int tsv = 0; tsv < 2; ++tsv) {
+            const std::string o = tsv ? std::string(path) + ".tsv" : out;
+            if (crf_write_rows(o.c_str(), 0, tsv, names, bases, offsets, rec.data(), st.data(), en.data(), kk.data(), rec.size(), &bytes) != CRF_OK) {
+                printf("crf_write_rows failed: %s\n", g_err);
+                bad = 1;
+            }
+        }
+        printf("%s: %zu rows written\n", path, rec.size());
     }
     crf_fasta_close(fa);
     return bad;

@@ -377,7 +377,7 @@ def test_gunzip_fuzz_under_sanitizers(tmp_path):
 
 
 def test_reader_and_packer_under_sanitizers(tmp_path, monkeypatch):
-    """tests/fuzz_reader.cpp: csrc/crf_fasta.h + csrc/crf_pack.h compiled without the CUDA runtime under ASan + UBSan.  Plain,
+    """tests/fuzz_reader.cpp: csrc/crf_fasta.h + csrc/crf_pack.h + csrc/crf_rows.h compiled without the CUDA runtime under ASan + UBSan.  Plain,
     gzip (several threads, small chunks), multi-member and BGZF files with ragged lines, CRLF, IUPAC letters, empty records and
     30 000 short reads: the harness checks the planes, the exotic list and the mask runs against the text base by base; its
     record table (name, length, FNV-1a of the bases) is compared here with the line-by-line reading of the same bytes."""
@@ -418,8 +418,23 @@ def test_reader_and_packer_under_sanitizers(tmp_path, monkeypatch):
     for name, raw in files.items():
         (tmp_path / name).write_bytes(raw)
     monkeypatch.setenv("CRF_GUNZIP_CHUNK_KB", "256")
+    monkeypatch.setenv("FUZZ_READER_ROWS", "150000")    # the row writer too (csrc/crf_rows.h), on several threads
     run = subprocess.run([exe] + [str(tmp_path / n) for n in files], capture_output=True, text=True, timeout=900)
     assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-4000:]
+    # the BED / TSV files the harness wrote for one input, against the same rows formatted here
+    recs = [(n, seq) for n, seq in _simple_fasta(files["iupac_crlf.fa"])]
+    bed, tsv, i = [], ["start_0based\tend\tmotif\n"], 0
+    while len(bed) < 150000:
+        name, seq = recs[i % len(recs)]
+        if seq:
+            k = min(1 + i % 50, len(seq))
+            st = (i * 7919) % (len(seq) - k + 1)
+            motif = seq[st:st + k].decode().upper()
+            bed.append(f"{name}\t{st}\t{st + 3 * k}\t{motif}\n")
+            tsv.append(f"{st}\t{st + 3 * k}\t{motif}\n")
+        i += 1
+    assert (tmp_path / "iupac_crlf.fa.bed").read_text() == "".join(bed)
+    assert (tmp_path / "iupac_crlf.fa.tsv").read_text() == "".join(tsv)
 
     def fnv(seq):
         h = 1469598103934665603
